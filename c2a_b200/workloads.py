@@ -1,0 +1,65 @@
+"""Synthetic pose batches for the BASELINE.json configs.
+
+A query is 48 float64: trans00, trans01 (object 1 begin/end), trans10, trans11 (object 2 begin/end),
+each R (9, row-major) + T (3) -- the four ``Transform*`` arguments of ``C2A_Solve``
+(/root/reference/C2A/C2A.h:23-35).
+"""
+import numpy as np
+
+BUNNY_RADIUS = 131.4   # max |v| of tri_models/bunny_noholes.tri
+KNOT_RADIUS = 198.0    # 60*3 + 18 for meshes.torus_knot defaults
+
+
+def quat_to_matrix(q):
+    """q: [n,4] (x,y,z,w), need not be normalised. Returns [n,9] row-major rotation matrices."""
+    q = q / np.linalg.norm(q, axis=1, keepdims=True)
+    x, y, z, w = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
+                  2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+                  2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], 1)
+    return R
+
+
+def axis_angle_to_matrix(axis, theta):
+    axis = axis / np.linalg.norm(axis, axis=1, keepdims=True)
+    h = 0.5 * theta
+    q = np.concatenate([axis * np.sin(h)[:, None], np.cos(h)[:, None]], 1)
+    return quat_to_matrix(q)
+
+
+def _matmul9(A, B):
+    return np.einsum("nij,njk->nik", A.reshape(-1, 3, 3), B.reshape(-1, 3, 3)).reshape(-1, 9)
+
+
+def approach_batch(n, seed, radius=BUNNY_RADIUS, max_turn=2.0):
+    """Configs 2/3: object 2 static (random rotation, T=0); object 1 starts 300 units out (in bunny
+    units; scaled by radius/BUNNY_RADIUS) along a random direction u and ends at s*u, s~U(-300,200),
+    while turning by theta~U(0,max_turn) about a random body axis."""
+    rng = np.random.default_rng(seed)
+    k = radius / BUNNY_RADIUS
+    u = rng.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    T0 = 300.0 * k * u
+    s = rng.uniform(-300.0, 200.0, size=n) * k
+    T1 = s[:, None] * u
+    R0 = quat_to_matrix(rng.normal(size=(n, 4)))
+    turn = axis_angle_to_matrix(rng.normal(size=(n, 3)), rng.uniform(0.0, max_turn, size=n))
+    R1 = _matmul9(R0, turn)
+    R2 = quat_to_matrix(rng.normal(size=(n, 4)))
+    Z = np.zeros((n, 3))
+    return np.ascontiguousarray(np.concatenate([R0, T0, R1, T1, R2, Z, R2, Z], 1))
+
+
+def demo_batch(R1f, T1f, R2f, T2f):
+    """Config 1: the 303 queries ``cb_display`` builds from torusknot1.ani / torusknot2.ani
+    (/root/reference/CCDDemo/mainTorusknot.cpp:216-266): object 1 moves from frame step1 to step2 of
+    file 1; object 2 keeps the rotation of frame ``iframe`` of file 2 with the translations of
+    frames step1 -> step2 of file 2."""
+    n = R1f.shape[0]
+    out = np.zeros((n, 48))
+    for i in range(n):
+        s1, s2 = (0, 1) if i < 101 else ((101, 102) if i < 202 else (202, 203))
+        out[i, 0:9] = R1f[s1]; out[i, 9:12] = T1f[s1]
+        out[i, 12:21] = R1f[s2]; out[i, 21:24] = T1f[s2]
+        out[i, 24:33] = R2f[i]; out[i, 33:36] = T2f[s1]
+        out[i, 36:45] = R2f[i]; out[i, 45:48] = T2f[s2]
+    return out

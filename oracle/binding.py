@@ -1,0 +1,188 @@
+"""ctypes bindings for the CPU oracle: the port (libc2a_oracle.so) and, when it was
+built in the container that has /root/reference, the compiled reference
+(oracle/_ref/libc2a_ref.so).  TEST INFRASTRUCTURE -- not imported by c2a_b200."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PORT_SO = os.path.join(_HERE, "libc2a_oracle.so")
+_REF_SO = os.path.join(_HERE, "_ref", "libc2a_ref.so")
+
+# mirrors struct orc_result (oracle/c2a_oracle.h)
+RESULT_DTYPE = np.dtype([
+    ("collisionfree", np.int32), ("numCA", np.int32), ("num_bv_tests", np.int32), ("num_tri_tests", np.int32),
+    ("toc", np.float64), ("distance", np.float64), ("mint", np.float64),
+    ("p1", np.float64, 3), ("p2", np.float64, 3), ("pose_toc", np.float64, 24),
+], align=True)
+OrcResult = RESULT_DTYPE
+
+
+class _Bvh(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("n_tris", C.c_int32),
+                ("R", C.c_void_p), ("Tr", C.c_void_p), ("l", C.c_void_p), ("r", C.c_void_p),
+                ("R_loc", C.c_void_p), ("ang_radius", C.c_void_p), ("first_child", C.c_void_p),
+                ("tris", C.c_void_p)]
+
+
+def build_oracle(verbose=False):
+    """make -C oracle: always builds the port; builds _ref only where /root/reference exists."""
+    out = subprocess.run(["make", "-C", _HERE, "-j8"], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + out.stdout + out.stderr)
+    if verbose:
+        print(out.stdout)
+
+
+def have_ref():
+    return os.path.exists(_REF_SO)
+
+
+_port = None
+_ref = None
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def bvh_struct(bvh):
+    """bvh: dict of contiguous numpy arrays (R, Tr, l, r, R_loc, ang_radius, first_child, tris)."""
+    s = _Bvh()
+    s.n_nodes = int(bvh["first_child"].shape[0])
+    s.n_tris = int(bvh["tris"].shape[0])
+    for k in ("R", "Tr", "l", "r", "R_loc", "ang_radius", "tris"):
+        a = bvh[k]
+        assert a.dtype == np.float64 and a.flags.c_contiguous, k
+        setattr(s, k, a.ctypes.data)
+    a = bvh["first_child"]
+    assert a.dtype == np.int32 and a.flags.c_contiguous
+    s.first_child = a.ctypes.data
+    s._keep = bvh
+    return s
+
+
+class _Port:
+    def __init__(self):
+        if not os.path.exists(_PORT_SO):
+            build_oracle()
+        self.lib = C.CDLL(_PORT_SO)
+        L = self.lib
+        L.orc_rect_dist.restype = C.c_double
+        L.orc_tri_distance.restype = C.c_double
+        L.orc_tri_dist.restype = C.c_double
+        L.orc_motion_bound_bv.restype = C.c_double
+        L.orc_motion_bound_leaf.restype = C.c_double
+
+    def solve_batch(self, bvhA, bvhB, poses, seedA=None, seedB=None, tol_d=1e-4, tol_t=1e-4, threads=1):
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 48)
+        n = poses.shape[0]
+        out = np.zeros(n, dtype=RESULT_DTYPE)
+        sA, sB = bvh_struct(bvhA), bvh_struct(bvhB)
+        seedA = None if seedA is None else np.ascontiguousarray(seedA, dtype=np.int32)
+        seedB = None if seedB is None else np.ascontiguousarray(seedB, dtype=np.int32)
+        self.lib.orc_solve_batch(C.byref(sA), C.byref(sB), _ptr(poses), C.c_int64(n),
+                                 _ptr(seedA) if seedA is not None else None,
+                                 _ptr(seedB) if seedB is not None else None,
+                                 C.c_double(tol_d), C.c_double(tol_t), _ptr(out), C.c_int32(threads))
+        return out
+
+    def rect_dist(self, Rab, Tab, a, b):
+        Rab = np.ascontiguousarray(Rab, np.float64); Tab = np.ascontiguousarray(Tab, np.float64)
+        a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64)
+        P = np.zeros(3); Q = np.zeros(3); S = np.full(3, np.nan)
+        d = self.lib.orc_rect_dist(_ptr(Rab), _ptr(Tab), _ptr(a), _ptr(b), _ptr(P), _ptr(Q), _ptr(S))
+        return d, P, Q, S
+
+    def tri_distance(self, R, T, t1, t2):
+        R = np.ascontiguousarray(R, np.float64); T = np.ascontiguousarray(T, np.float64)
+        t1 = np.ascontiguousarray(t1, np.float64); t2 = np.ascontiguousarray(t2, np.float64)
+        p = np.zeros(3); q = np.zeros(3)
+        d = self.lib.orc_tri_distance(_ptr(R), _ptr(T), _ptr(t1), _ptr(t2), _ptr(p), _ptr(q))
+        return d, p, q
+
+
+class RefModel:
+    """A C2A_Model built by the reference's own BeginModel/AddTri/EndModel."""
+
+    def __init__(self, lib, tris9, vidx=None):
+        tris9 = np.ascontiguousarray(tris9, dtype=np.float64).reshape(-1, 9)
+        self.lib = lib
+        vi = None if vidx is None else np.ascontiguousarray(vidx, dtype=np.int32)
+        lib.ref_model_build.restype = C.c_void_p
+        self.h = C.c_void_p(lib.ref_model_build(_ptr(tris9), _ptr(vi) if vi is not None else None,
+                                                C.c_int32(tris9.shape[0])))
+        nn, nt = C.c_int32(), C.c_int32()
+        lib.ref_model_counts(self.h, C.byref(nn), C.byref(nt))
+        self.n_nodes, self.n_tris = nn.value, nt.value
+
+    def export(self):
+        nn, nt = self.n_nodes, self.n_tris
+        b = {"R": np.zeros((nn, 9)), "Tr": np.zeros((nn, 3)), "l": np.zeros((nn, 2)), "r": np.zeros(nn),
+             "R_loc": np.zeros((nn, 9)), "ang_radius": np.zeros(nn), "first_child": np.zeros(nn, np.int32),
+             "tris": np.zeros((nt, 9)), "tri_ids": np.zeros(nt, np.int32)}
+        self.lib.ref_model_export(self.h, _ptr(b["R"]), _ptr(b["Tr"]), _ptr(b["l"]), _ptr(b["r"]), _ptr(b["R_loc"]),
+                                  _ptr(b["ang_radius"]), _ptr(b["first_child"]), _ptr(b["tris"]), _ptr(b["tri_ids"]))
+        return b
+
+
+class _Ref:
+    def __init__(self):
+        if not os.path.exists(_REF_SO):
+            raise RuntimeError("oracle/_ref/libc2a_ref.so not built (needs /root/reference; run make -C oracle)")
+        self.lib = C.CDLL(_REF_SO)
+        self.lib.ref_rect_dist.restype = C.c_double
+        self.lib.ref_tri_distance_intree.restype = C.c_double
+
+    def model(self, tris9, vidx=None):
+        return RefModel(self.lib, tris9, vidx)
+
+    def solve_batch(self, mA, mB, poses, seedA=None, seedB=None, mode=0, tol_d=1e-4, tol_t=1e-4, threads=1):
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 48)
+        n = poses.shape[0]
+        out = np.zeros(n, dtype=RESULT_DTYPE)
+        ncont = np.zeros(n, dtype=np.int32)
+        seedA = None if seedA is None else np.ascontiguousarray(seedA, dtype=np.int32)
+        seedB = None if seedB is None else np.ascontiguousarray(seedB, dtype=np.int32)
+        self.lib.ref_solve_batch(mA.h, mB.h, _ptr(poses), C.c_int64(n),
+                                 _ptr(seedA) if seedA is not None else None,
+                                 _ptr(seedB) if seedB is not None else None,
+                                 C.c_int32(mode), C.c_double(tol_d), C.c_double(tol_t), _ptr(out), _ptr(ncont),
+                                 C.c_int32(threads))
+        return (out, ncont) if mode == 1 else out
+
+    def rect_dist(self, Rab, Tab, a, b):
+        Rab = np.ascontiguousarray(Rab, np.float64); Tab = np.ascontiguousarray(Tab, np.float64)
+        a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64)
+        P = np.zeros(3); Q = np.zeros(3); S = np.full(3, np.nan)
+        d = self.lib.ref_rect_dist(_ptr(Rab), _ptr(Tab), _ptr(a), _ptr(b), _ptr(P), _ptr(Q), _ptr(S))
+        return d, P, Q, S
+
+    def tri_distance_intree(self, R, T, t1, t2):
+        R = np.ascontiguousarray(R, np.float64); T = np.ascontiguousarray(T, np.float64)
+        t1 = np.ascontiguousarray(t1, np.float64); t2 = np.ascontiguousarray(t2, np.float64)
+        p = np.zeros(3); q = np.zeros(3); col = C.c_int32(0)
+        d = self.lib.ref_tri_distance_intree(_ptr(R), _ptr(T), _ptr(t1), _ptr(t2), _ptr(p), _ptr(q), C.byref(col))
+        return d, p, q, col.value
+
+    def motion_probe(self, poses24, t, ang_radius, direction):
+        poses24 = np.ascontiguousarray(poses24, np.float64); direction = np.ascontiguousarray(direction, np.float64)
+        out = np.zeros(21)
+        self.lib.ref_motion_probe(_ptr(poses24), C.c_double(t), C.c_double(ang_radius), _ptr(direction), _ptr(out))
+        return out
+
+
+def port():
+    global _port
+    if _port is None:
+        _port = _Port()
+    return _port
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        _ref = _Ref()
+    return _ref

@@ -1,0 +1,828 @@
+// TEST INFRASTRUCTURE -- NOT PART OF THE PRODUCT.  See c2a_oracle.h.
+//
+// Scalar FP64 restatement of the reference's controlled-CA CCD path.  Paths are
+// relative to /root/reference.  Arithmetic order follows the reference
+// expression by expression (sums left to right, no FMA: build with
+// -ffp-contract=off) because the traversal's predicates are bit-sensitive.
+#include "c2a_oracle.h"
+
+#include <math.h>
+#include <string.h>
+#include <thread>
+#include <vector>
+
+namespace {
+
+// ---- 3-vector / 3x3 helpers (conventions of PQP MatVec.h as implied by the
+// reference's call sites, C2A/src/C2A_PQP.cpp:296-299,934-941) ------------------
+inline void v_sub(double r[3], const double a[3], const double b[3]) { r[0] = a[0] - b[0]; r[1] = a[1] - b[1]; r[2] = a[2] - b[2]; }
+inline void v_add(double r[3], const double a[3], const double b[3]) { r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2]; }
+inline void v_cpy(double r[3], const double a[3]) { r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; }
+inline void v_madd(double r[3], const double a[3], const double b[3], double s) { r[0] = a[0] + b[0] * s; r[1] = a[1] + b[1] * s; r[2] = a[2] + b[2] * s; }
+inline double v_dot(const double a[3], const double b[3]) { return (a[0] * b[0] + a[1] * b[1] + a[2] * b[2]); }
+inline void v_cross(double r[3], const double a[3], const double b[3])
+{
+  r[0] = a[1] * b[2] - a[2] * b[1];
+  r[1] = a[2] * b[0] - a[0] * b[2];
+  r[2] = a[0] * b[1] - a[1] * b[0];
+}
+inline double v_dist2(const double a[3], const double b[3])
+{
+  return ((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]));
+}
+inline double v_len(const double a[3]) { return sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); }
+inline void v_normalize(double a[3])
+{
+  double d = 1.0 / sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+  a[0] *= d; a[1] *= d; a[2] *= d;
+}
+// r = M v
+inline void m_v(double r[3], const double M[9], const double v[3])
+{
+  r[0] = (M[0] * v[0] + M[1] * v[1] + M[2] * v[2]);
+  r[1] = (M[3] * v[0] + M[4] * v[1] + M[5] * v[2]);
+  r[2] = (M[6] * v[0] + M[7] * v[1] + M[8] * v[2]);
+}
+// r = M v + t
+inline void m_v_p(double r[3], const double M[9], const double v[3], const double t[3])
+{
+  r[0] = (M[0] * v[0] + M[1] * v[1] + M[2] * v[2] + t[0]);
+  r[1] = (M[3] * v[0] + M[4] * v[1] + M[5] * v[2] + t[1]);
+  r[2] = (M[6] * v[0] + M[7] * v[1] + M[8] * v[2] + t[2]);
+}
+// r = M^T v
+inline void mt_v(double r[3], const double M[9], const double v[3])
+{
+  r[0] = (M[0] * v[0] + M[3] * v[1] + M[6] * v[2]);
+  r[1] = (M[1] * v[0] + M[4] * v[1] + M[7] * v[2]);
+  r[2] = (M[2] * v[0] + M[5] * v[1] + M[8] * v[2]);
+}
+// r = A B
+inline void m_m(double r[9], const double A[9], const double B[9])
+{
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      r[3 * i + j] = (A[3 * i + 0] * B[0 + j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j]);
+}
+// r = A^T B
+inline void mt_m(double r[9], const double A[9], const double B[9])
+{
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      r[3 * i + j] = (A[0 + i] * B[0 + j] + A[3 + i] * B[3 + j] + A[6 + i] * B[6 + j]);
+}
+
+// ---- rectangle-rectangle distance ------------------------------------------
+// C2A/C2A_RectDist.h:44-50
+inline void clamp_to(double &v, double lo, double hi) { if (v < lo) v = lo; else if (v > hi) v = hi; }
+
+// C2A/C2A_RectDist.h:81-111 (Lumelsky segment-segment parameters)
+inline void seg_params(double &t, double &u, double a, double b, double AdB, double AdT, double BdT)
+{
+  double denom = 1 - (AdB) * (AdB);
+  if (denom == 0) t = 0;
+  else { t = (AdT - BdT * AdB) / denom; clamp_to(t, 0, a); }
+  u = t * AdB - BdT;
+  if (u < 0) { u = 0; t = AdT; clamp_to(t, 0, a); }
+  else if (u > b) { u = b; t = u * AdB + AdT; clamp_to(t, 0, a); }
+}
+
+// C2A/C2A_RectDist.h:123-154
+inline bool in_voronoi(double a, double b, double AnB, double AnT, double AdB, double AdT, double BdT)
+{
+  if (((AnB < 0) ? -AnB : AnB) < 1e-7) return false;
+  double t, u, v;
+  u = -AnT / AnB; clamp_to(u, 0, b);
+  t = u * AdB + AdT; clamp_to(t, 0, a);
+  v = t * AdB - BdT;
+  if (AnB > 0) { if (v > (u + 1e-7)) return true; }
+  else { if (v < (u - 1e-7)) return true; }
+  return false;
+}
+
+struct RectCtx
+{
+  const double *R, *T, *a, *b;
+  double *P, *Q, *S;
+};
+
+// Closest points once an edge pair (A-edge along axis ea on the upper/lower side
+// ua; B-edge along axis eb, side ub) is accepted: the P/Q/S block that follows
+// each ClosestPoint call in C2A/C2A_RectDist.h:233-848.
+inline double rect_edge_finish(const RectCtx &c, int ea, bool ua, int eb, bool ub, double t, double u)
+{
+  const int oa = 1 - ea, ob = 1 - eb;
+  c.P[ea] = t; c.P[oa] = ua ? c.a[oa] : 0; c.P[2] = 0;
+  for (int k = 0; k < 3; k++)
+  {
+    if (ub) c.Q[k] = c.T[k] + c.R[3 * k + ob] * c.b[ob] + c.R[3 * k + eb] * u;
+    else c.Q[k] = c.T[k] + c.R[3 * k + eb] * u;
+  }
+  c.S[0] = c.Q[0] - c.P[0]; c.S[1] = c.Q[1] - c.P[1]; c.S[2] = c.Q[2] - c.P[2];
+  return sqrt(v_dot(c.S, c.S));
+}
+
+}  // namespace
+
+// C2A/C2A_RectDist.h:157-934 (C2ARectDist).  S = Q - P is left untouched when
+// both face separations are negative (the reference does the same).
+extern "C" double orc_rect_dist(const double Rab[9], const double Tab[3], const double a[2],
+                                const double b[2], double P[3], double Q[3], double S[3])
+{
+  RectCtx cx = {Rab, Tab, a, b, P, Q, S};
+  const double A0B0 = Rab[0], A0B1 = Rab[1], A1B0 = Rab[3], A1B1 = Rab[4];
+  const double aA0B0 = a[0] * A0B0, aA0B1 = a[0] * A0B1, aA1B0 = a[1] * A1B0, aA1B1 = a[1] * A1B1;
+  const double bA0B0 = b[0] * A0B0, bA1B0 = b[0] * A1B0, bA0B1 = b[1] * A0B1, bA1B1 = b[1] * A1B1;
+  double Tba[3];
+  mt_v(Tba, Rab, Tab);
+  double t, u;
+
+#define RD_EDGE(c1, c2, trivA, ivA, trivB, ivB, ea, ua, eb, ub, la, lb, AdB, AdT, BdT) \
+  if ((c1) && (c2))                                                                    \
+  {                                                                                    \
+    if (((trivA) || in_voronoi ivA) && ((trivB) || in_voronoi ivB))                    \
+    {                                                                                  \
+      seg_params(t, u, la, lb, AdB, AdT, BdT);                                         \
+      return rect_edge_finish(cx, ea, ua, eb, ub, t, u);                               \
+    }                                                                                  \
+  }
+
+  // --- A1 edges against B1 edges: extents along B0 (x in B) and A0 (x in A) -- :193-360
+  double ALL_x = -Tba[0], ALU_x = ALL_x + aA1B0, AUL_x = ALL_x + aA0B0, AUU_x = ALU_x + aA0B0;
+  double LA1_lx, LA1_ux, UA1_lx, UA1_ux;
+  if (ALL_x < ALU_x) { LA1_lx = ALL_x; LA1_ux = ALU_x; UA1_lx = AUL_x; UA1_ux = AUU_x; }
+  else { LA1_lx = ALU_x; LA1_ux = ALL_x; UA1_lx = AUU_x; UA1_ux = AUL_x; }
+  double BLL_x = Tab[0], BLU_x = BLL_x + bA0B1, BUL_x = BLL_x + bA0B0, BUU_x = BLU_x + bA0B0;
+  double LB1_lx, LB1_ux, UB1_lx, UB1_ux;
+  if (BLL_x < BLU_x) { LB1_lx = BLL_x; LB1_ux = BLU_x; UB1_lx = BUL_x; UB1_ux = BUU_x; }
+  else { LB1_lx = BLU_x; LB1_ux = BLL_x; UB1_lx = BUU_x; UB1_ux = BUL_x; }
+
+  RD_EDGE(UA1_ux > b[0], UB1_ux > a[0],
+          UA1_lx > b[0], (b[1], a[1], A1B0, aA0B0 - b[0] - Tba[0], A1B1, aA0B1 - Tba[1], -Tab[1] - bA1B0),
+          UB1_lx > a[0], (a[1], b[1], A0B1, Tab[0] + bA0B0 - a[0], A1B1, Tab[1] + bA1B0, Tba[1] - aA0B1),
+          1, true, 1, true, a[1], b[1], A1B1, Tab[1] + bA1B0, Tba[1] - aA0B1)
+  RD_EDGE(UA1_lx < 0, LB1_ux > a[0],
+          UA1_ux < 0, (b[1], a[1], -A1B0, Tba[0] - aA0B0, A1B1, aA0B1 - Tba[1], -Tab[1]),
+          LB1_lx > a[0], (a[1], b[1], A0B1, Tab[0] - a[0], A1B1, Tab[1], Tba[1] - aA0B1),
+          1, true, 1, false, a[1], b[1], A1B1, Tab[1], Tba[1] - aA0B1)
+  RD_EDGE(LA1_ux > b[0], UB1_lx < 0,
+          LA1_lx > b[0], (b[1], a[1], A1B0, -Tba[0] - b[0], A1B1, -Tba[1], -Tab[1] - bA1B0),
+          UB1_ux < 0, (a[1], b[1], -A0B1, -Tab[0] - bA0B0, A1B1, Tab[1] + bA1B0, Tba[1]),
+          1, false, 1, true, a[1], b[1], A1B1, Tab[1] + bA1B0, Tba[1])
+  RD_EDGE(LA1_lx < 0, LB1_lx < 0,
+          LA1_ux < 0, (b[1], a[1], -A1B0, Tba[0], A1B1, -Tba[1], -Tab[1]),
+          LB1_ux < 0, (a[1], b[1], -A0B1, -Tab[0], A1B1, Tab[1], Tba[1]),
+          1, false, 1, false, a[1], b[1], A1B1, Tab[1], Tba[1])
+
+  // --- A1 edges against B0 edges: extents along B1 (y in B) and A0 -- :362-543
+  double ALL_y = -Tba[1], ALU_y = ALL_y + aA1B1, AUL_y = ALL_y + aA0B1, AUU_y = ALU_y + aA0B1;
+  double LA1_ly, LA1_uy, UA1_ly, UA1_uy;
+  if (ALL_y < ALU_y) { LA1_ly = ALL_y; LA1_uy = ALU_y; UA1_ly = AUL_y; UA1_uy = AUU_y; }
+  else { LA1_ly = ALU_y; LA1_uy = ALL_y; UA1_ly = AUU_y; UA1_uy = AUL_y; }
+  double LB0_lx, LB0_ux, UB0_lx, UB0_ux;
+  if (BLL_x < BUL_x) { LB0_lx = BLL_x; LB0_ux = BUL_x; UB0_lx = BLU_x; UB0_ux = BUU_x; }
+  else { LB0_lx = BUL_x; LB0_ux = BLL_x; UB0_lx = BUU_x; UB0_ux = BLU_x; }
+
+  RD_EDGE(UA1_uy > b[1], UB0_ux > a[0],
+          UA1_ly > b[1], (b[0], a[1], A1B1, aA0B1 - Tba[1] - b[1], A1B0, aA0B0 - Tba[0], -Tab[1] - bA1B1),
+          UB0_lx > a[0], (a[1], b[0], A0B0, Tab[0] - a[0] + bA0B1, A1B0, Tab[1] + bA1B1, Tba[0] - aA0B0),
+          1, true, 0, true, a[1], b[0], A1B0, Tab[1] + bA1B1, Tba[0] - aA0B0)
+  RD_EDGE(UA1_ly < 0, LB0_ux > a[0],
+          UA1_uy < 0, (b[0], a[1], -A1B1, Tba[1] - aA0B1, A1B0, aA0B0 - Tba[0], -Tab[1]),
+          LB0_lx > a[0], (a[1], b[0], A0B0, Tab[0] - a[0], A1B0, Tab[1], Tba[0] - aA0B0),
+          1, true, 0, false, a[1], b[0], A1B0, Tab[1], Tba[0] - aA0B0)
+  RD_EDGE(LA1_uy > b[1], UB0_lx < 0,
+          LA1_ly > b[1], (b[0], a[1], A1B1, -Tba[1] - b[1], A1B0, -Tba[0], -Tab[1] - bA1B1),
+          UB0_ux < 0, (a[1], b[0], -A0B0, -Tab[0] - bA0B1, A1B0, Tab[1] + bA1B1, Tba[0]),
+          1, false, 0, true, a[1], b[0], A1B0, Tab[1] + bA1B1, Tba[0])
+  RD_EDGE(LA1_ly < 0, LB0_lx < 0,
+          LA1_uy < 0, (b[0], a[1], -A1B1, Tba[1], A1B0, -Tba[0], -Tab[1]),
+          LB0_ux < 0, (a[1], b[0], -A0B0, -Tab[0], A1B0, Tab[1], Tba[0]),
+          1, false, 0, false, a[1], b[0], A1B0, Tab[1], Tba[0])
+
+  // --- A0 edges against B1 edges: extents along B0 and A1 (y in A) -- :545-725
+  double BLL_y = Tab[1], BLU_y = BLL_y + bA1B1, BUL_y = BLL_y + bA1B0, BUU_y = BLU_y + bA1B0;
+  double LA0_lx, LA0_ux, UA0_lx, UA0_ux;
+  if (ALL_x < AUL_x) { LA0_lx = ALL_x; LA0_ux = AUL_x; UA0_lx = ALU_x; UA0_ux = AUU_x; }
+  else { LA0_lx = AUL_x; LA0_ux = ALL_x; UA0_lx = AUU_x; UA0_ux = ALU_x; }
+  double LB1_ly, LB1_uy, UB1_ly, UB1_uy;
+  if (BLL_y < BLU_y) { LB1_ly = BLL_y; LB1_uy = BLU_y; UB1_ly = BUL_y; UB1_uy = BUU_y; }
+  else { LB1_ly = BLU_y; LB1_uy = BLL_y; UB1_ly = BUU_y; UB1_uy = BUL_y; }
+
+  RD_EDGE(UA0_ux > b[0], UB1_uy > a[1],
+          UA0_lx > b[0], (b[1], a[0], A0B0, aA1B0 - Tba[0] - b[0], A0B1, aA1B1 - Tba[1], -Tab[0] - bA0B0),
+          UB1_ly > a[1], (a[0], b[1], A1B1, Tab[1] - a[1] + bA1B0, A0B1, Tab[0] + bA0B0, Tba[1] - aA1B1),
+          0, true, 1, true, a[0], b[1], A0B1, Tab[0] + bA0B0, Tba[1] - aA1B1)
+  RD_EDGE(UA0_lx < 0, LB1_uy > a[1],
+          UA0_ux < 0, (b[1], a[0], -A0B0, Tba[0] - aA1B0, A0B1, aA1B1 - Tba[1], -Tab[0]),
+          LB1_ly > a[1], (a[0], b[1], A1B1, Tab[1] - a[1], A0B1, Tab[0], Tba[1] - aA1B1),
+          0, true, 1, false, a[0], b[1], A0B1, Tab[0], Tba[1] - aA1B1)
+  RD_EDGE(LA0_ux > b[0], UB1_ly < 0,
+          LA0_lx > b[0], (b[1], a[0], A0B0, -b[0] - Tba[0], A0B1, -Tba[1], -bA0B0 - Tab[0]),
+          UB1_uy < 0, (a[0], b[1], -A1B1, -Tab[1] - bA1B0, A0B1, Tab[0] + bA0B0, Tba[1]),
+          0, false, 1, true, a[0], b[1], A0B1, Tab[0] + bA0B0, Tba[1])
+  RD_EDGE(LA0_lx < 0, LB1_ly < 0,
+          LA0_ux < 0, (b[1], a[0], -A0B0, Tba[0], A0B1, -Tba[1], -Tab[0]),
+          LB1_uy < 0, (a[0], b[1], -A1B1, -Tab[1], A0B1, Tab[0], Tba[1]),
+          0, false, 1, false, a[0], b[1], A0B1, Tab[0], Tba[1])
+
+  // --- A0 edges against B0 edges: extents along B1 and A1 -- :727-848
+  double LA0_ly, LA0_uy, UA0_ly, UA0_uy;
+  if (ALL_y < AUL_y) { LA0_ly = ALL_y; LA0_uy = AUL_y; UA0_ly = ALU_y; UA0_uy = AUU_y; }
+  else { LA0_ly = AUL_y; LA0_uy = ALL_y; UA0_ly = AUU_y; UA0_uy = ALU_y; }
+  double LB0_ly, LB0_uy, UB0_ly, UB0_uy;
+  if (BLL_y < BUL_y) { LB0_ly = BLL_y; LB0_uy = BUL_y; UB0_ly = BLU_y; UB0_uy = BUU_y; }
+  else { LB0_ly = BUL_y; LB0_uy = BLL_y; UB0_ly = BUU_y; UB0_uy = BLU_y; }
+
+  RD_EDGE(UA0_uy > b[1], UB0_uy > a[1],
+          UA0_ly > b[1], (b[0], a[0], A0B1, aA1B1 - Tba[1] - b[1], A0B0, aA1B0 - Tba[0], -Tab[0] - bA0B1),
+          UB0_ly > a[1], (a[0], b[0], A1B0, Tab[1] - a[1] + bA1B1, A0B0, Tab[0] + bA0B1, Tba[0] - aA1B0),
+          0, true, 0, true, a[0], b[0], A0B0, Tab[0] + bA0B1, Tba[0] - aA1B0)
+  RD_EDGE(UA0_ly < 0, LB0_uy > a[1],
+          UA0_uy < 0, (b[0], a[0], -A0B1, Tba[1] - aA1B1, A0B0, aA1B0 - Tba[0], -Tab[0]),
+          LB0_ly > a[1], (a[0], b[0], A1B0, Tab[1] - a[1], A0B0, Tab[0], Tba[0] - aA1B0),
+          0, true, 0, false, a[0], b[0], A0B0, Tab[0], Tba[0] - aA1B0)
+  RD_EDGE(LA0_uy > b[1], UB0_ly < 0,
+          LA0_ly > b[1], (b[0], a[0], A0B1, -Tba[1] - b[1], A0B0, -Tba[0], -Tab[0] - bA0B1),
+          UB0_uy < 0, (a[0], b[0], -A1B0, -Tab[1] - bA1B1, A0B0, Tab[0] + bA0B1, Tba[0]),
+          0, false, 0, true, a[0], b[0], A0B0, Tab[0] + bA0B1, Tba[0])
+  RD_EDGE(LA0_ly < 0, LB0_ly < 0,
+          LA0_uy < 0, (b[0], a[0], -A0B1, Tba[1], A0B0, -Tba[0], -Tab[0]),
+          LB0_uy < 0, (a[0], b[0], -A1B0, -Tab[1], A0B0, Tab[0], Tba[0]),
+          0, false, 0, false, a[0], b[0], A0B0, Tab[0], Tba[0])
+#undef RD_EDGE
+
+  // --- no edge pair: separation along the two face normals -- :850-933
+  double sep1, sep2;
+  if (Tab[2] > 0.0)
+  {
+    sep1 = Tab[2];
+    if (Rab[6] < 0.0) sep1 += b[0] * Rab[6];
+    if (Rab[7] < 0.0) sep1 += b[1] * Rab[7];
+  }
+  else
+  {
+    sep1 = -Tab[2];
+    if (Rab[6] > 0.0) sep1 -= b[0] * Rab[6];
+    if (Rab[7] > 0.0) sep1 -= b[1] * Rab[7];
+  }
+  if (Tba[2] < 0)
+  {
+    sep2 = -Tba[2];
+    if (Rab[2] < 0.0) sep2 += a[0] * Rab[2];
+    if (Rab[5] < 0.0) sep2 += a[1] * Rab[5];
+  }
+  else
+  {
+    sep2 = Tba[2];
+    if (Rab[2] > 0.0) sep2 -= a[0] * Rab[2];
+    if (Rab[5] > 0.0) sep2 -= a[1] * Rab[5];
+  }
+  if (sep1 >= sep2 && sep1 >= 0)
+  {
+    P[0] = P[1] = P[2] = 0.0;
+    Q[0] = Q[1] = 0.0;
+    Q[2] = (Tab[2] > 0.0) ? sep1 : -sep1;
+    S[0] = Q[0] - P[0]; S[1] = Q[1] - P[1]; S[2] = Q[2] - P[2];
+  }
+  if (sep2 >= sep1 && sep2 >= 0)
+  {
+    Q[0] = Tab[0]; Q[1] = Tab[1]; Q[2] = Tab[2];
+    if (Tba[2] < 0)
+    {
+      P[0] = Rab[2] * sep2 + Tab[0]; P[1] = Rab[5] * sep2 + Tab[1]; P[2] = Rab[8] * sep2 + Tab[2];
+    }
+    else
+    {
+      P[0] = -Rab[2] * sep2 + Tab[0]; P[1] = -Rab[5] * sep2 + Tab[1]; P[2] = -Rab[8] * sep2 + Tab[2];
+    }
+    S[0] = Q[0] - P[0]; S[1] = Q[1] - P[1]; S[2] = Q[2] - P[2];
+  }
+  double sep = (sep1 > sep2 ? sep1 : sep2);
+  return (sep > 0 ? sep : 0);
+}
+
+// ---- triangle-triangle distance --------------------------------------------
+// PQP SegPoints, as the reference's in-tree copy "ClosestPoints", C2A/src/C2A.cpp:59-163.
+extern "C" void orc_seg_points(double VEC[3], double X[3], double Y[3], const double P[3],
+                               const double A[3], const double Q[3], const double B[3])
+{
+  double T[3], TMP[3];
+  v_sub(T, Q, P);
+  const double AdA = v_dot(A, A), BdB = v_dot(B, B), AdB = v_dot(A, B);
+  const double AdT = v_dot(A, T), BdT = v_dot(B, T);
+  double denom = AdA * BdB - AdB * AdB;
+  double t = (AdT * BdB - BdT * AdB) / denom;
+  if ((t < 0) || isnan(t)) t = 0; else if (t > 1) t = 1;
+  double u = (t * AdB - BdT) / BdB;
+
+  if ((u <= 0) || isnan(u))
+  {
+    v_cpy(Y, Q);
+    t = AdT / AdA;
+    if ((t <= 0) || isnan(t)) { v_cpy(X, P); v_sub(VEC, Q, P); }
+    else if (t >= 1) { v_add(X, P, A); v_sub(VEC, Q, X); }
+    else { v_madd(X, P, A, t); v_cross(TMP, T, A); v_cross(VEC, A, TMP); }
+  }
+  else if (u >= 1)
+  {
+    v_add(Y, Q, B);
+    t = (AdB + AdT) / AdA;
+    if ((t <= 0) || isnan(t)) { v_cpy(X, P); v_sub(VEC, Y, P); }
+    else if (t >= 1) { v_add(X, P, A); v_sub(VEC, Y, X); }
+    else { v_madd(X, P, A, t); v_sub(T, Y, P); v_cross(TMP, T, A); v_cross(VEC, A, TMP); }
+  }
+  else
+  {
+    v_madd(Y, Q, B, u);
+    if ((t <= 0) || isnan(t)) { v_cpy(X, P); v_cross(TMP, T, B); v_cross(VEC, B, TMP); }
+    else if (t >= 1) { v_add(X, P, A); v_sub(T, Q, X); v_cross(TMP, T, B); v_cross(VEC, B, TMP); }
+    else
+    {
+      v_madd(X, P, A, t);
+      v_cross(VEC, A, B);
+      if (v_dot(VEC, T) < 0) { VEC[0] = VEC[0] * -1; VEC[1] = VEC[1] * -1; VEC[2] = VEC[2] * -1; }
+    }
+  }
+}
+
+namespace {
+// vertex-of-T against face-of-S test shared by both orientations, C2A/src/C2A.cpp:282-339 / :346-391.
+// Returns true and fills (onFace, vertex) when the closest pair is (face of F, vertex of G).
+inline bool face_vertex_case(const double F[9], const double Fv[9], const double G[9],
+                             int &shown_disjoint, double onFace[3], double vertex[3])
+{
+  double n[3], V[3], Z[3];
+  v_cross(n, &Fv[0], &Fv[3]);
+  double nl = v_dot(n, n);
+  if (!(nl > 1e-15)) return false;
+  double proj[3];
+  v_sub(V, &F[0], &G[0]); proj[0] = v_dot(V, n);
+  v_sub(V, &F[0], &G[3]); proj[1] = v_dot(V, n);
+  v_sub(V, &F[0], &G[6]); proj[2] = v_dot(V, n);
+  int point = -1;
+  if ((proj[0] > 0) && (proj[1] > 0) && (proj[2] > 0))
+  {
+    if (proj[0] < proj[1]) point = 0; else point = 1;
+    if (proj[2] < proj[point]) point = 2;
+  }
+  else if ((proj[0] < 0) && (proj[1] < 0) && (proj[2] < 0))
+  {
+    if (proj[0] > proj[1]) point = 0; else point = 1;
+    if (proj[2] > proj[point]) point = 2;
+  }
+  if (point < 0) return false;
+  shown_disjoint = 1;
+  const double *g = &G[3 * point];
+  for (int e = 0; e < 3; e++)
+  {
+    v_sub(V, g, &F[3 * e]);
+    v_cross(Z, n, &Fv[3 * e]);
+    if (!(v_dot(V, Z) > 0)) return false;
+  }
+  v_madd(onFace, g, n, proj[point] / nl);
+  v_cpy(vertex, g);
+  return true;
+}
+}  // namespace
+
+// PQP TriDist, as the reference's in-tree copy C2A/src/C2A.cpp:165-405 minus the
+// contact-feature writes; overlap returns 0 (P,Q then hold the last edge pair).
+extern "C" double orc_tri_dist(double P[3], double Q[3], const double S[9], const double T[9])
+{
+  double Sv[9], Tv[9], VEC[3], V[3], Z[3];
+  v_sub(&Sv[0], &S[3], &S[0]); v_sub(&Sv[3], &S[6], &S[3]); v_sub(&Sv[6], &S[0], &S[6]);
+  v_sub(&Tv[0], &T[3], &T[0]); v_sub(&Tv[3], &T[6], &T[3]); v_sub(&Tv[6], &T[0], &T[6]);
+
+  double minP[3], minQ[3], mindd;
+  int shown_disjoint = 0;
+  mindd = v_dist2(&S[0], &T[0]) + 1;
+
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+    {
+      orc_seg_points(VEC, P, Q, &S[3 * i], &Sv[3 * i], &T[3 * j], &Tv[3 * j]);
+      v_sub(V, Q, P);
+      double dd = v_dot(V, V);
+      if (dd <= mindd)
+      {
+        v_cpy(minP, P); v_cpy(minQ, Q); mindd = dd;
+        v_sub(Z, &S[3 * ((i + 2) % 3)], P);
+        double a = v_dot(Z, VEC);
+        v_sub(Z, &T[3 * ((j + 2) % 3)], Q);
+        double b = v_dot(Z, VEC);
+        if ((a <= 0) && (b >= 0)) return sqrt(dd);
+        double p = v_dot(V, VEC);
+        if (a < 0) a = 0;
+        if (b > 0) b = 0;
+        if ((p - a + b) > 0) shown_disjoint = 1;
+      }
+    }
+
+  double onFace[3], vert[3];
+  if (face_vertex_case(S, Sv, T, shown_disjoint, onFace, vert))
+  {
+    v_cpy(P, onFace); v_cpy(Q, vert);
+    return sqrt(v_dist2(P, Q));
+  }
+  if (face_vertex_case(T, Tv, S, shown_disjoint, onFace, vert))
+  {
+    v_cpy(P, vert); v_cpy(Q, onFace);
+    return sqrt(v_dist2(P, Q));
+  }
+  if (shown_disjoint) { v_cpy(P, minP); v_cpy(Q, minQ); return sqrt(mindd); }
+  return 0;
+}
+
+// PQP TriDistance (call sites C2A/src/C2A.cpp:1148,1916); same shape as C2A/src/C2A.cpp:408-424.
+extern "C" double orc_tri_distance(const double R[9], const double T[3], const double t1[9],
+                                   const double t2[9], double p[3], double q[3])
+{
+  double tri2[9];
+  m_v_p(&tri2[0], R, &t2[0], T);
+  m_v_p(&tri2[3], R, &t2[3], T);
+  m_v_p(&tri2[6], R, &t2[6], T);
+  return orc_tri_dist(p, q, t1, tri2);
+}
+
+// ---- motion ------------------------------------------------------------------
+namespace {
+// Matrix3x3::Quaternion_, C2A/LinearMath.h:759-793.  q = (x,y,z,w).
+inline void quat_from_matrix(double q[4], const double val[9])
+{
+  double trace = val[0] + val[4] + val[8];
+  if (trace > 0.0)
+  {
+    double s = sqrt(trace + 1.0);
+    q[3] = s * 0.5;
+    s = 0.5 / s;
+    q[0] = (val[7] - val[5]) * s;
+    q[1] = (val[2] - val[6]) * s;
+    q[2] = (val[3] - val[1]) * s;
+  }
+  else
+  {
+    int i = val[0] < val[4] ? (val[4] < val[8] ? 2 : 1) : (val[0] < val[8] ? 2 : 0);
+    int j = (i + 1) % 3, k = (i + 2) % 3;
+    double s = sqrt(val[i * 3 + i] - val[j * 3 + j] - val[k * 3 + k] + 1.0);
+    q[i] = s * 0.5;
+    s = 0.5 / s;
+    q[3] = (val[k * 3 + j] - val[j * 3 + k]) * s;
+    q[j] = (val[j * 3 + i] + val[i * 3 + j]) * s;
+    q[k] = (val[k * 3 + i] + val[i * 3 + k]) * s;
+  }
+}
+// Quaternion operator%, C2A/LinearMath.h:1018-1025 (Hamilton product).
+inline void quat_mul(double r[4], const double a[4], const double b[4])
+{
+  r[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+  r[1] = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+  r[2] = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+  r[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+}
+// Matrix3x3::Set_Value(Quaternion), C2A/LinearMath.h:809-831.
+inline void matrix_from_quat(double v[9], const double q[4])
+{
+  double d = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  double s = 2.0 / d;
+  double xs = q[0] * s, ys = q[1] * s, zs = q[2] * s;
+  double wx = q[3] * xs, wy = q[3] * ys, wz = q[3] * zs;
+  double xx = q[0] * xs, xy = q[0] * ys, xz = q[0] * zs;
+  double yy = q[1] * ys, yz = q[1] * zs, zz = q[2] * zs;
+  v[0] = 1.0 - (yy + zz); v[1] = xy - wz; v[2] = xz + wy;
+  v[3] = xy + wz; v[4] = 1.0 - (xx + zz); v[5] = yz - wx;
+  v[6] = xz - wy; v[7] = yz + wx; v[8] = 1.0 - (xx + yy);
+}
+}  // namespace
+
+// CInterpMotion ctor (C2A/src/InterpMotion.cpp:148-168) + CInterpMotion_Linear ctor
+// (:494-502) -> velocity (:486-491) -> LinearAngularVelocity (:228-270).
+extern "C" void orc_motion_init(orc_motion *m, const double R0[9], const double T0[3],
+                                const double R1[9], const double T1[3])
+{
+  memcpy(m->Rs, R0, sizeof(double) * 9); memcpy(m->Ts, T0, sizeof(double) * 3);
+  memcpy(m->Re, R1, sizeof(double) * 9); memcpy(m->Te, T1, sizeof(double) * 3);
+  memcpy(m->Rc, R0, sizeof(double) * 9); memcpy(m->Tc, T0, sizeof(double) * 3);
+  v_sub(m->cv, T1, T0);
+
+  double qs[4], qt[4], q0[4], qd[4];
+  quat_from_matrix(qs, m->Rs);
+  quat_from_matrix(qt, m->Re);
+  q0[0] = -qs[0]; q0[1] = -qs[1]; q0[2] = -qs[2]; q0[3] = qs[3];
+  quat_mul(qd, q0, qt);
+
+  double s = 1 < qd[3] ? 1 : qd[3];
+  double sign = s < 0 ? -1 : 1;
+  double a = (fabs(s - 1) <= 1e-40 || fabs(s + 1) <= 1e-40) ? (2 * sign)
+                                                            : (sign * acos(2 * s * s - 1) / sqrt(1 - s * s));
+  double tangent[3] = {a * qd[0], a * qd[1], a * qd[2]};
+  m->axis[0] = tangent[0]; m->axis[1] = tangent[1]; m->axis[2] = tangent[2];
+  m->ang_vel = v_len(tangent);
+  double len = m->axis[0] * m->axis[0] + m->axis[1] * m->axis[1] + m->axis[2] * m->axis[2];
+  if (len < 0.00000001f) { m->axis[0] = 1.f; m->axis[1] = 0.f; m->axis[2] = 0.f; }
+  else
+  {
+    const double inv = 1.0 / sqrt(len);
+    m->axis[0] *= inv; m->axis[1] *= inv; m->axis[2] *= inv;
+  }
+}
+
+// CInterpMotion_Linear::integrate (C2A/src/InterpMotion.cpp:516-568) with
+// AbsoluteRt / DeltaRt (:273-287): mutates the current transform.
+extern "C" void orc_motion_integrate(orc_motion *m, double t_in, double q_out[4])
+{
+  double dt = t_in;
+  if (dt > 1) dt = 1;
+  m->Tc[0] = m->Ts[0] + dt * m->cv[0];
+  m->Tc[1] = m->Ts[1] + dt * m->cv[1];
+  m->Tc[2] = m->Ts[2] + dt * m->cv[2];
+  double ang = 0.5f * m->ang_vel * dt;
+  double sn = sin(ang);
+  double drt[4] = {sn * m->axis[0], sn * m->axis[1], sn * m->axis[2], cos(ang)};
+  double q0[4], q[4];
+  quat_from_matrix(q0, m->Rs);  // re-derived on every call, InterpMotion.cpp:284
+  quat_mul(q, q0, drt);
+  matrix_from_quat(m->Rc, q);
+  if (q_out) { q_out[0] = q[0]; q_out[1] = q[1]; q_out[2] = q[2]; q_out[3] = q[3]; }
+}
+
+// CInterpMotion_Linear::computeTOC_MotionBound, C2A/src/InterpMotion.cpp:831-881.
+// Normalises N in place, like the reference.
+extern "C" double orc_motion_bound_bv(const orc_motion *m, double ang_radius, double N[3])
+{
+  double cross[3];
+  v_normalize(N);
+  v_cross(cross, m->axis, N);
+  double w_max = (ang_radius)*v_len(cross) * m->ang_vel;
+  double v_max = v_dot(m->cv, N);
+  if (v_max < 0) v_max = 0;
+  double path_max = v_max + w_max;
+  if (path_max <= 0) path_max = 1e-30;
+  return path_max;
+}
+
+// CInterpMotion_Linear::computeTOC(d, r1, S), C2A/src/InterpMotion.cpp:746-828.
+extern "C" double orc_motion_bound_leaf(const orc_motion *m, double ang_radius, double S[3])
+{
+  double v_max, w_max;
+  v_normalize(S);
+  if (m->ang_vel == 0)
+  {
+    w_max = 0;
+    v_max = v_dot(m->cv, S);
+    if (v_max < 0) v_max = 0;
+  }
+  else
+  {
+    double cwc[3] = {m->axis[0], m->axis[1], m->axis[2]}, cross[3];
+    cwc[0] *= m->ang_vel; cwc[1] *= m->ang_vel; cwc[2] *= m->ang_vel;
+    v_cross(cross, cwc, S);
+    w_max = ang_radius * v_len(cross);
+    v_max = v_dot(m->cv, S);
+    if (v_max < 0) v_max = 0;
+  }
+  double path_max = w_max + v_max;
+  if (path_max == 0) path_max = 1e-30;
+  return path_max;
+}
+
+// ---- traversal + CA loop -----------------------------------------------------
+namespace {
+struct Step
+{
+  const orc_bvh *A, *B;
+  const orc_motion *m1, *m2;
+  double Rrel[9], Trel[3];  // res->R, res->T
+  double abs_err, rel_err, upbound;
+  double distance, mint;
+  double p1[3], p2[3];
+  int num_bv_tests, num_tri_tests;
+};
+
+inline double bv_size(const orc_bvh *M, int n)
+{
+  const double *l = &M->l[2 * n];
+  return (sqrt(l[0] * l[0] + l[1] * l[1]) + 2 * M->r[n]);  // PQP BV::GetSize, RSS form
+}
+
+// C2A_BV_Distance, C2A/src/C2A_BV.cpp:666-675
+inline double bv_distance(const double R[9], const double T[3], const orc_bvh *A, int a, const orc_bvh *B,
+                          int b, double S[3])
+{
+  double P[3], Q[3];
+  double dist = orc_rect_dist(R, T, &A->l[2 * a], &B->l[2 * b], P, Q, S);
+  dist -= (A->r[a] + B->r[b]);
+  return (dist < 0.0) ? 0.0 : dist;
+}
+
+// TOCStepRecurse_Dis, C2A/src/C2A.cpp:1114-1354
+void toc_recurse(Step &st, const double R[9], const double T[3], int b1, int b2)
+{
+  const orc_bvh *A = st.A, *B = st.B;
+  const int l1 = A->first_child[b1] < 0, l2 = B->first_child[b2] < 0;
+  const double *r1 = st.m1->Rc, *tt1 = st.m1->Tc;
+
+  if (l1 && l2)
+  {
+    double p[3], q[3];
+    const double *t1 = &A->tris[9 * (-A->first_child[b1] - 1)];
+    const double *t2 = &B->tris[9 * (-B->first_child[b2] - 1)];
+    double dTri = orc_tri_distance(st.Rrel, st.Trel, t1, t2, p, q);
+    if (dTri <= st.distance)
+    {
+      st.distance = dTri;
+      double w1[3], w2[3], S1[3], S2[3], tmp[3];
+      m_v(tmp, r1, p); v_add(w1, tmp, tt1);
+      m_v(tmp, r1, q); v_add(w2, tmp, tt1);
+      v_sub(S1, w2, w1);
+      S2[0] = S1[0] * -1; S2[1] = S1[1] * -1; S2[2] = S1[2] * -1;
+      v_cpy(st.p1, p); v_cpy(st.p2, q);
+      double mb1 = orc_motion_bound_leaf(st.m1, A->ang_radius[b1], S1);
+      double mb2 = orc_motion_bound_leaf(st.m2, B->ang_radius[b2], S2);
+      double mint = (dTri) / (mb1 + mb2);
+      if (mint < 0.0) mint = 0.0;
+      if (mint <= st.mint) st.mint = mint;
+    }
+    st.num_tri_tests++;
+    return;
+  }
+
+  int a1, a2, c1, c2;
+  double R1[9], T1[3], R2[9], T2[3], Tt[3];
+  double sz1 = bv_size(A, b1), sz2 = bv_size(B, b2);
+  if (l2 || (!l1 && (sz1 > sz2)))
+  {
+    a1 = A->first_child[b1]; a2 = b2; c1 = a1 + 1; c2 = b2;
+    mt_m(R1, &A->R[9 * a1], R); v_sub(Tt, T, &A->Tr[3 * a1]); mt_v(T1, &A->R[9 * a1], Tt);
+    mt_m(R2, &A->R[9 * c1], R); v_sub(Tt, T, &A->Tr[3 * c1]); mt_v(T2, &A->R[9 * c1], Tt);
+  }
+  else
+  {
+    a1 = b1; a2 = B->first_child[b2]; c1 = b1; c2 = a2 + 1;
+    m_m(R1, R, &B->R[9 * a2]); m_v_p(T1, R, &B->Tr[3 * a2], T);
+    m_m(R2, R, &B->R[9 * c2]); m_v_p(T2, R, &B->Tr[3 * c2], T);
+  }
+
+  double S1[3], S2[3], tmp[3], minta, mintb;
+  double d1 = bv_distance(R1, T1, A, a1, B, a2, S1);
+  if (d1 != 0.0)
+  {
+    m_v(tmp, &A->R_loc[9 * a1], S1); m_v(S1, r1, tmp);
+    S2[0] = S1[0] * -1; S2[1] = S1[1] * -1; S2[2] = S1[2] * -1;
+    double mb1 = orc_motion_bound_bv(st.m1, A->ang_radius[a1], S1);
+    double mb2 = orc_motion_bound_bv(st.m2, B->ang_radius[a2], S2);
+    mintb = (d1) / (mb1 + mb2);
+    if (mintb <= 0) mintb = 0.0;
+  }
+  else mintb = 0.0;
+
+  double d2 = bv_distance(R2, T2, A, c1, B, c2, S1);
+  if (d2 != 0.0)
+  {
+    m_v(tmp, &A->R_loc[9 * c1], S1); m_v(S1, r1, tmp);
+    S2[0] = S1[0] * -1; S2[1] = S1[1] * -1; S2[2] = S1[2] * -1;
+    double mb1 = orc_motion_bound_bv(st.m1, A->ang_radius[c1], S1);
+    double mb2 = orc_motion_bound_bv(st.m2, B->ang_radius[c2], S2);
+    minta = (d2) / (mb1 + mb2);
+    if (minta <= 0) minta = 0.0;
+  }
+  else minta = 0.0;
+
+  st.num_bv_tests += 2;
+
+  // descend test evaluated with the CURRENT st.distance at that moment, :1281-1351
+#define DESCEND(mt, d) ((mt) < st.upbound && (((d) < (st.distance - st.abs_err)) || ((d) * (1 + st.rel_err) < st.distance)))
+  if (d2 < d1)
+  {
+    if (DESCEND(minta, d2)) toc_recurse(st, R2, T2, c1, c2);
+    else if (minta < st.mint) st.mint = minta;
+    if (DESCEND(mintb, d1)) toc_recurse(st, R1, T1, a1, a2);
+    else if (mintb < st.mint) st.mint = mintb;
+  }
+  else
+  {
+    if (DESCEND(mintb, d1)) toc_recurse(st, R1, T1, a1, a2);
+    else if (mintb < st.mint) st.mint = mintb;
+    if (DESCEND(minta, d2)) toc_recurse(st, R2, T2, c1, c2);
+    else if (minta < st.mint) st.mint = minta;
+  }
+#undef DESCEND
+}
+
+// C2A_TimeOfContactStep (rotational branch), C2A/src/C2A.cpp:1778-1931.
+// numCA / prev_mint carry res->numCA and the previous step's res->mint.
+void toc_step(Step &st, int numCA, int seedA, int seedB)
+{
+  const orc_bvh *A = st.A, *B = st.B;
+  const double *R1 = st.m1->Rc, *T1 = st.m1->Tc, *R2 = st.m2->Rc, *T2 = st.m2->Tc;
+  double Tt[3], Rt[9], R[9], T[3];
+  mt_m(st.Rrel, R1, R2);
+  v_sub(Tt, T2, T1);
+  mt_v(st.Trel, R1, Tt);
+  m_m(Rt, st.Rrel, &B->R[0]);
+  mt_m(R, &A->R[0], Rt);
+  m_v_p(Tt, st.Rrel, &B->Tr[0], st.Trel);
+  v_sub(Tt, Tt, &A->Tr[0]);
+  mt_v(T, &A->R[0], Tt);
+
+  double p[3], q[3];
+  st.distance = orc_tri_distance(st.Rrel, st.Trel, &A->tris[9 * seedA], &B->tris[9 * seedB], p, q);
+  if (numCA == 0) st.mint = 1;
+  if (st.mint <= 0.005 || st.distance <= 0.5 || numCA > 5) { st.abs_err = 0; st.rel_err = 0; }
+  else
+  {
+    st.abs_err = 1e+30;
+    st.rel_err = (numCA <= 2) ? 3 : 0.5;
+  }
+  st.mint = 1;
+  toc_recurse(st, R, T, 0, 0);
+}
+}  // namespace
+
+// C2A_Solve (C2A/src/C2A.cpp:2315-2444) up to and including the pose outputs,
+// around C2A_QueryTimeOfContact (:1987-2146); the contact pass (:2433) is not
+// part of the parity contract.
+extern "C" void orc_solve(const orc_bvh *A, const orc_bvh *B, const double poses[48], int32_t seedA,
+                          int32_t seedB, double tol_d, double tol_t, orc_result *out)
+{
+  orc_motion m1, m2;
+  orc_motion_init(&m1, &poses[0], &poses[9], &poses[12], &poses[21]);
+  orc_motion_init(&m2, &poses[24], &poses[33], &poses[36], &poses[45]);
+  memset(out, 0, sizeof(*out));
+  if (m1.ang_vel < 1e-8 && m2.ang_vel < 1e-8)
+  {
+    // translation-only branch (C2A.cpp:2391-2395, :1362-1521) -- SURVEY.md section 8f rank 2, not restated yet
+    out->collisionfree = -1;
+    return;
+  }
+
+  Step st;
+  st.A = A; st.B = B; st.m1 = &m1; st.m2 = &m2;
+  st.num_bv_tests = 0; st.num_tri_tests = 0; st.upbound = 1; st.mint = 1; st.distance = 0;
+  st.p1[0] = st.p1[1] = st.p1[2] = st.p2[0] = st.p2[1] = st.p2[2] = 0;
+  int numCA = 0;
+  double lamda = 0.0, lastLamda = 0, dlamda = 0.0, toc = 0;
+  int collisionfree = 0;
+  bool done_free = false;
+
+  toc_step(st, numCA, seedA, seedB);
+  int nItrs = 0;
+  double dist = st.distance, mint = st.mint;
+  numCA = 1;
+  lastLamda = mint;
+
+  while (dist > tol_d)
+  {
+    nItrs++;
+    if (nItrs > 150) break;
+    if (mint >= 1.0) { collisionfree = 1; toc = 0; done_free = true; break; }
+    dlamda = mint;
+    if (dlamda < tol_t) break;
+    lamda += dlamda;
+    if (lamda >= 1.0) { collisionfree = 1; toc = 0; done_free = true; break; }
+    lastLamda = lamda;
+    numCA++;
+    orc_motion_integrate(&m1, lamda, 0);
+    orc_motion_integrate(&m2, lamda, 0);
+    st.upbound = 1.0 - lamda;
+    toc_step(st, numCA, seedA, seedB);
+    dist = st.distance;
+    mint = st.mint;
+  }
+
+  if (!done_free)
+  {
+    if (dist == 0 && mint < 0) toc = lastLamda - dlamda;
+    else toc = lastLamda;
+    collisionfree = 0;
+    if (toc >= 1 - tol_t) toc = 0;
+    // pose at toc: C2A.cpp:2143 and :2411-2429 (trans0/trans1 = integrate(toc))
+    orc_motion_integrate(&m1, toc, 0);
+    orc_motion_integrate(&m2, toc, 0);
+    memcpy(&out->pose_toc[0], m1.Rc, sizeof(double) * 9); memcpy(&out->pose_toc[9], m1.Tc, sizeof(double) * 3);
+    memcpy(&out->pose_toc[12], m2.Rc, sizeof(double) * 9); memcpy(&out->pose_toc[21], m2.Tc, sizeof(double) * 3);
+  }
+  out->collisionfree = collisionfree;
+  out->numCA = numCA;
+  out->num_bv_tests = st.num_bv_tests;
+  out->num_tri_tests = st.num_tri_tests;
+  out->toc = toc;
+  out->distance = st.distance;
+  out->mint = st.mint;
+  v_cpy(out->p1, st.p1); v_cpy(out->p2, st.p2);
+}
+
+extern "C" void orc_solve_batch(const orc_bvh *A, const orc_bvh *B, const double *poses, int64_t n,
+                                const int32_t *seedA, const int32_t *seedB, double tol_d, double tol_t,
+                                orc_result *out, int32_t n_threads)
+{
+  if (n_threads < 1) n_threads = 1;
+  auto work = [&](int tid) {
+    for (int64_t i = tid; i < n; i += n_threads)
+      orc_solve(A, B, poses + 48 * i, seedA ? seedA[i] : 0, seedB ? seedB[i] : 0, tol_d, tol_t, &out[i]);
+  };
+  if (n_threads == 1) { work(0); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < n_threads; t++) th.emplace_back(work, t);
+  for (auto &t : th) t.join();
+}

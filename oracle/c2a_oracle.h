@@ -1,0 +1,96 @@
+/* TEST INFRASTRUCTURE -- NOT PART OF THE PRODUCT.
+ *
+ * CPU oracle ("port"): a plain, scalar FP64 restatement of the reference's
+ * controlled conservative-advancement CCD hot path
+ *   C2A_Solve -> C2A_QueryTimeOfContact -> C2A_TimeOfContactStep -> TOCStepRecurse_Dis
+ * (reference: /root/reference/C2A/src/C2A.cpp, InterpMotion.cpp, C2A_RectDist.h,
+ * LinearMath.h; each function in c2a_oracle.cpp cites the file:line it follows).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may call this.  The product (c2a_b200/csrc) never links it.
+ *
+ * Pinning: the reference ships no golden vectors, and its
+ * PQP dependency is absent, so this port is pinned against the reference's own
+ * object code run here: oracle/_ref (the reference's five .cpp compiled verbatim
+ * against oracle/pqp_shim) -- bit-exact on every query of the fixtures under
+ * tests/golden/ (see oracle/README.md).  Parity at the PQP boundary itself
+ * (Meigen, TriDist) is "unpinned" in the sense of SURVEY.md section 8c: PQP is
+ * unpinned upstream; TriDist is cross-checked bit-exactly against the
+ * reference's in-tree copy (C2A/src/C2A.cpp:165-405).
+ *
+ * Build: g++ -O2 -ffp-contract=off (no -ffast-math).
+ */
+#ifndef C2A_ORACLE_H
+#define C2A_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Flattened RSS-BVH: the hot fields of C2A_BV (C2A/C2A_BV.h:33-77 + PQP BV) and
+ * the triangles (PQP Tri p1,p2,p3), as produced by the reference's builder. */
+typedef struct orc_bvh
+{
+  int32_t n_nodes, n_tris;
+  const double *R;            /* [n_nodes][9]  BV::R, parent-relative (root: model frame) */
+  const double *Tr;           /* [n_nodes][3]  BV::Tr, parent-relative                    */
+  const double *l;            /* [n_nodes][2]  rectangle side lengths                     */
+  const double *r;            /* [n_nodes]     RSS radius                                 */
+  const double *R_loc;        /* [n_nodes][9]  C2A_BV::R_loc, model frame                 */
+  const double *ang_radius;   /* [n_nodes]     C2A_BV::angularRadius                      */
+  const int32_t *first_child; /* [n_nodes]     >=0 child index; <0: -(tri+1)              */
+  const double *tris;         /* [n_tris][9]   p1,p2,p3 in builder (permuted) order       */
+} orc_bvh;
+
+typedef struct orc_result
+{
+  int32_t collisionfree;  /* C2A_TimeOfContactResult::collisionfree */
+  int32_t numCA;          /* ::numCA  (== number_of_iteration of C2A_Solve) */
+  int32_t num_bv_tests;   /* ::num_bv_tests */
+  int32_t num_tri_tests;  /* ::num_tri_tests */
+  double toc;             /* ::toc */
+  double distance;        /* ::distance */
+  double mint;            /* ::mint of the last step */
+  double p1[3], p2[3];    /* ::p1, ::p2 (model-1 frame) */
+  double pose_toc[24];    /* C2A_Solve's trans0, trans1 as R(9)+T(3) each; written only on a hit */
+} orc_result;
+
+/* geometry kernels */
+double orc_rect_dist(const double Rab[9], const double Tab[3], const double a[2], const double b[2],
+                     double P[3], double Q[3], double S[3]);
+double orc_tri_dist(double P[3], double Q[3], const double S[9], const double T[9]);
+void orc_seg_points(double VEC[3], double X[3], double Y[3], const double P[3], const double A[3],
+                    const double Q[3], const double B[3]);
+double orc_tri_distance(const double R[9], const double T[3], const double t1[9], const double t2[9],
+                        double p[3], double q[3]);
+
+/* motion (CInterpMotion_Linear) */
+typedef struct orc_motion
+{
+  double Rs[9], Ts[3], Re[9], Te[3]; /* transform_s, transform_t */
+  double cv[3], axis[3], ang_vel;    /* cv, m_axis, m_angVel */
+  double Rc[9], Tc[3];               /* transform (current pose; mutated by integrate) */
+} orc_motion;
+void orc_motion_init(orc_motion *m, const double R0[9], const double T0[3], const double R1[9],
+                     const double T1[3]);
+void orc_motion_integrate(orc_motion *m, double t, double q_out[4] /* x,y,z,w; may be NULL */);
+double orc_motion_bound_bv(const orc_motion *m, double ang_radius, double N[3]);
+double orc_motion_bound_leaf(const orc_motion *m, double ang_radius, double S[3]);
+
+/* One query.  poses = trans00, trans01, trans10, trans11 as R(9 row-major)+T(3) each (48 doubles).
+ * seedA/seedB: triangle indices playing res->last_triA/B.
+ * Mirrors C2A_Solve minus the contact pass when tol_d = tol_t = 1e-4 (C2A.cpp:2384-2385). */
+void orc_solve(const orc_bvh *A, const orc_bvh *B, const double poses[48], int32_t seedA,
+               int32_t seedB, double tol_d, double tol_t, orc_result *out);
+
+/* Batch over n queries on n_threads std::threads (static interleave). */
+void orc_solve_batch(const orc_bvh *A, const orc_bvh *B, const double *poses, int64_t n,
+                     const int32_t *seedA, const int32_t *seedB, double tol_d, double tol_t,
+                     orc_result *out, int32_t n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
