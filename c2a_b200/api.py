@@ -1,0 +1,146 @@
+"""ctypes bindings of the C ABI in ``include/c2a_b200.h`` (``c2a_b200/csrc/libc2a_b200.so``).
+
+Plumbing only: the compute is the CUDA library.  There is no CPU fallback -- if the library is
+missing or no CUDA device is present, calls raise."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libc2a_b200.so")
+_lib = None
+
+RESULT_FIELDS = (("status", np.int32, ()), ("collisionfree", np.int32, ()), ("num_ca", np.int32, ()),
+                 ("num_bv_tests", np.int32, ()), ("num_tri_tests", np.int32, ()), ("toc", np.float64, ()),
+                 ("distance", np.float64, ()), ("mint", np.float64, ()), ("p1p2", np.float64, (6,)),
+                 ("pose_toc", np.float64, (24,)))
+
+
+class C2AError(RuntimeError):
+    pass
+
+
+class Bvh(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("n_tris", C.c_int32),
+                ("R", C.c_void_p), ("Tr", C.c_void_p), ("l", C.c_void_p), ("r", C.c_void_p),
+                ("R_loc", C.c_void_p), ("ang_radius", C.c_void_p), ("first_child", C.c_void_p),
+                ("tris", C.c_void_p)]
+
+
+class Results(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name, _, _ in RESULT_FIELDS]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise C2AError(f"{_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+        L = C.CDLL(_LIB_PATH)
+        L.c2a_b200_last_error.restype = C.c_char_p
+        L.c2a_b200_launch_count.restype = C.c_int64
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise C2AError(f"c2a_b200 error {rc}: {lib().c2a_b200_last_error().decode()}")
+
+
+def device_count():
+    n = C.c_int32(0)
+    _check(lib().c2a_b200_device_count(C.byref(n)))
+    return n.value
+
+
+def launch_count():
+    return int(lib().c2a_b200_launch_count())
+
+
+class Model:
+    """A C2A model resident on one GPU.  ``bvh`` is a dict of contiguous numpy arrays with the keys of
+    ``struct c2a_b200_bvh`` (R, Tr, l, r, R_loc, ang_radius float64; first_child int32; tris float64)."""
+
+    def __init__(self, bvh, device=0):
+        s = Bvh()
+        s.n_nodes = int(bvh["first_child"].shape[0])
+        s.n_tris = int(bvh["tris"].shape[0])
+        keep = []
+        for k in ("R", "Tr", "l", "r", "R_loc", "ang_radius", "tris"):
+            a = np.ascontiguousarray(bvh[k], dtype=np.float64)
+            keep.append(a)
+            setattr(s, k, a.ctypes.data)
+        fc = np.ascontiguousarray(bvh["first_child"], dtype=np.int32)
+        keep.append(fc)
+        s.first_child = fc.ctypes.data
+        h = C.c_void_p()
+        _check(lib().c2a_b200_model_upload(C.byref(s), C.c_int32(device), C.byref(h)))
+        self.h = h
+        self.device = device
+        self.n_nodes, self.n_tris = s.n_nodes, s.n_tris
+
+    def info(self):
+        d, nn, nt, dep = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        _check(lib().c2a_b200_model_info(self.h, C.byref(d), C.byref(nn), C.byref(nt), C.byref(dep)))
+        return {"device": d.value, "n_nodes": nn.value, "n_tris": nt.value, "depth": dep.value}
+
+    def free(self):
+        if self.h:
+            lib().c2a_b200_model_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def solve_batch(model_a, model_b, poses, seed_a=None, seed_b=None, tol_d=1e-4, tol_t=1e-4, fields=None):
+    """Host-buffer entry (H2D + kernel + D2H inside the call).  Returns a dict of numpy arrays."""
+    poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 48)
+    n = poses.shape[0]
+    res = Results()
+    out = {}
+    for name, dt, shape in RESULT_FIELDS:
+        if fields is not None and name not in fields:
+            continue
+        a = np.zeros((n,) + shape, dtype=dt)
+        out[name] = a
+        setattr(res, name, a.ctypes.data)
+    sa = None if seed_a is None else np.ascontiguousarray(seed_a, dtype=np.int32)
+    sb = None if seed_b is None else np.ascontiguousarray(seed_b, dtype=np.int32)
+    _check(lib().c2a_b200_solve_batch(model_a.h, model_b.h, poses.ctypes.data_as(C.c_void_p),
+                                      sa.ctypes.data_as(C.c_void_p) if sa is not None else None,
+                                      sb.ctypes.data_as(C.c_void_p) if sb is not None else None,
+                                      C.c_int64(n), C.c_double(tol_d), C.c_double(tol_t), C.byref(res)))
+    return out
+
+
+def motions_from_poses(poses, threads=0, out=None):
+    """Host half of the motion model (acos via the host libm): poses [n,48] -> motion records [n,48]."""
+    poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 48)
+    n = poses.shape[0]
+    if out is None:
+        out = np.empty((n, 48), dtype=np.float64)
+    _check(lib().c2a_b200_motions_from_poses(poses.ctypes.data_as(C.c_void_p), C.c_int64(n),
+                                             out.ctypes.data_as(C.c_void_p), C.c_int32(threads)))
+    return out
+
+
+def solve_batch_device(model_a, model_b, poses_ptr, n, out_ptrs, seed_a_ptr=None, seed_b_ptr=None,
+                       tol_d=1e-4, tol_t=1e-4, stream=None):
+    """Device-pointer entry: ``poses_ptr`` (MOTION RECORDS from ``motions_from_poses``, resident on the
+    device) and the values of ``out_ptrs`` (dict field -> int address) are CUDA device addresses (e.g. ``torch.Tensor.data_ptr()``); enqueues on ``stream`` (a
+    cudaStream_t address or None) and returns without synchronising."""
+    res = Results()
+    for name, _, _ in RESULT_FIELDS:
+        if name in out_ptrs and out_ptrs[name]:
+            setattr(res, name, out_ptrs[name])
+    _check(lib().c2a_b200_solve_batch_device(model_a.h, model_b.h, C.c_void_p(poses_ptr),
+                                             C.c_void_p(seed_a_ptr) if seed_a_ptr else None,
+                                             C.c_void_p(seed_b_ptr) if seed_b_ptr else None,
+                                             C.c_int64(n), C.c_double(tol_d), C.c_double(tol_t), C.byref(res),
+                                             C.c_void_p(stream) if stream else None))

@@ -1,0 +1,121 @@
+/* c2a_b200 -- C ABI of the B200-native C2A continuous-collision-detection hot path.
+ *
+ * Drop-in boundary.  The reference (EwhaGlab/C2A) has no FFI layer: its boundary is the C++ header
+ * C2A/C2A.h.  The C++ shims in include/C2A/ keep those entry points (C2A_Solve C2A/C2A.h:23-35,
+ * C2A_QueryTimeOfContact C2A/C2A.h:274-281, C2A_TimeOfContactStep C2A/src/C2A.cpp:1778-1789) and
+ * call the functions below; a batched C2A_SolveBatch is added.  Everything here is extern "C",
+ * plain pointers and sizes; no C++ or torch types cross it.  See INTEGRATION.md.
+ *
+ * All functions return 0 on success, a negative C2A_B200_ERR_* code otherwise;
+ * c2a_b200_last_error() describes the last failure on the calling thread.  Nothing here prints
+ * to stdout or calls exit() (the reference does both: C2A/src/C2A.cpp:2408, C2A/LinearMath.h:768).
+ * There is no CPU fallback: without a CUDA device every compute entry fails with
+ * C2A_B200_ERR_CUDA.
+ */
+#ifndef C2A_B200_H
+#define C2A_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C2A_B200_OK 0
+#define C2A_B200_ERR_ARG (-1)         /* null pointer, bad size, malformed BVH */
+#define C2A_B200_ERR_CUDA (-2)        /* CUDA runtime error (including: no device) */
+#define C2A_B200_ERR_DEPTH (-3)       /* depth(A)+depth(B) exceeds the traversal stack */
+#define C2A_B200_ERR_DEVICE (-4)      /* models live on different devices */
+
+/* per-query status written to c2a_b200_results.status */
+#define C2A_B200_QUERY_OK 0
+#define C2A_B200_QUERY_TRANSLATION_ONLY 1 /* both angular speeds < 1e-8: the reference switches to its
+                                             translation-only branch (C2A/src/C2A.cpp:2391-2395), which
+                                             this build does not implement yet; outputs are not written */
+
+/* Flattened RSS bounding-volume hierarchy of one C2A_Model after EndModel(): the hot fields of
+ * C2A_BV (C2A/C2A_BV.h:33-77 on top of PQP's BV) and the triangles (PQP Tri p1,p2,p3) in the
+ * builder's (permuted) order.  Children of node n are first_child[n] and first_child[n]+1
+ * (C2A/src/C2A_Build.cpp:456-457); first_child[n] < 0 marks a leaf holding triangle
+ * -first_child[n]-1 (:451).  R/Tr are parent-relative (:533-538), R_loc is in the model frame
+ * (:439).  Host pointers; the upload copies everything. */
+typedef struct c2a_b200_bvh
+{
+  int32_t n_nodes;
+  int32_t n_tris;
+  const double *R;            /* [n_nodes][9] row-major */
+  const double *Tr;           /* [n_nodes][3] */
+  const double *l;            /* [n_nodes][2] */
+  const double *r;            /* [n_nodes]    */
+  const double *R_loc;        /* [n_nodes][9] row-major */
+  const double *ang_radius;   /* [n_nodes]    C2A_BV::angularRadius */
+  const int32_t *first_child; /* [n_nodes]    */
+  const double *tris;         /* [n_tris][9]  p1,p2,p3 */
+} c2a_b200_bvh;
+
+typedef struct c2a_b200_model c2a_b200_model; /* device-resident model, opaque */
+
+/* Per-query outputs, structure of arrays; any pointer may be NULL to skip that output.
+ * Host pointers for c2a_b200_solve_batch, device pointers for c2a_b200_solve_batch_device. */
+typedef struct c2a_b200_results
+{
+  int32_t *status;        /* [n]     C2A_B200_QUERY_*                                                  */
+  int32_t *collisionfree; /* [n]     C2A_TimeOfContactResult::collisionfree (the verdict, quirk Q1)    */
+  int32_t *num_ca;        /* [n]     ::numCA == number_of_iteration of C2A_Solve                        */
+  int32_t *num_bv_tests;  /* [n]     ::num_bv_tests                                                    */
+  int32_t *num_tri_tests; /* [n]     ::num_tri_tests                                                   */
+  double *toc;            /* [n]     ::toc == time_of_contact of C2A_Solve                              */
+  double *distance;       /* [n]     ::distance                                                        */
+  double *mint;           /* [n]     ::mint of the last CA step                                        */
+  double *p1p2;           /* [n][6]  ::p1, ::p2 (closest points, model-1 frame)                        */
+  double *pose_toc;       /* [n][24] trans0, trans1 of C2A_Solve as R(9)+T(3) each; only written when
+                                     collisionfree == 0, like the reference                            */
+} c2a_b200_results;
+
+int c2a_b200_device_count(int32_t *count);
+
+/* Upload a built model to `device`.  Replaces nothing in the reference (its models live in host
+ * memory, C2A/C2A_Internal.h:32-81); the input is what C2A_Model::EndModel() produced
+ * (C2A/src/C2A_PQP.cpp:331-417). */
+int c2a_b200_model_upload(const c2a_b200_bvh *bvh, int32_t device, c2a_b200_model **out);
+int c2a_b200_model_free(c2a_b200_model *m);
+int c2a_b200_model_info(const c2a_b200_model *m, int32_t *device, int32_t *n_nodes, int32_t *n_tris,
+                        int32_t *depth);
+
+/* Batched C2A_Solve (C2A/src/C2A.cpp:2315-2444, without its contact pass) over n independent
+ * queries on the models' device.  poses: [n][48] = trans00, trans01, trans10, trans11, each R (9,
+ * row-major) + T (3) (the four Transform* of C2A_Solve).  seed_a / seed_b: [n] triangle indices
+ * standing in for res->last_triA / last_triB (C2A/src/C2A.cpp:1816-1817; NULL = triangle 0, the
+ * state after EndModel, C2A/src/C2A_PQP.cpp:401).  tol_d / tol_t: C2A_Solve hard-codes 1e-4 for
+ * both (C2A/src/C2A.cpp:2384-2385); C2A_QueryTimeOfContact takes them as arguments.
+ * Host buffers; host<->device copies are inside the call. */
+int c2a_b200_solve_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses,
+                         const int32_t *seed_a, const int32_t *seed_b, int64_t n, double tol_d, double tol_t,
+                         const c2a_b200_results *out);
+
+/* Host half of the motion model: what constructing the two CInterpMotion_Linear objects does in
+ * C2A_Solve (C2A/src/C2A.cpp:2378-2379 -> C2A/src/InterpMotion.cpp:148-168, 486-491, 228-270).
+ * poses [n][48] -> motions [n][C2A_B200_MOTION_DOUBLES]: per object R0(9) T0(3) cv(3) axis(3) angVel
+ * qs(4) pad.  It stays on the host because LinearAngularVelocity calls acos(): the reference's
+ * constants are whatever the host libm returns, and the device consumes exactly those.
+ * n_threads <= 0: all host cores. */
+#define C2A_B200_MOTION_DOUBLES 48
+int c2a_b200_motions_from_poses(const double *poses, int64_t n, double *motions, int32_t n_threads);
+
+/* Batched C2A_QueryTimeOfContact (+ the pose outputs of C2A_Solve) with everything already resident
+ * on the models' device: motions_dev [n][C2A_B200_MOTION_DOUBLES] from c2a_b200_motions_from_poses,
+ * seeds and outputs device pointers.  Enqueued on `cuda_stream` (a cudaStream_t; NULL = default
+ * stream) without synchronising. */
+int c2a_b200_solve_batch_device(const c2a_b200_model *a, const c2a_b200_model *b, const double *motions_dev,
+                                const int32_t *seed_a_dev, const int32_t *seed_b_dev, int64_t n, double tol_d,
+                                double tol_t, const c2a_b200_results *out_dev, void *cuda_stream);
+
+/* Number of kernel launches issued by this library on the calling process so far. */
+int64_t c2a_b200_launch_count(void);
+
+const char *c2a_b200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

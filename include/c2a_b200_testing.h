@@ -1,0 +1,35 @@
+/* c2a_b200 -- unit-test hooks: the device functions of the CCD hot path, one element per thread, so
+ * that tests/ can check each against the CPU oracle (and sin/cos against the host libm).
+ * Host pointers in, host pointers out; each call copies, launches one kernel and synchronises.
+ * Not part of the drop-in boundary. */
+#ifndef C2A_B200_TESTING_H
+#define C2A_B200_TESTING_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* C2ARectDist (C2A/C2A_RectDist.h:157-934): R [n][9], T [n][3], ab [n][4] = a0,a1,b0,b1 ->
+ * dist [n], S [n][3] (pre-filled with NaN where the reference leaves S untouched). */
+int c2a_b200_test_rect_dist(const double *R, const double *T, const double *ab, int64_t n, double *dist, double *S);
+
+/* PQP TriDistance (call sites C2A/src/C2A.cpp:1148,1916): R [n][9], T [n][3], t1/t2 [n][9] ->
+ * dist [n], pq [n][6]. */
+int c2a_b200_test_tri_distance(const double *R, const double *T, const double *t1, const double *t2, int64_t n,
+                               double *dist, double *pq);
+
+/* CInterpMotion_Linear::integrate and the two motion bounds: rec [n][24] (one object's motion record),
+ * t [n], ang_radius [n], dir [n][3] -> out [n][14] = R(9) T(3) computeTOC_MotionBound computeTOC. */
+int c2a_b200_test_motion(const double *rec, const double *t, const double *ang_radius, const double *dir, int64_t n,
+                         double *out);
+
+/* device sin/cos that mirror the host libm (c2a_libm.cuh) and their host twins (no GPU needed). */
+int c2a_b200_test_sincos(const double *x, int64_t n, double *s, double *c);
+int c2a_b200_host_sincos(const double *x, int64_t n, double *s, double *c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

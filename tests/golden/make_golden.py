@@ -1,0 +1,107 @@
+"""Generates the committed fixtures under tests/golden/ by running the REFERENCE's own object code
+(oracle/_ref/libc2a_ref.so = /root/reference/C2A/src/*.cpp compiled verbatim against oracle/pqp_shim).
+
+Run in the container that has /root/reference:   python tests/golden/make_golden.py
+
+Outputs (all consumed by tests/ and bench.py; nothing under /root/reference is read at test time):
+  bunny_mesh.npz        verts float64 [34834,3], vidx int32 [69664,3] parsed from tri_models/bunny_noholes.tri
+  demo_poses.npy        the 303 queries of the CCDDemo (config 1), from models/torusknot{1,2}.ani
+  ref_<case>.npz        per-query results of the reference (collisionfree, toc, distance, numCA, counters,
+                        p1p2, pose_toc) + the poses / tolerances that produced them
+  bvh_digest.json       sha256 of every flattened BVH array built by the reference's builder
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+import oracle  # noqa: E402
+from c2a_b200 import meshes, workloads  # noqa: E402
+
+REF = "/root/reference"
+THREADS = os.cpu_count() or 1
+
+
+def save_results(name, res, poses, tol_d, tol_t, extra=None):
+    d = {k: res[k] for k in res.dtype.names}
+    d["p1p2"] = np.concatenate([res["p1"], res["p2"]], 1)
+    del d["p1"], d["p2"]
+    d["poses"] = poses
+    d["tol_d"] = np.float64(tol_d)
+    d["tol_t"] = np.float64(tol_t)
+    if extra:
+        d.update(extra)
+    np.savez_compressed(os.path.join(HERE, name), **d)
+    hits = int((res["collisionfree"] == 0).sum())
+    print(f"{name}: n={len(res)} hits={hits} mean numCA={res['numCA'].mean():.2f} "
+          f"mean nbv={res['num_bv_tests'].mean():.0f} mean ntri={res['num_tri_tests'].mean():.0f}")
+
+
+def digest(bvh):
+    return {k: hashlib.sha256(np.ascontiguousarray(bvh[k]).tobytes()).hexdigest() for k in sorted(bvh)}
+
+
+def main():
+    oracle.build_oracle()
+    R = oracle.ref()
+
+    # --- meshes
+    with open(os.path.join(REF, "tri_models/bunny_noholes.tri")) as f:
+        tok = f.read().split()
+    nv, nt = int(tok[1]), int(tok[2])
+    verts = np.array(tok[3:3 + 3 * nv], dtype=np.float64).reshape(nv, 3)
+    vidx = np.array(tok[3 + 3 * nv:3 + 3 * nv + 3 * nt], dtype=np.int32).reshape(nt, 3)
+    np.savez_compressed(os.path.join(HERE, "bunny_mesh.npz"), verts=verts, vidx=vidx)
+    bunny_tris = verts[vidx].reshape(nt, 9).copy()
+
+    digests = {}
+    bunny = R.model(bunny_tris, vidx)
+    digests["bunny"] = digest(bunny.export())
+
+    # --- config 1: the demo's 303 queries
+    R1, T1 = meshes.load_ani(os.path.join(REF, "models/torusknot1.ani"))
+    R2, T2 = meshes.load_ani(os.path.join(REF, "models/torusknot2.ani"))
+    demo = workloads.demo_batch(R1, T1, R2, T2)
+    np.save(os.path.join(HERE, "demo_poses.npy"), demo)
+    res = R.solve_batch(bunny, bunny, demo, threads=THREADS)
+    save_results("ref_demo_bunny.npz", res, demo, 1e-4, 1e-4)
+    # the full, unmodified C2A_Solve (incl. contact pass) must agree with the TOC-only wrapper
+    full, ncont = R.solve_batch(bunny, bunny, demo[:40], mode=1)
+    for k in ("collisionfree", "numCA", "num_bv_tests", "num_tri_tests", "toc", "distance", "pose_toc"):
+        assert np.array_equal(full[k], res[k][:40]), k
+    np.save(os.path.join(HERE, "ref_demo_num_contact.npy"), ncont)
+
+    # --- config 2 (sample): bunny vs bunny random approach
+    poses = workloads.approach_batch(2000, 20260001)
+    res = R.solve_batch(bunny, bunny, poses, threads=THREADS)
+    save_results("ref_bunny_approach.npz", res, poses, 1e-4, 1e-4)
+
+    # --- config 3 (samples): torus knots at three resolutions
+    for nu, nvv, n in ((128, 16, 1500), (512, 32, 2000), (1024, 32, 500)):
+        tris, vi = meshes.torus_knot(nu, nvv)
+        knot = R.model(tris, vi)
+        digests[f"knot_{nu}x{nvv}"] = digest(knot.export())
+        poses = workloads.approach_batch(n, 20260002, radius=workloads.KNOT_RADIUS)
+        res = R.solve_batch(knot, knot, poses, threads=THREADS)
+        save_results(f"ref_knot_{nu}x{nvv}.npz", res, poses, 1e-4, 1e-4)
+        if nu == 512:
+            # heterogeneous pair + explicit seeds + non-default tolerances
+            rng = np.random.default_rng(7)
+            sa = rng.integers(0, bunny.n_tris, 400).astype(np.int32)
+            sb = rng.integers(0, knot.n_tris, 400).astype(np.int32)
+            poses = workloads.approach_batch(400, 20260003, radius=workloads.KNOT_RADIUS)
+            res = R.solve_batch(bunny, knot, poses, seedA=sa, seedB=sb, tol_d=1e-3, tol_t=1e-5, threads=THREADS)
+            save_results("ref_bunny_vs_knot_seeded.npz", res, poses, 1e-3, 1e-5, {"seed_a": sa, "seed_b": sb})
+
+    with open(os.path.join(HERE, "bvh_digest.json"), "w") as f:
+        json.dump(digests, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()
