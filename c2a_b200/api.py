@@ -59,6 +59,37 @@ def launch_count():
     return int(lib().c2a_b200_launch_count())
 
 
+def build_bvh(tris9):
+    """Host-side RSS BVH build (the product's own builder, c2a_host_model.cpp).  tris9: [n,9] float64.
+    Returns a dict of numpy arrays with the keys of ``struct c2a_b200_bvh`` plus ``tri_ids``/``depth``."""
+    tris9 = np.ascontiguousarray(tris9, dtype=np.float64).reshape(-1, 9)
+    n = tris9.shape[0]
+    h = C.c_void_p()
+    _check(lib().c2a_b200_bvh_build(tris9.ctypes.data_as(C.c_void_p), C.c_int32(n), C.byref(h)))
+    try:
+        v = Bvh()
+        ids = C.c_void_p()
+        depth = C.c_int32()
+        _check(lib().c2a_b200_bvh_view(h, C.byref(v), C.byref(ids), C.byref(depth)))
+        nn = v.n_nodes
+
+        def arr(ptr, count, ctype, dtype):
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,)).astype(dtype, copy=True)
+        out = {"R": arr(v.R, 9 * nn, C.c_double, np.float64).reshape(nn, 9),
+               "Tr": arr(v.Tr, 3 * nn, C.c_double, np.float64).reshape(nn, 3),
+               "l": arr(v.l, 2 * nn, C.c_double, np.float64).reshape(nn, 2),
+               "r": arr(v.r, nn, C.c_double, np.float64),
+               "R_loc": arr(v.R_loc, 9 * nn, C.c_double, np.float64).reshape(nn, 9),
+               "ang_radius": arr(v.ang_radius, nn, C.c_double, np.float64),
+               "first_child": arr(v.first_child, nn, C.c_int32, np.int32),
+               "tris": arr(v.tris, 9 * n, C.c_double, np.float64).reshape(n, 9),
+               "tri_ids": arr(ids, n, C.c_int32, np.int32),
+               "depth": depth.value}
+    finally:
+        lib().c2a_b200_bvh_free(h)
+    return out
+
+
 class Model:
     """A C2A model resident on one GPU.  ``bvh`` is a dict of contiguous numpy arrays with the keys of
     ``struct c2a_b200_bvh`` (R, Tr, l, r, R_loc, ang_radius float64; first_child int32; tris float64)."""

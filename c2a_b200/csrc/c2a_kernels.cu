@@ -1,22 +1,6 @@
-// Batched controlled-conservative-advancement CCD on the GPU (sm_100a, FP64) + the C ABI of
-// include/c2a_b200.h.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo.
-//
-// What runs on the device, per query (reference paths relative to /root/reference):
-//   C2A_Solve's motion set-up                    C2A/src/C2A.cpp:2342-2395
-//   C2A_QueryTimeOfContact  (the CA loop)        C2A/src/C2A.cpp:1987-2146
-//   C2A_TimeOfContactStep   (per-step set-up)    C2A/src/C2A.cpp:1778-1931
-//   TOCStepRecurse_Dis      (BVTT traversal)     C2A/src/C2A.cpp:1114-1354
-//   pose outputs of C2A_Solve                    C2A/src/C2A.cpp:2411-2429
-// with no host round trip between CA iterations.
-//
-// Execution model.  The traversal result is order dependent (res->distance shrinks as leaves are
-// visited and gates pruning, C2A.cpp:1281-1351), so parallelism is taken ACROSS queries: one lane
-// owns one query and commits node pairs in the reference's depth-first order.  The kernel is
-// persistent: lanes claim queries from a global atomic counter until the batch is drained, so a
-// lane whose query ended early (far-apart pair, one CA step) immediately starts another one.
-// Every lane is a small state machine (ADVANCE / TRAVERSE / LEAF); the warp executes one phase at
-// a time and votes (ballot) on which phase to run, so that lanes run the long FP64 routines
-// (rectangle distance, triangle distance) together instead of serialising them against each other.
+// C ABI of include/c2a_b200.h: model upload, host half of the motion model, batch launch of the
+// persistent CCD kernel (c2a_solve.cuh), unit-test hooks.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo (see c2a_b200/build.py).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -29,372 +13,9 @@
 #include <vector>
 
 #include "../../include/c2a_b200.h"
-#include "c2a_geom.cuh"
-#include "c2a_motion.cuh"
+#include "c2a_solve.cuh"
 
 namespace c2a {
-
-// ---- device-resident model ---------------------------------------------------------------
-// geom  [n][16]  R(9) Tr(3) l(2) r ang_radius      one 128-byte line per node; children adjacent
-// rloc  [n][9]   R_loc (only read when a BV distance is non-zero)
-// meta  [n]      {GetSize() = sqrt(l0^2+l1^2)+2r precomputed (PQP BV::GetSize), first_child}
-// tris  [n][9]
-constexpr int GEOM_STRIDE = 16;
-struct NodeMeta { double size; int first_child; int pad; };
-struct DevModel
-{
-  const double *geom;
-  const double *rloc;
-  const NodeMeta *meta;
-  const double *tris;
-  int n_nodes, n_tris;
-};
-
-constexpr int MAX_STACK = 64;     // >= depth(A)+depth(B)+2, validated on the host
-constexpr int ENTRY_DOUBLES = 16; // R(9) T(3) d mint {b1,b2} pad  -> 128 B
-constexpr int BLOCK_THREADS = 128;
-
-struct BatchArgs
-{
-  DevModel A, B;
-  const double *motions;  // [n][2][MOTION_DOUBLES], see c2a_motion.cuh
-  const int *seedA, *seedB;
-  long long n;
-  double tol_d, tol_t;
-  c2a_b200_results out;
-  unsigned long long *counter;
-};
-
-enum LaneState { ST_ADVANCE = 0, ST_TRAVERSE = 1, ST_LEAF = 2, ST_EXIT = 3 };
-
-C2A_DEV void load9(double d[9], const double *s)
-{
-#pragma unroll
-  for (int i = 0; i < 9; i++) d[i] = __ldg(s + i);
-}
-C2A_DEV void load3(double d[3], const double *s) { d[0] = __ldg(s); d[1] = __ldg(s + 1); d[2] = __ldg(s + 2); }
-
-__device__ __noinline__ double tri_distance_nl(const double R[9], const double T[3], const double *t1,
-                                               const double *t2, double p[3], double q[3])
-{
-  double a[9], b[9];
-  load9(a, t1);
-  load9(b, t2);
-  return tri_distance(R, T, a, b, p, q);
-}
-
-// One child BV test of an expansion (C2A.cpp:1237-1276): RSS distance, direction to world frame,
-// the two directional motion bounds, and the child's conservative step bound.
-//   gs: geom record of the side-1 node of the test, gt: of the side-2 node, rl: R_loc of the side-1 node.
-C2A_DEV void child_test(const double Rc[9], const double Tc[3], const double *gs, const double *gt,
-                        const double *rl, const double r1[9], const Motion &m1, const Motion &m2, double &d_out,
-                        double &mint_out)
-{
-  double S[3];
-  const double a0 = __ldg(gs + 12), a1 = __ldg(gs + 13), ra = __ldg(gs + 14);
-  const double b0 = __ldg(gt + 12), b1 = __ldg(gt + 13), rb = __ldg(gt + 14);
-  double d = rss_rect_dist(Rc, Tc, a0, a1, b0, b1, S);
-  d -= (ra + rb);
-  d = (d < 0.0) ? 0.0 : d;
-  double mint = 0.0;
-  if (d != 0.0)
-  {
-    double Rl[9], tmp[3], S1[3], S2[3];
-    load9(Rl, rl);
-    m_v(tmp, Rl, S);
-    m_v(S1, r1, tmp);
-    S2[0] = S1[0] * -1; S2[1] = S1[1] * -1; S2[2] = S1[2] * -1;
-    const double mb1 = motion_bound_bv(m1, __ldg(gs + 15), S1);
-    const double mb2 = motion_bound_bv(m2, __ldg(gt + 15), S2);
-    mint = (d) / (mb1 + mb2);
-    if (mint <= 0) mint = 0.0;
-  }
-  d_out = d;
-  mint_out = mint;
-}
-
-__global__ void __launch_bounds__(BLOCK_THREADS) c2a_solve_kernel(const BatchArgs args)
-{
-  const unsigned FULL = 0xffffffffu;
-  const DevModel &A = args.A, &B = args.B;
-
-  // per-lane traversal stack (local memory: interleaved across the warp by the hardware)
-  double stk[MAX_STACK * ENTRY_DOUBLES];
-  int sp = 0;
-
-  // query state
-  long long q = -1;
-  Motion m1, m2;
-  double r1[9], tt1[3];      // current pose of object 1 (objmotion1->transform)
-  double Rrel[9], Trel[3];   // res->R, res->T
-  double dist = 0, mint = 1, abs_err = 0, rel_err = 0, upbound = 1;
-  double p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0};
-  double lamda = 0, lastLamda = 0;
-  int numCA = 0, nItrs = 0, nbv = 0, ntri = 0;
-  int seedA = 0, seedB = 0;
-  int leaf_b1 = 0, leaf_b2 = 0;
-  bool step_pending = false;  // a step set-up is due (first step or after advancing lamda)
-
-  int state = ST_ADVANCE;
-
-  while (true)
-  {
-    const unsigned mT = __ballot_sync(FULL, state == ST_TRAVERSE);
-    const unsigned mL = __ballot_sync(FULL, state == ST_LEAF);
-    const unsigned mA = __ballot_sync(FULL, state == ST_ADVANCE);
-    if ((mT | mL | mA) == 0) break;
-    const bool runL = (__popc(mL) >= 12) || (mT == 0 && mL != 0);
-    const bool runA = (__popc(mA) >= 8) || (mT == 0 && !runL && mA != 0);
-
-    // ------------------------------------------------------------------ ADVANCE ----------
-    // claim a query / CA-loop bookkeeping after a finished step / next step's set-up
-    if (runA && state == ST_ADVANCE)
-    {
-      bool finished = false, hit = false;
-      if (q >= 0 && !step_pending)
-      {
-        // a step just ended: C2A_QueryTimeOfContact's loop, C2A.cpp:2053-2123
-        if (numCA == 0) { numCA = 1; lastLamda = mint; }
-        if (!(dist > args.tol_d)) { finished = true; hit = true; }
-        else
-        {
-          nItrs++;
-          if (nItrs > 150) { finished = true; hit = true; }
-          else if (mint >= 1.0) { finished = true; hit = false; }
-          else
-          {
-            const double dlamda = mint;
-            if (dlamda < args.tol_t) { finished = true; hit = true; }
-            else
-            {
-              lamda += dlamda;
-              if (lamda >= 1.0) { finished = true; hit = false; }
-              else
-              {
-                lastLamda = lamda;
-                numCA++;
-                motion_pose(m1, lamda, r1, tt1);
-                upbound = 1.0 - lamda;
-                step_pending = true;
-              }
-            }
-          }
-        }
-        if (finished)
-        {
-          // C2A.cpp:2125-2143 and the pose outputs of C2A_Solve :2411-2429
-          double toc = 0.0;
-          const c2a_b200_results &o = args.out;
-          if (hit)
-          {
-            toc = lastLamda;
-            if (toc >= 1 - args.tol_t) toc = 0;
-            if (o.pose_toc)
-            {
-              double R[9], T[3];
-              motion_pose(m1, toc, R, T);
-#pragma unroll
-              for (int i = 0; i < 9; i++) o.pose_toc[24 * q + i] = R[i];
-#pragma unroll
-              for (int i = 0; i < 3; i++) o.pose_toc[24 * q + 9 + i] = T[i];
-              motion_pose(m2, toc, R, T);
-#pragma unroll
-              for (int i = 0; i < 9; i++) o.pose_toc[24 * q + 12 + i] = R[i];
-#pragma unroll
-              for (int i = 0; i < 3; i++) o.pose_toc[24 * q + 21 + i] = T[i];
-            }
-          }
-          if (o.status) o.status[q] = C2A_B200_QUERY_OK;
-          if (o.collisionfree) o.collisionfree[q] = hit ? 0 : 1;
-          if (o.num_ca) o.num_ca[q] = numCA;
-          if (o.num_bv_tests) o.num_bv_tests[q] = nbv;
-          if (o.num_tri_tests) o.num_tri_tests[q] = ntri;
-          if (o.toc) o.toc[q] = toc;
-          if (o.distance) o.distance[q] = dist;
-          if (o.mint) o.mint[q] = mint;
-          if (o.p1p2)
-          {
-#pragma unroll
-            for (int i = 0; i < 3; i++) { o.p1p2[6 * q + i] = p1[i]; o.p1p2[6 * q + 3 + i] = p2[i]; }
-          }
-          q = -1;
-        }
-      }
-
-      if (q < 0)
-      {
-        // claim the next query
-        const long long nq = (long long)atomicAdd(args.counter, 1ull);
-        if (nq >= args.n) state = ST_EXIT;
-        else
-        {
-          q = nq;
-          const double *pose = args.motions + (size_t)(2 * MOTION_DOUBLES) * q;
-          motion_load(m1, pose);
-          motion_load(m2, pose + MOTION_DOUBLES);
-          seedA = args.seedA ? args.seedA[q] : 0;
-          seedB = args.seedB ? args.seedB[q] : 0;
-          if (m1.w < 1e-8 && m2.w < 1e-8)
-          {
-            // translation-only branch of the reference (C2A.cpp:2391-2395): not implemented
-            if (args.out.status) args.out.status[q] = C2A_B200_QUERY_TRANSLATION_ONLY;
-            q = -1;  // stay in ADVANCE: claim another one next round
-          }
-          else
-          {
-            load9(r1, pose);
-            load3(tt1, pose + 9);
-            numCA = 0; nItrs = 0; nbv = 0; ntri = 0;
-            lamda = 0; lastLamda = 0; upbound = 1; mint = 1; dist = 0;
-            p1[0] = p1[1] = p1[2] = p2[0] = p2[1] = p2[2] = 0;
-            step_pending = true;
-          }
-        }
-      }
-
-      if (q >= 0 && step_pending)
-      {
-        // C2A_TimeOfContactStep, C2A.cpp:1791-1894
-        double R2[9], T2[3], Tt[3], Rt[9], g1[12], g2[12], R[9], T[3];
-        if (numCA == 0)
-        {
-          const double *rec2 = args.motions + (size_t)(2 * MOTION_DOUBLES) * q + MOTION_DOUBLES;
-          load9(R2, rec2); load3(T2, rec2 + 9);
-        }
-        else motion_pose(m2, lamda, R2, T2);
-        mt_m(Rrel, r1, R2);
-        v_sub(Tt, T2, tt1);
-        mt_v(Trel, r1, Tt);
-#pragma unroll
-        for (int i = 0; i < 12; i++) { g1[i] = __ldg(A.geom + i); g2[i] = __ldg(B.geom + i); }
-        m_m(Rt, Rrel, g2);
-        mt_m(R, g1, Rt);
-        m_v_p(Tt, Rrel, &g2[9], Trel);
-        v_sub(Tt, Tt, &g1[9]);
-        mt_v(T, g1, Tt);
-
-        double p[3], qq[3];
-        dist = tri_distance_nl(Rrel, Trel, A.tris + 9 * seedA, B.tris + 9 * seedB, p, qq);
-        if (numCA == 0) mint = 1;
-        if (mint <= 0.005 || dist <= 0.5 || numCA > 5) { abs_err = 0; rel_err = 0; }
-        else { abs_err = 1e+30; rel_err = (numCA <= 2) ? 3 : 0.5; }
-        mint = 1;
-
-        // root pair: always descended (d = -huge, mint = -1 pass every test)
-        double *e = stk;
-#pragma unroll
-        for (int i = 0; i < 9; i++) e[i] = R[i];
-        e[9] = T[0]; e[10] = T[1]; e[11] = T[2];
-        e[12] = -1e300; e[13] = -1.0;
-        e[14] = __hiloint2double(0, 0);
-        sp = 1;
-        step_pending = false;
-        state = ST_TRAVERSE;
-      }
-    }
-
-    // ------------------------------------------------------------------ TRAVERSE ---------
-    if (state == ST_TRAVERSE)
-    {
-      // pop until an entry passes the descend test with the CURRENT distance (C2A.cpp:1281-1351);
-      // entries that fail contribute their BV-level step bound
-      int b1 = -1, b2 = -1;
-      double R[9], T[3];
-      while (sp > 0)
-      {
-        const double *e = stk + (sp - 1) * ENTRY_DOUBLES;
-        sp--;
-        const double d = e[12], mt = e[13];
-        if (mt < upbound && ((d < (dist - abs_err)) || (d * (1 + rel_err) < dist)))
-        {
-          b1 = __double2hiint(e[14]); b2 = __double2loint(e[14]);
-#pragma unroll
-          for (int i = 0; i < 9; i++) R[i] = e[i];
-          T[0] = e[9]; T[1] = e[10]; T[2] = e[11];
-          break;
-        }
-        if (mt < mint) mint = mt;
-      }
-      if (b1 < 0) state = ST_ADVANCE;  // step finished
-      else
-      {
-        const NodeMeta ma = A.meta[b1], mb = B.meta[b2];
-        const bool l1 = ma.first_child < 0, l2 = mb.first_child < 0;
-        if (l1 && l2) { leaf_b1 = b1; leaf_b2 = b2; state = ST_LEAF; }
-        else
-        {
-          // expansion, C2A.cpp:1192-1279: two child pairs 'a' and 'c'
-          int a1, a2, c1, c2;
-          double Ra[9], Ta[3], Rc[9], Tc[3], d1, d2, mintb, minta;
-          if (l2 || (!l1 && (ma.size > mb.size)))
-          {
-            a1 = ma.first_child; a2 = b2; c1 = a1 + 1; c2 = b2;
-            const double *ga = A.geom + (size_t)a1 * GEOM_STRIDE, *gc = ga + GEOM_STRIDE;
-            const double *gb = B.geom + (size_t)b2 * GEOM_STRIDE;
-            double Rn[9], Tn[3], Tt[3];
-            load9(Rn, ga); load3(Tn, ga + 9);
-            mt_m(Ra, Rn, R); v_sub(Tt, T, Tn); mt_v(Ta, Rn, Tt);
-            load9(Rn, gc); load3(Tn, gc + 9);
-            mt_m(Rc, Rn, R); v_sub(Tt, T, Tn); mt_v(Tc, Rn, Tt);
-            child_test(Ra, Ta, ga, gb, A.rloc + (size_t)a1 * 9, r1, m1, m2, d1, mintb);
-            child_test(Rc, Tc, gc, gb, A.rloc + (size_t)c1 * 9, r1, m1, m2, d2, minta);
-          }
-          else
-          {
-            a1 = b1; a2 = mb.first_child; c1 = b1; c2 = a2 + 1;
-            const double *ga = B.geom + (size_t)a2 * GEOM_STRIDE, *gc = ga + GEOM_STRIDE;
-            const double *gb = A.geom + (size_t)b1 * GEOM_STRIDE;
-            double Rn[9], Tn[3];
-            load9(Rn, ga); load3(Tn, ga + 9);
-            m_m(Ra, R, Rn); m_v_p(Ta, R, Tn, T);
-            load9(Rn, gc); load3(Tn, gc + 9);
-            m_m(Rc, R, Rn); m_v_p(Tc, R, Tn, T);
-            child_test(Ra, Ta, gb, ga, A.rloc + (size_t)b1 * 9, r1, m1, m2, d1, mintb);
-            child_test(Rc, Tc, gb, gc, A.rloc + (size_t)b1 * 9, r1, m1, m2, d2, minta);
-          }
-          nbv += 2;
-          // push far child first, near child on top (visited first); ties visit 'a' first (d2 < d1 test)
-          const bool c_first = d2 < d1;
-          double *e0 = stk + sp * ENTRY_DOUBLES, *e1 = e0 + ENTRY_DOUBLES;
-          double *ea = c_first ? e0 : e1, *ec = c_first ? e1 : e0;
-#pragma unroll
-          for (int i = 0; i < 9; i++) { ea[i] = Ra[i]; ec[i] = Rc[i]; }
-#pragma unroll
-          for (int i = 0; i < 3; i++) { ea[9 + i] = Ta[i]; ec[9 + i] = Tc[i]; }
-          ea[12] = d1; ea[13] = mintb; ea[14] = __hiloint2double(a1, a2);
-          ec[12] = d2; ec[13] = minta; ec[14] = __hiloint2double(c1, c2);
-          sp += 2;
-        }
-      }
-    }
-
-    // ------------------------------------------------------------------ LEAF -------------
-    if (runL && state == ST_LEAF)
-    {
-      // C2A.cpp:1141-1183
-      double p[3], qq[3];
-      const int ta = -A.meta[leaf_b1].first_child - 1, tb = -B.meta[leaf_b2].first_child - 1;
-      const double dTri = tri_distance_nl(Rrel, Trel, A.tris + (size_t)9 * ta, B.tris + (size_t)9 * tb, p, qq);
-      if (dTri <= dist)
-      {
-        dist = dTri;
-        double w1[3], w2[3], S1[3], S2[3], tmp[3];
-        m_v(tmp, r1, p); v_add(w1, tmp, tt1);
-        m_v(tmp, r1, qq); v_add(w2, tmp, tt1);
-        v_sub(S1, w2, w1);
-        S2[0] = S1[0] * -1; S2[1] = S1[1] * -1; S2[2] = S1[2] * -1;
-        v_cpy(p1, p); v_cpy(p2, qq);
-        const double mb1 = motion_bound_leaf(m1, __ldg(A.geom + (size_t)leaf_b1 * GEOM_STRIDE + 15), S1);
-        const double mb2 = motion_bound_leaf(m2, __ldg(B.geom + (size_t)leaf_b2 * GEOM_STRIDE + 15), S2);
-        double mt = (dTri) / (mb1 + mb2);
-        if (mt < 0.0) mt = 0.0;
-        if (mt <= mint) mint = mt;
-      }
-      ntri++;
-      state = ST_TRAVERSE;
-    }
-  }
-}
 
 // ---- host side -----------------------------------------------------------------------------
 static thread_local std::string g_err;
@@ -594,18 +215,29 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   args.motions = poses; args.seedA = sa; args.seedB = sb; args.n = n;
   args.tol_d = tol_d; args.tol_t = tol_t; args.out = *out; args.counter = counter;
 
+  static std::atomic<bool> attr_set{false};
+  if (!attr_set.exchange(true))
+    CUDA_TRY(cudaFuncSetAttribute(c2a_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BLOCK_SMEM_BYTES));
   int sms = 0, per_sm = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, a->device));
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c2a_solve_kernel, BLOCK_THREADS, 0));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c2a_solve_kernel, BLOCK_THREADS, BLOCK_SMEM_BYTES));
   if (per_sm < 1) per_sm = 1;
-  long long blocks = (long long)sms * per_sm;  // persistent: one resident wave
-  const long long need = (n + BLOCK_THREADS - 1) / BLOCK_THREADS;
+  long long blocks = (long long)sms * per_sm;  // persistent: one resident wave (a multiple of the SM count)
+  const long long need = (n + WARPS_PER_BLOCK * Q - 1) / (WARPS_PER_BLOCK * Q);
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
+  // traversal stacks: one per query slot, depth(A)+depth(B)+2 entries of 128 B
+  args.stack_entries = a->depth + b->depth + 2;
+  const size_t stack_bytes = (size_t)blocks * WARPS_PER_BLOCK * Q * args.stack_entries * ENTRY_DOUBLES * sizeof(double);
+  double *stacks = nullptr;
+  CUDA_TRY(cudaMallocAsync(&stacks, stack_bytes, stream));
+  args.stacks = stacks;
   CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
-  c2a_solve_kernel<<<(unsigned)blocks, BLOCK_THREADS, 0, stream>>>(args);
+  c2a_solve_kernel<<<(unsigned)blocks, BLOCK_THREADS, BLOCK_SMEM_BYTES, stream>>>(args);
   g_launches.fetch_add(1);
-  CUDA_TRY(cudaGetLastError());
+  cudaError_t le = cudaGetLastError();
+  cudaFreeAsync(stacks, stream);
+  if (le != cudaSuccess) return fail(C2A_B200_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(le));
   return C2A_B200_OK;
 }
 
@@ -615,7 +247,7 @@ static int check_pair(const c2a_b200_model *a, const c2a_b200_model *b, int64_t 
   if (!a || !b || !out || (n > 0 && !poses)) return fail(C2A_B200_ERR_ARG, "NULL argument");
   if (n < 0) return fail(C2A_B200_ERR_ARG, "negative batch size");
   if (a->device != b->device) return fail(C2A_B200_ERR_DEVICE, "models live on different devices");
-  if (a->depth + b->depth + 2 > MAX_STACK)
+  if (a->depth + b->depth + 2 > 512)
     return fail(C2A_B200_ERR_DEPTH, "BVH depths exceed the traversal stack (" + std::to_string(a->depth) + "+" +
                                         std::to_string(b->depth) + ")");
   return C2A_B200_OK;
@@ -843,3 +475,64 @@ int c2a_b200_host_sincos(const double *x, int64_t n, double *s, double *c)
 }
 
 }  // extern "C"
+
+// ---- FP64 pipe peak probe (co-roofline denominator; MEASURED_PEAKS.json has no FP64 entry) ----
+namespace c2a {
+template <bool FMA>
+__global__ void k_fp64_peak(double *out, int iters)
+{
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++)
+  {
+    if (FMA)
+    {
+      a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+      a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+    }
+    else
+    {
+      a0 = __dadd_rn(__dmul_rn(a0, m), c); a1 = __dadd_rn(__dmul_rn(a1, m), c); a2 = __dadd_rn(__dmul_rn(a2, m), c);
+      a3 = __dadd_rn(__dmul_rn(a3, m), c); a4 = __dadd_rn(__dmul_rn(a4, m), c); a5 = __dadd_rn(__dmul_rn(a5, m), c);
+      a6 = __dadd_rn(__dmul_rn(a6, m), c); a7 = __dadd_rn(__dmul_rn(a7, m), c);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+}  // namespace c2a
+
+extern "C" int c2a_b200_fp64_peak(double *tflops_fma, double *tflops_mul_add)
+{
+  int sms = 0, dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = sms * 8, threads = 256, iters = 1 << 14;
+  double *out = nullptr;
+  CUDA_TRY(cudaMalloc(&out, (size_t)blocks * threads * 8));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double res[2] = {0, 0};
+  for (int mode = 0; mode < 2; mode++)
+  {
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++)
+    {
+      cudaEventRecord(e0);
+      if (mode == 0) k_fp64_peak<true><<<blocks, threads>>>(out, iters);
+      else k_fp64_peak<false><<<blocks, threads>>>(out, iters);
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (rep > 0 && ms < best) best = ms;
+    }
+    const double flops = 2.0 * 8 * (double)iters * blocks * threads;  // both modes: one mul + one add per element-op
+    res[mode] = flops / (best * 1e-3) / 1e12;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  CUDA_TRY(cudaGetLastError());
+  if (tflops_fma) *tflops_fma = res[0];
+  if (tflops_mul_add) *tflops_mul_add = res[1];
+  return C2A_B200_OK;
+}

@@ -1,0 +1,542 @@
+// Persistent warp-cooperative kernel: batched controlled conservative advancement (sm_100a, FP64).
+//
+// What runs on the device, per query (reference paths relative to /root/reference):
+//   C2A_QueryTimeOfContact  (the CA loop)        C2A/src/C2A.cpp:1987-2146
+//   C2A_TimeOfContactStep   (per-step set-up)    C2A/src/C2A.cpp:1778-1931
+//   TOCStepRecurse_Dis      (BVTT traversal)     C2A/src/C2A.cpp:1114-1354
+//   pose outputs of C2A_Solve                    C2A/src/C2A.cpp:2411-2429
+// with no host round trip between CA iterations.
+//
+// Execution model.  The traversal result is order dependent (res->distance shrinks as leaves are
+// visited and gates pruning, C2A.cpp:1281-1351), so every query commits node pairs in the reference's
+// depth-first order and parallelism is taken ACROSS queries and across the two child tests of one
+// expansion.  A warp owns a pool of Q query slots whose state lives in shared memory; lanes are
+// anonymous workers.  Each trip round the main loop the warp ballots the slot states and runs ONE
+// phase with as many lanes as it can fill:
+//   EXPAND   16 slots at a time, a lane PAIR per slot: both lanes fetch the slot's next node pair
+//            (the current entry in shared memory, else pop the slot's stack until an entry passes
+//            the descend test), then lane c runs child test c (transform, RSS distance, motion
+//            bounds); the pair exchanges (d, mint) by shuffle and commits: near child -> current
+//            entry, far child -> stack (only if it passes the descend test now: the distance only
+//            shrinks, so a child that fails now fails later and its step bound is folded at once).
+//   LEAF     one lane per slot waiting on a triangle pair: triangle distance + leaf motion bounds.
+//   ADVANCE  one lane per slot whose step ended or that is empty: CA-loop bookkeeping, result
+//            write-out, claim of the next query from a global atomic counter, next step's set-up.
+// Traversal stacks live in global memory (L2-resident), one 128-byte entry per pending far child.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/c2a_b200.h"
+#include "c2a_geom.cuh"
+#include "c2a_motion.cuh"
+
+namespace c2a {
+
+// ---- device-resident model ---------------------------------------------------------------
+// geom  [n][16]  R(9) Tr(3) l(2) r ang_radius      one 128-byte line per node; children adjacent
+// rloc  [n][9]   R_loc (only read when a BV distance is non-zero)
+// meta  [n]      {GetSize() = sqrt(l0^2+l1^2)+2r precomputed (PQP BV::GetSize), first_child}
+// tris  [n][9]
+constexpr int GEOM_STRIDE = 16;
+struct NodeMeta { double size; int first_child; int pad; };
+struct DevModel
+{
+  const double *geom;
+  const double *rloc;
+  const NodeMeta *meta;
+  const double *tris;
+  int n_nodes, n_tris;
+};
+
+constexpr int ENTRY_DOUBLES = 16;  // R(9) T(3) d mint {b1,b2} pad  -> 128 B
+constexpr int WARPS_PER_BLOCK = 4;
+constexpr int BLOCK_THREADS = 32 * WARPS_PER_BLOCK;
+constexpr int Q = 32;              // query slots per warp
+
+struct BatchArgs
+{
+  DevModel A, B;
+  const double *motions;  // [n][2][MOTION_DOUBLES], see c2a_motion.cuh
+  const int *seedA, *seedB;
+  long long n;
+  double tol_d, tol_t;
+  c2a_b200_results out;
+  unsigned long long *counter;
+  double *stacks;         // [n_slots][stack_entries][ENTRY_DOUBLES]
+  int stack_entries;
+};
+
+enum SlotState { ST_ADVANCE = 0, ST_TRAVERSE = 1, ST_LEAF = 2, ST_EXIT = 3 };
+
+// per-slot state in shared memory, structure of arrays [field][slot]
+enum
+{
+  F_R1 = 0,      // 9  current rotation of object 1 (objmotion1->transform)
+  F_TT1 = 9,     // 3  current translation of object 1
+  F_CV1 = 12, F_AX1 = 15, F_W1 = 18,   // motion 1: cv, m_axis, m_angVel
+  F_CV2 = 19, F_AX2 = 22, F_W2 = 25,   // motion 2
+  F_RREL = 26,   // 9  res->R
+  F_TREL = 35,   // 3  res->T
+  F_DIST = 38, F_MINT = 39, F_ABS = 40, F_REL = 41, F_UPB = 42,
+  F_CUR = 43,    // 12 current entry: R(9) T(3) of the node pair to visit next
+  F_LAMDA = 55, F_LASTL = 56,
+  F_P1 = 57, F_P2 = 60,
+  F_NDBL = 63
+};
+enum
+{
+  I_STATE = 0, I_SP, I_NBV, I_NTRI, I_NUMCA, I_NITRS, I_CURB1, I_CURB2, I_LEAFB1, I_LEAFB2, I_SEEDA, I_SEEDB,
+  I_QLO, I_QHI, I_PENDING, I_NINT = 16
+};
+constexpr size_t WARP_SMEM_BYTES = (size_t)F_NDBL * Q * 8 + (size_t)I_NINT * Q * 4;
+constexpr size_t BLOCK_SMEM_BYTES = WARP_SMEM_BYTES * WARPS_PER_BLOCK;
+
+C2A_DEV void load9(double d[9], const double *s)
+{
+#pragma unroll
+  for (int i = 0; i < 9; i++) d[i] = __ldg(s + i);
+}
+C2A_DEV void load3(double d[3], const double *s) { d[0] = __ldg(s); d[1] = __ldg(s + 1); d[2] = __ldg(s + 2); }
+
+__device__ __noinline__ double tri_distance_nl(const double R[9], const double T[3], const double *t1,
+                                               const double *t2, double p[3], double q[3])
+{
+  double a[9], b[9];
+  load9(a, t1);
+  load9(b, t2);
+  return tri_distance(R, T, a, b, p, q);
+}
+
+__global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const BatchArgs args)
+{
+  extern __shared__ double smem[];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *sd = smem + (size_t)warp * (WARP_SMEM_BYTES / 8);
+  int *si = reinterpret_cast<int *>(sd + (size_t)F_NDBL * Q);
+  const DevModel &A = args.A, &B = args.B;
+  double *const stack_base = args.stacks + ((size_t)(blockIdx.x * WARPS_PER_BLOCK + warp) * Q) * args.stack_entries * ENTRY_DOUBLES;
+  const size_t stack_stride = (size_t)args.stack_entries * ENTRY_DOUBLES;
+
+#define SD(f, s) sd[(f) * Q + (s)]
+#define SI(f, s) si[(f) * Q + (s)]
+
+  SI(I_STATE, lane) = ST_ADVANCE;
+  SI(I_QLO, lane) = -1; SI(I_QHI, lane) = -1;
+  SI(I_PENDING, lane) = 0;
+  __syncwarp();
+
+  while (true)
+  {
+    const int st = SI(I_STATE, lane);
+    const unsigned mT = __ballot_sync(FULL, st == ST_TRAVERSE);
+    const unsigned mL = __ballot_sync(FULL, st == ST_LEAF);
+    const unsigned mA = __ballot_sync(FULL, st == ST_ADVANCE);
+    if ((mT | mL | mA) == 0) break;
+    const int nT = __popc(mT), nL = __popc(mL), nA = __popc(mA);
+    // run the phase that fills the most lanes (an expansion uses two lanes per slot)
+    int phase;
+    {
+      const int fT = nT >= 16 ? 64 : 2 * nT;  // a full expansion pass always wins
+      phase = ST_TRAVERSE;
+      int best = fT;
+      if (nL > best) { best = nL; phase = ST_LEAF; }
+      if (nA > best) { best = nA; phase = ST_ADVANCE; }
+    }
+
+    if (phase == ST_TRAVERSE)
+    {
+      // -------------------------------------------------------------------- EXPAND ----------
+      const int j = lane >> 1, c = lane & 1;
+      if (j < nT)
+      {
+        const int slot = __fns(mT, 0, j + 1);
+        const unsigned pair = 3u << (lane & ~1);
+        double *stk = stack_base + (size_t)slot * stack_stride;
+        int b1 = SI(I_CURB1, slot), b2 = SI(I_CURB2, slot);
+        int sp = SI(I_SP, slot);
+        const double dist = SD(F_DIST, slot), abs_err = SD(F_ABS, slot), rel_err = SD(F_REL, slot), upbound = SD(F_UPB, slot);
+        double mint = SD(F_MINT, slot);
+        double R[9], T[3];
+        if (b1 >= 0)
+        {
+#pragma unroll
+          for (int i = 0; i < 9; i++) R[i] = SD(F_CUR + i, slot);
+#pragma unroll
+          for (int i = 0; i < 3; i++) T[i] = SD(F_CUR + 9 + i, slot);
+        }
+        else
+        {
+          // pop until an entry passes the descend test with the CURRENT distance (C2A.cpp:1281-1351);
+          // entries that fail contribute their BV-level step bound.  Both lanes of the pair do this
+          // redundantly on identical data.
+          while (sp > 0)
+          {
+            const double *e = stk + (size_t)(sp - 1) * ENTRY_DOUBLES;
+            sp--;
+            const double2 dm = *reinterpret_cast<const double2 *>(e + 12);
+            if (dm.y < upbound && ((dm.x < (dist - abs_err)) || (dm.x * (1 + rel_err) < dist)))
+            {
+              const double ids = e[14];
+              b1 = __double2hiint(ids); b2 = __double2loint(ids);
+#pragma unroll
+              for (int i = 0; i < 6; i++)
+              {
+                const double2 v = *reinterpret_cast<const double2 *>(e + 2 * i);
+                if (2 * i < 9) R[2 * i] = v.x; else T[2 * i - 9] = v.x;
+                if (2 * i + 1 < 9) R[2 * i + 1] = v.y; else T[2 * i + 1 - 9] = v.y;
+              }
+              break;
+            }
+            if (dm.y < mint) mint = dm.y;
+          }
+        }
+
+        if (b1 < 0)
+        {
+          // stack drained: this CA step's traversal is over
+          if (c == 0) { SD(F_MINT, slot) = mint; SI(I_SP, slot) = 0; SI(I_STATE, slot) = ST_ADVANCE; }
+        }
+        else
+        {
+          const NodeMeta ma = A.meta[b1], mb = B.meta[b2];
+          const bool l1 = ma.first_child < 0, l2 = mb.first_child < 0;
+          if (l1 && l2)
+          {
+            if (c == 0)
+            {
+              SD(F_MINT, slot) = mint; SI(I_SP, slot) = sp; SI(I_CURB1, slot) = -1;
+              SI(I_LEAFB1, slot) = b1; SI(I_LEAFB2, slot) = b2; SI(I_STATE, slot) = ST_LEAF;
+            }
+          }
+          else
+          {
+            // expansion, C2A.cpp:1192-1279: child pairs 'a' (lane c=0) and 'c' (lane c=1)
+            int n1, n2;  // node ids of my child pair
+            double Rc[9], Tc[3];
+            const double *gs, *gt, *rl;  // side-1 node geom, side-2 node geom, R_loc of the side-1 node
+            if (l2 || (!l1 && (ma.size > mb.size)))
+            {
+              n1 = ma.first_child + c; n2 = b2;
+              gs = A.geom + (size_t)n1 * GEOM_STRIDE; gt = B.geom + (size_t)b2 * GEOM_STRIDE;
+              rl = A.rloc + (size_t)n1 * 9;
+              double Rn[9], Tn[3], Tt[3];
+              load9(Rn, gs); load3(Tn, gs + 9);
+              mt_m(Rc, Rn, R); v_sub(Tt, T, Tn); mt_v(Tc, Rn, Tt);
+            }
+            else
+            {
+              n1 = b1; n2 = mb.first_child + c;
+              gs = A.geom + (size_t)b1 * GEOM_STRIDE; gt = B.geom + (size_t)n2 * GEOM_STRIDE;
+              rl = A.rloc + (size_t)b1 * 9;
+              double Rn[9], Tn[3];
+              load9(Rn, gt); load3(Tn, gt + 9);
+              m_m(Rc, R, Rn); m_v_p(Tc, R, Tn, T);
+            }
+            // child BV test (C2A.cpp:1237-1276): RSS distance, direction to world frame, the two
+            // directional motion bounds, the child's conservative step bound
+            double d, mt = 0.0;
+            {
+              double S[3];
+              const double a0 = __ldg(gs + 12), a1 = __ldg(gs + 13), ra = __ldg(gs + 14);
+              const double e0 = __ldg(gt + 12), e1 = __ldg(gt + 13), rb = __ldg(gt + 14);
+              d = rss_rect_dist(Rc, Tc, a0, a1, e0, e1, S);
+              d -= (ra + rb);
+              d = (d < 0.0) ? 0.0 : d;
+              if (d != 0.0)
+              {
+                double Rl[9], tmp[3], S1[3], S2[3], r1[9];
+                load9(Rl, rl);
+                m_v(tmp, Rl, S);
+#pragma unroll
+                for (int i = 0; i < 9; i++) r1[i] = SD(F_R1 + i, slot);
+                m_v(S1, r1, tmp);
+                S2[0] = S1[0] * -1; S2[1] = S1[1] * -1; S2[2] = S1[2] * -1;
+                Motion m;  // only cv, axis, w are read by the bound
+#pragma unroll
+                for (int i = 0; i < 3; i++) { m.cv[i] = SD(F_CV1 + i, slot); m.axis[i] = SD(F_AX1 + i, slot); }
+                m.w = SD(F_W1, slot);
+                const double mb1 = motion_bound_bv(m, __ldg(gs + 15), S1);
+#pragma unroll
+                for (int i = 0; i < 3; i++) { m.cv[i] = SD(F_CV2 + i, slot); m.axis[i] = SD(F_AX2 + i, slot); }
+                m.w = SD(F_W2, slot);
+                const double mb2 = motion_bound_bv(m, __ldg(gt + 15), S2);
+                mt = (d) / (mb1 + mb2);
+                if (mt <= 0) mt = 0.0;
+              }
+            }
+            // commit in the reference's order: the child with the smaller d is visited first; ties
+            // visit 'a' first (the test is d2 < d1)
+            const double d_o = __shfl_xor_sync(pair, d, 1), mt_o = __shfl_xor_sync(pair, mt, 1);
+            const bool v = mt < upbound && ((d < (dist - abs_err)) || (d * (1 + rel_err) < dist));
+            const bool v_o = mt_o < upbound && ((d_o < (dist - abs_err)) || (d_o * (1 + rel_err) < dist));
+            const double d1 = c ? d_o : d, d2 = c ? d : d_o;
+            const bool c_first = d2 < d1;
+            const bool near = (c == 1) == c_first;
+            const bool v_near = near ? v : v_o, v_far = near ? v_o : v;
+            if (v)
+            {
+              if (near || !v_near)
+              {
+#pragma unroll
+                for (int i = 0; i < 9; i++) SD(F_CUR + i, slot) = Rc[i];
+#pragma unroll
+                for (int i = 0; i < 3; i++) SD(F_CUR + 9 + i, slot) = Tc[i];
+                SI(I_CURB1, slot) = n1; SI(I_CURB2, slot) = n2;
+              }
+              else
+              {
+                double *e = stk + (size_t)sp * ENTRY_DOUBLES;
+                double2 *e2 = reinterpret_cast<double2 *>(e);
+                e2[0] = make_double2(Rc[0], Rc[1]); e2[1] = make_double2(Rc[2], Rc[3]);
+                e2[2] = make_double2(Rc[4], Rc[5]); e2[3] = make_double2(Rc[6], Rc[7]);
+                e2[4] = make_double2(Rc[8], Tc[0]); e2[5] = make_double2(Tc[1], Tc[2]);
+                e2[6] = make_double2(d, mt); e2[7] = make_double2(__hiloint2double(n1, n2), 0.0);
+              }
+            }
+            if (c == 0)
+            {
+              if (!v && mt < mint) mint = mt;
+              if (!v_o && mt_o < mint) mint = mt_o;
+              SD(F_MINT, slot) = mint;
+              SI(I_SP, slot) = sp + ((v_near && v_far) ? 1 : 0);
+              SI(I_NBV, slot) = SI(I_NBV, slot) + 2;
+              if (!v && !v_o) SI(I_CURB1, slot) = -1;
+            }
+          }
+        }
+      }
+    }
+    else if (phase == ST_LEAF)
+    {
+      // ---------------------------------------------------------------------- LEAF -----------
+      // C2A.cpp:1141-1183
+      if (lane < nL)
+      {
+        const int slot = __fns(mL, 0, lane + 1);
+        const int b1 = SI(I_LEAFB1, slot), b2 = SI(I_LEAFB2, slot);
+        double Rrel[9], Trel[3], p[3], qq[3];
+#pragma unroll
+        for (int i = 0; i < 9; i++) Rrel[i] = SD(F_RREL + i, slot);
+#pragma unroll
+        for (int i = 0; i < 3; i++) Trel[i] = SD(F_TREL + i, slot);
+        const int ta = -A.meta[b1].first_child - 1, tb = -B.meta[b2].first_child - 1;
+        const double dTri = tri_distance_nl(Rrel, Trel, A.tris + (size_t)9 * ta, B.tris + (size_t)9 * tb, p, qq);
+        if (dTri <= SD(F_DIST, slot))
+        {
+          SD(F_DIST, slot) = dTri;
+          double r1[9], tt1[3], w1[3], w2[3], S1[3], S2[3], tmp[3];
+#pragma unroll
+          for (int i = 0; i < 9; i++) r1[i] = SD(F_R1 + i, slot);
+#pragma unroll
+          for (int i = 0; i < 3; i++) tt1[i] = SD(F_TT1 + i, slot);
+          m_v(tmp, r1, p); v_add(w1, tmp, tt1);
+          m_v(tmp, r1, qq); v_add(w2, tmp, tt1);
+          v_sub(S1, w2, w1);
+          S2[0] = S1[0] * -1; S2[1] = S1[1] * -1; S2[2] = S1[2] * -1;
+#pragma unroll
+          for (int i = 0; i < 3; i++) { SD(F_P1 + i, slot) = p[i]; SD(F_P2 + i, slot) = qq[i]; }
+          Motion m;
+#pragma unroll
+          for (int i = 0; i < 3; i++) { m.cv[i] = SD(F_CV1 + i, slot); m.axis[i] = SD(F_AX1 + i, slot); }
+          m.w = SD(F_W1, slot);
+          const double mb1 = motion_bound_leaf(m, __ldg(A.geom + (size_t)b1 * GEOM_STRIDE + 15), S1);
+#pragma unroll
+          for (int i = 0; i < 3; i++) { m.cv[i] = SD(F_CV2 + i, slot); m.axis[i] = SD(F_AX2 + i, slot); }
+          m.w = SD(F_W2, slot);
+          const double mb2 = motion_bound_leaf(m, __ldg(B.geom + (size_t)b2 * GEOM_STRIDE + 15), S2);
+          double mt = (dTri) / (mb1 + mb2);
+          if (mt < 0.0) mt = 0.0;
+          if (mt <= SD(F_MINT, slot)) SD(F_MINT, slot) = mt;
+        }
+        SI(I_NTRI, slot) = SI(I_NTRI, slot) + 1;
+        SI(I_STATE, slot) = ST_TRAVERSE;
+      }
+    }
+    else
+    {
+      // -------------------------------------------------------------------- ADVANCE ----------
+      // CA-loop bookkeeping after a finished step / result write-out / claim / next step's set-up
+      if (lane < nA)
+      {
+        const int slot = __fns(mA, 0, lane + 1);
+        long long q = ((long long)SI(I_QHI, slot) << 32) | (unsigned)SI(I_QLO, slot);
+        bool pending = SI(I_PENDING, slot) != 0;
+        int numCA = SI(I_NUMCA, slot);
+        double lamda = SD(F_LAMDA, slot);
+        Motion m1, m2;
+        if (q >= 0 && !pending)
+        {
+          // a step just ended: C2A_QueryTimeOfContact's loop, C2A.cpp:2053-2123
+          const double *rec = args.motions + (size_t)(2 * MOTION_DOUBLES) * q;
+          const double dist = SD(F_DIST, slot), mint = SD(F_MINT, slot);
+          double lastLamda = SD(F_LASTL, slot);
+          int nItrs = SI(I_NITRS, slot);
+          bool finished = false, hit = false;
+          if (numCA == 0) { numCA = 1; lastLamda = mint; }
+          if (!(dist > args.tol_d)) { finished = true; hit = true; }
+          else
+          {
+            nItrs++;
+            if (nItrs > 150) { finished = true; hit = true; }
+            else if (mint >= 1.0) { finished = true; hit = false; }
+            else
+            {
+              const double dlamda = mint;
+              if (dlamda < args.tol_t) { finished = true; hit = true; }
+              else
+              {
+                lamda += dlamda;
+                if (lamda >= 1.0) { finished = true; hit = false; }
+                else
+                {
+                  lastLamda = lamda;
+                  numCA++;
+                  SD(F_UPB, slot) = 1.0 - lamda;
+                  pending = true;
+                }
+              }
+            }
+          }
+          SI(I_NITRS, slot) = nItrs;
+          SD(F_LASTL, slot) = lastLamda;
+          if (finished)
+          {
+            // C2A.cpp:2125-2143 and the pose outputs of C2A_Solve :2411-2429
+            double toc = 0.0;
+            const c2a_b200_results &o = args.out;
+            if (hit)
+            {
+              toc = lastLamda;
+              if (toc >= 1 - args.tol_t) toc = 0;
+              if (o.pose_toc)
+              {
+                double R[9], T[3];
+                motion_load(m1, rec);
+                motion_pose(m1, toc, R, T);
+#pragma unroll
+                for (int i = 0; i < 9; i++) o.pose_toc[24 * q + i] = R[i];
+#pragma unroll
+                for (int i = 0; i < 3; i++) o.pose_toc[24 * q + 9 + i] = T[i];
+                motion_load(m2, rec + MOTION_DOUBLES);
+                motion_pose(m2, toc, R, T);
+#pragma unroll
+                for (int i = 0; i < 9; i++) o.pose_toc[24 * q + 12 + i] = R[i];
+#pragma unroll
+                for (int i = 0; i < 3; i++) o.pose_toc[24 * q + 21 + i] = T[i];
+              }
+            }
+            if (o.status) o.status[q] = C2A_B200_QUERY_OK;
+            if (o.collisionfree) o.collisionfree[q] = hit ? 0 : 1;
+            if (o.num_ca) o.num_ca[q] = numCA;
+            if (o.num_bv_tests) o.num_bv_tests[q] = SI(I_NBV, slot);
+            if (o.num_tri_tests) o.num_tri_tests[q] = SI(I_NTRI, slot);
+            if (o.toc) o.toc[q] = toc;
+            if (o.distance) o.distance[q] = dist;
+            if (o.mint) o.mint[q] = mint;
+            if (o.p1p2)
+            {
+#pragma unroll
+              for (int i = 0; i < 3; i++) { o.p1p2[6 * q + i] = SD(F_P1 + i, slot); o.p1p2[6 * q + 3 + i] = SD(F_P2 + i, slot); }
+            }
+            q = -1;
+          }
+        }
+
+        if (q < 0)
+        {
+          // claim the next query
+          const long long nq = (long long)atomicAdd(args.counter, 1ull);
+          if (nq >= args.n) SI(I_STATE, slot) = ST_EXIT;
+          else
+          {
+            q = nq;
+            const double *rec = args.motions + (size_t)(2 * MOTION_DOUBLES) * q;
+            const double w1 = __ldg(rec + 18), w2 = __ldg(rec + MOTION_DOUBLES + 18);
+            if (w1 < 1e-8 && w2 < 1e-8)
+            {
+              // translation-only branch of the reference (C2A.cpp:2391-2395): not implemented
+              if (args.out.status) args.out.status[q] = C2A_B200_QUERY_TRANSLATION_ONLY;
+              q = -1;  // stay in ADVANCE: claim another one next round
+            }
+            else
+            {
+#pragma unroll
+              for (int i = 0; i < 3; i++)
+              {
+                SD(F_CV1 + i, slot) = __ldg(rec + 12 + i); SD(F_AX1 + i, slot) = __ldg(rec + 15 + i);
+                SD(F_CV2 + i, slot) = __ldg(rec + MOTION_DOUBLES + 12 + i); SD(F_AX2 + i, slot) = __ldg(rec + MOTION_DOUBLES + 15 + i);
+              }
+              SD(F_W1, slot) = w1; SD(F_W2, slot) = w2;
+              SI(I_SEEDA, slot) = args.seedA ? args.seedA[q] : 0;
+              SI(I_SEEDB, slot) = args.seedB ? args.seedB[q] : 0;
+              numCA = 0; lamda = 0;
+              SI(I_NITRS, slot) = 0; SI(I_NBV, slot) = 0; SI(I_NTRI, slot) = 0;
+              SD(F_LASTL, slot) = 0; SD(F_UPB, slot) = 1; SD(F_MINT, slot) = 1; SD(F_DIST, slot) = 0;
+#pragma unroll
+              for (int i = 0; i < 3; i++) { SD(F_P1 + i, slot) = 0; SD(F_P2 + i, slot) = 0; }
+              pending = true;
+            }
+          }
+          SI(I_QLO, slot) = (int)(unsigned)(q & 0xffffffffll); SI(I_QHI, slot) = (int)(q >> 32);
+        }
+
+        if (q >= 0 && pending)
+        {
+          // C2A_TimeOfContactStep, C2A.cpp:1791-1894
+          const double *rec = args.motions + (size_t)(2 * MOTION_DOUBLES) * q;
+          double r1[9], tt1[3], R2[9], T2[3], Tt[3], Rt[9], g1[12], g2[12], R[9], T[3], Rrel[9], Trel[3];
+          if (numCA == 0)
+          {
+            load9(r1, rec); load3(tt1, rec + 9);
+            load9(R2, rec + MOTION_DOUBLES); load3(T2, rec + MOTION_DOUBLES + 9);
+          }
+          else
+          {
+            motion_load(m1, rec);
+            motion_pose(m1, lamda, r1, tt1);
+            motion_load(m2, rec + MOTION_DOUBLES);
+            motion_pose(m2, lamda, R2, T2);
+          }
+          mt_m(Rrel, r1, R2);
+          v_sub(Tt, T2, tt1);
+          mt_v(Trel, r1, Tt);
+#pragma unroll
+          for (int i = 0; i < 12; i++) { g1[i] = __ldg(A.geom + i); g2[i] = __ldg(B.geom + i); }
+          m_m(Rt, Rrel, g2);
+          mt_m(R, g1, Rt);
+          m_v_p(Tt, Rrel, &g2[9], Trel);
+          v_sub(Tt, Tt, &g1[9]);
+          mt_v(T, g1, Tt);
+
+          double p[3], qq[3];
+          const double dist = tri_distance_nl(Rrel, Trel, A.tris + (size_t)9 * SI(I_SEEDA, slot),
+                                              B.tris + (size_t)9 * SI(I_SEEDB, slot), p, qq);
+          double mint = SD(F_MINT, slot);
+          if (numCA == 0) mint = 1;
+          if (mint <= 0.005 || dist <= 0.5 || numCA > 5) { SD(F_ABS, slot) = 0; SD(F_REL, slot) = 0; }
+          else { SD(F_ABS, slot) = 1e+30; SD(F_REL, slot) = (numCA <= 2) ? 3 : 0.5; }
+          SD(F_MINT, slot) = 1;
+          SD(F_DIST, slot) = dist;
+#pragma unroll
+          for (int i = 0; i < 9; i++) { SD(F_R1 + i, slot) = r1[i]; SD(F_RREL + i, slot) = Rrel[i]; SD(F_CUR + i, slot) = R[i]; }
+#pragma unroll
+          for (int i = 0; i < 3; i++) { SD(F_TT1 + i, slot) = tt1[i]; SD(F_TREL + i, slot) = Trel[i]; SD(F_CUR + 9 + i, slot) = T[i]; }
+          // the root pair is descended unconditionally
+          SI(I_CURB1, slot) = 0; SI(I_CURB2, slot) = 0; SI(I_SP, slot) = 0;
+          pending = false;
+          SI(I_STATE, slot) = ST_TRAVERSE;
+        }
+        SI(I_NUMCA, slot) = numCA;
+        SD(F_LAMDA, slot) = lamda;
+        SI(I_PENDING, slot) = pending ? 1 : 0;
+      }
+    }
+    __syncwarp();
+  }
+#undef SD
+#undef SI
+}
+
+}  // namespace c2a

@@ -54,6 +54,18 @@ typedef struct c2a_b200_bvh
 } c2a_b200_bvh;
 
 typedef struct c2a_b200_model c2a_b200_model; /* device-resident model, opaque */
+typedef struct c2a_b200_host_bvh c2a_b200_host_bvh; /* host-resident built hierarchy, opaque */
+
+/* Host-side BVH build: what C2A_Model::BeginModel / AddTri / EndModel do for the CCD path
+ * (C2A/src/C2A_PQP.cpp:82-121,228-290,331-417 -> C2A_BuildModel C2A/src/C2A_Build.cpp:546-574).
+ * tris9: [n_tris][9] = p1,p2,p3 in AddTri order.  The tree is bit-identical to the reference's.
+ * c2a_b200_bvh_view fills `view` with pointers into the built hierarchy (valid until
+ * c2a_b200_bvh_free); tri_ids [n_tris] maps the builder's permuted triangle order back to the AddTri
+ * index (PQP Tri::id). */
+int c2a_b200_bvh_build(const double *tris9, int32_t n_tris, c2a_b200_host_bvh **out);
+int c2a_b200_bvh_view(const c2a_b200_host_bvh *h, struct c2a_b200_bvh *view, const int32_t **tri_ids,
+                      int32_t *depth);
+int c2a_b200_bvh_free(c2a_b200_host_bvh *h);
 
 /* Per-query outputs, structure of arrays; any pointer may be NULL to skip that output.
  * Host pointers for c2a_b200_solve_batch, device pointers for c2a_b200_solve_batch_device. */

@@ -1,0 +1,73 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _native_built():
+    """Build the product library (nvcc cross-compiles without a GPU) and the CPU oracle once."""
+    from c2a_b200 import build as c2a_build
+    import oracle
+    c2a_build.build()
+    oracle.build_oracle()
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return load_golden
+
+
+@pytest.fixture(scope="session")
+def bunny_tris():
+    m = np.load(os.path.join(GOLDEN, "bunny_mesh.npz"))
+    return m["verts"][m["vidx"]].reshape(-1, 9).copy()
+
+
+@pytest.fixture(scope="session")
+def bvhs(bunny_tris):
+    """Hierarchies built by the PRODUCT's host builder (bit-identical to the reference's, see
+    test_host_side.py::test_bvh_matches_reference_digest), cached per session."""
+    from c2a_b200 import api, meshes
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            if name == "bunny":
+                cache[name] = api.build_bvh(bunny_tris)
+            else:
+                nu, nv = (int(x) for x in name.split("_")[1].split("x"))
+                cache[name] = api.build_bvh(meshes.torus_knot(nu, nv)[0])
+        return cache[name]
+    return get
+
+
+@pytest.fixture(scope="session")
+def bvh_digest():
+    with open(os.path.join(GOLDEN, "bvh_digest.json")) as f:
+        return json.load(f)
+
+
+GOLDEN_CASES = [  # (fixture, model A, model B)
+    ("ref_demo_bunny", "bunny", "bunny"),
+    ("ref_bunny_approach", "bunny", "bunny"),
+    ("ref_knot_128x16", "knot_128x16", "knot_128x16"),
+    ("ref_knot_512x32", "knot_512x32", "knot_512x32"),
+    ("ref_knot_1024x32", "knot_1024x32", "knot_1024x32"),
+    ("ref_bunny_vs_knot_seeded", "bunny", "knot_512x32"),
+]

@@ -1,0 +1,228 @@
+"""GPU parity tests (pytest -m gpu, on the B200 box).  Everything goes through the C ABI of
+include/c2a_b200.h; the oracle port and the committed reference fixtures are the checkers.
+
+Bar: the path is FP64 with data-dependent branching, and every device expression keeps the reference's
+rounding sequence, so the comparison is BIT-EXACT (stronger than the contract of BASELINE.json:
+identical verdict, |toc - toc_ref| <= tolerance_t, distance within 1e-9 relative)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+from c2a_b200 import api, meshes, workloads
+from conftest import GOLDEN_CASES
+from test_oracle import rect_cases, tri_cases
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = (("collisionfree", "collisionfree"), ("num_ca", "numCA"), ("num_bv_tests", "num_bv_tests"),
+          ("num_tri_tests", "num_tri_tests"), ("toc", "toc"), ("distance", "distance"), ("mint", "mint"),
+          ("pose_toc", "pose_toc"))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def models(bvhs):
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = api.Model(bvhs(name), 0)
+        return cache[name]
+    return get
+
+
+def assert_contract(got, ref, tol_t):
+    """BASELINE.json's contract, checked explicitly besides the bit-exact comparison."""
+    assert (got["status"] == 0).all()
+    assert np.array_equal(got["collisionfree"], ref["collisionfree"])
+    assert (np.abs(got["toc"] - ref["toc"]) <= tol_t).all()
+    assert (np.abs(got["distance"] - ref["distance"]) <= 1e-9 * np.maximum(1.0, np.abs(ref["distance"]))).all()
+
+
+# ---------------------------------------------------------------- device functions ----------
+def test_device_sincos_match_libm():
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-3.3, 3.3, 400000), rng.uniform(-0.13, 0.13, 100000), rng.uniform(-1e4, 1e4, 100000),
+                        np.array([0.0, -0.0, 0.126, 1 / 128, 0.85546875, 2.426265, math.pi, 2 ** -26, 2 ** -27])])
+    s = np.zeros_like(x); c = np.zeros_like(x)
+    api._check(api.lib().c2a_b200_test_sincos(_p(x), C.c_int64(len(x)), _p(s), _p(c)))
+    ms = np.array([math.sin(v) for v in x]); mc = np.array([math.cos(v) for v in x])
+    assert np.array_equal(s, ms) and np.array_equal(c, mc)
+
+
+def test_device_rect_dist_matches_oracle():
+    rng = np.random.default_rng(21)
+    cases = rect_cases(rng, 20000)
+    n = len(cases)
+    R = np.array([c[0] for c in cases]); T = np.array([c[1] for c in cases])
+    ab = np.array([np.concatenate([c[2], c[3]]) for c in cases])
+    dist = np.zeros(n); S = np.full((n, 3), np.nan)
+    api._check(api.lib().c2a_b200_test_rect_dist(_p(R), _p(T), _p(ab), C.c_int64(n), _p(dist), _p(S)))
+    P = oracle.port()
+    for i in range(n):
+        d, _, _, s = P.rect_dist(R[i], T[i], ab[i, :2], ab[i, 2:])
+        assert d == dist[i], i
+        assert np.array_equal(s, S[i], equal_nan=True), i
+    assert (dist == 0).sum() > 100 and (dist > 0).sum() > 1000
+
+
+def test_device_tri_distance_matches_oracle():
+    rng = np.random.default_rng(22)
+    cases = tri_cases(rng, 20000)
+    n = len(cases)
+    R = np.array([c[0] for c in cases]); T = np.array([c[1] for c in cases])
+    t1 = np.array([c[2] for c in cases]); t2 = np.array([c[3] for c in cases])
+    dist = np.zeros(n); pq = np.zeros((n, 6))
+    api._check(api.lib().c2a_b200_test_tri_distance(_p(R), _p(T), _p(t1), _p(t2), C.c_int64(n), _p(dist), _p(pq)))
+    P = oracle.port()
+    for i in range(n):
+        d, p, q = P.tri_distance(R[i], T[i], t1[i], t2[i])
+        assert d == dist[i] or (math.isnan(d) and math.isnan(dist[i])), i
+        assert np.array_equal(np.concatenate([p, q]), pq[i], equal_nan=True), i
+    assert (dist == 0).sum() > 100
+
+
+def test_device_motion_matches_oracle():
+    """integrate() and both motion bounds against the oracle port."""
+    rng = np.random.default_rng(23)
+    n = 5000
+    poses = workloads.approach_batch(n, 99)
+    rec = np.ascontiguousarray(api.motions_from_poses(poses)[:, :24])
+    t = rng.uniform(0, 1.2, n); ar = rng.uniform(0, 200, n); d = rng.normal(size=(n, 3))
+    d[::50] = 0.0  # zero direction -> NaN normalisation, like a zero triangle distance (quirk Q7)
+    out = np.zeros((n, 14))
+    api._check(api.lib().c2a_b200_test_motion(_p(rec), _p(t), _p(ar), _p(d), C.c_int64(n), _p(out)))
+
+    class M(C.Structure):
+        _fields_ = [("Rs", C.c_double * 9), ("Ts", C.c_double * 3), ("Re", C.c_double * 9), ("Te", C.c_double * 3),
+                    ("cv", C.c_double * 3), ("axis", C.c_double * 3), ("w", C.c_double), ("Rc", C.c_double * 9), ("Tc", C.c_double * 3)]
+    L = oracle.port().lib
+    for i in range(n):
+        p = np.ascontiguousarray(poses[i, :24]); m = M()
+        L.orc_motion_init(C.byref(m), _p(p[0:]), _p(p[9:]), _p(p[12:]), _p(p[21:]))
+        L.orc_motion_integrate(C.byref(m), C.c_double(t[i]), None)
+        assert list(m.Rc) == list(out[i, :9]) and list(m.Tc) == list(out[i, 9:12]), i
+        n1 = d[i].copy(); n2 = d[i].copy()
+        b1 = L.orc_motion_bound_bv(C.byref(m), C.c_double(ar[i]), _p(n1))
+        b2 = L.orc_motion_bound_leaf(C.byref(m), C.c_double(ar[i]), _p(n2))
+        assert np.array_equal(np.array([b1, b2]), out[i, 12:14], equal_nan=True), i
+
+
+# ---------------------------------------------------------------- whole queries -------------
+@pytest.mark.parametrize("case,ma,mb", GOLDEN_CASES)
+def test_golden_bit_exact(case, ma, mb, golden, models):
+    """Every query of every committed reference fixture, through c2a_b200_solve_batch (host buffers)."""
+    g = golden(case)
+    tol_d, tol_t = float(g["tol_d"]), float(g["tol_t"])
+    got = api.solve_batch(models(ma), models(mb), g["poses"], g.get("seed_a"), g.get("seed_b"), tol_d, tol_t)
+    assert_contract(got, g, tol_t)
+    for a, b in FIELDS:
+        assert np.array_equal(got[a], g[b]), (case, a, int((got[a] != g[b]).sum()))
+    upd = g["num_tri_tests"] > 0
+    same = (got["p1p2"] == g["p1p2"]).all(1)
+    assert same[upd & (got["p1p2"] != 0).any(1)].all()
+
+
+def test_fresh_batch_against_oracle_port(models, bvhs):
+    """Inputs that are in no fixture: GPU vs the oracle port run here, bit-exact."""
+    poses = workloads.approach_batch(300, 777, radius=workloads.KNOT_RADIUS, max_turn=3.1)
+    ref = oracle.port().solve_batch(bvhs("knot_128x16"), bvhs("knot_128x16"), poses, threads=8)
+    got = api.solve_batch(models("knot_128x16"), models("knot_128x16"), poses)
+    assert_contract(got, ref, 1e-4)
+    for a, b in FIELDS:
+        assert np.array_equal(got[a], ref[b]), a
+
+
+def test_tolerance_sweep_against_oracle_port(models, bvhs):
+    """config 5 flavour: tolerance_t from 1e-3 to 1e-6 through the exposed tolerances."""
+    poses = workloads.approach_batch(120, 31337, radius=workloads.KNOT_RADIUS)
+    for tol_t in (1e-3, 1e-5, 1e-6):
+        ref = oracle.port().solve_batch(bvhs("knot_128x16"), bvhs("knot_128x16"), poses, tol_d=1e-4, tol_t=tol_t, threads=8)
+        got = api.solve_batch(models("knot_128x16"), models("knot_128x16"), poses, tol_d=1e-4, tol_t=tol_t)
+        assert_contract(got, ref, tol_t)
+        for a, b in FIELDS:
+            assert np.array_equal(got[a], ref[b]), (tol_t, a)
+
+
+def test_device_resident_entry_matches_host_entry(models, golden):
+    """c2a_b200_solve_batch_device with torch tensors == the host-buffer entry."""
+    import torch
+    g = golden("ref_knot_512x32")
+    n = 700
+    m = models("knot_512x32")
+    host = api.solve_batch(m, m, g["poses"][:n])
+    mot = torch.from_numpy(api.motions_from_poses(g["poses"][:n])).cuda()
+    out = {"status": torch.full((n,), -7, dtype=torch.int32, device="cuda"),
+           "collisionfree": torch.zeros(n, dtype=torch.int32, device="cuda"),
+           "num_ca": torch.zeros(n, dtype=torch.int32, device="cuda"),
+           "toc": torch.zeros(n, dtype=torch.float64, device="cuda"),
+           "distance": torch.zeros(n, dtype=torch.float64, device="cuda"),
+           "pose_toc": torch.zeros(n, 24, dtype=torch.float64, device="cuda")}
+    stream = torch.cuda.current_stream()
+    api.solve_batch_device(m, m, mot.data_ptr(), n, {k: v.data_ptr() for k, v in out.items()}, stream=stream.cuda_stream)
+    torch.cuda.synchronize()
+    for k, v in out.items():
+        assert np.array_equal(v.cpu().numpy(), host[k]), k
+
+
+def test_edge_cases(models):
+    m = models("knot_128x16")
+    # empty batch
+    got = api.solve_batch(m, m, np.zeros((0, 48)))
+    assert got["toc"].shape == (0,)
+    # a single query
+    one = workloads.approach_batch(1, 1, radius=workloads.KNOT_RADIUS)
+    assert api.solve_batch(m, m, one)["status"][0] == 0
+    # ragged sizes around the warp / block size
+    for n in (31, 32, 33, 127, 129):
+        p = workloads.approach_batch(n, n, radius=workloads.KNOT_RADIUS)
+        a = api.solve_batch(m, m, p)
+        b = api.solve_batch(m, m, p[::-1].copy())
+        assert np.array_equal(a["toc"], b["toc"][::-1]) and np.array_equal(a["num_bv_tests"], b["num_bv_tests"][::-1])
+    # pure translation: the reference switches branch (C2A.cpp:2391-2395); reported, not silently mis-solved
+    p = workloads.approach_batch(4, 2, radius=workloads.KNOT_RADIUS)
+    p[1, 12:21] = p[1, 0:9]
+    got = api.solve_batch(m, m, p)
+    assert list(got["status"]) == [0, 1, 0, 0]
+    # bad seeds / mismatched devices are argument errors, not crashes
+    with pytest.raises(api.C2AError):
+        api._check(api.lib().c2a_b200_solve_batch(m.h, None, None, None, None, C.c_int64(1), C.c_double(1e-4), C.c_double(1e-4), None))
+
+
+def test_large_batch_properties(models):
+    """At a size the CPU oracle cannot check query by query: size-independent properties.
+    (i) the dynamic scheduler is order independent: a permuted batch gives the permuted results;
+    (ii) repeat runs are identical; (iii) verdict/toc invariants; (iv) a CPU-checked random sample."""
+    n = 120000
+    m = models("knot_512x32")
+    poses = workloads.approach_batch(n, 20260002, radius=workloads.KNOT_RADIUS)
+    f = ("status", "collisionfree", "toc", "distance", "num_ca", "num_bv_tests", "num_tri_tests")
+    a = api.solve_batch(m, m, poses, fields=f)
+    perm = np.random.default_rng(1).permutation(n)
+    b = api.solve_batch(m, m, poses[perm], fields=f)
+    for k in f:
+        assert np.array_equal(a[k][perm], b[k]), k
+    assert (a["status"] == 0).all()
+    free = a["collisionfree"] == 1
+    assert (a["toc"][free] == 0).all() and ((a["toc"] >= 0) & (a["toc"] < 1)).all()
+    assert (a["num_ca"] >= 1).all() and (a["num_ca"] <= 152).all()
+    assert (a["distance"][~free] >= 0).all()
+    assert 0.85 < (~free).mean() < 0.999
+
+
+def test_large_batch_sample_against_oracle(models, bvhs):
+    n = 120000
+    poses = workloads.approach_batch(n, 20260002, radius=workloads.KNOT_RADIUS)
+    idx = np.random.default_rng(2).choice(n, 400, replace=False)
+    m = models("knot_512x32")
+    got = api.solve_batch(m, m, poses[idx])
+    ref = oracle.port().solve_batch(bvhs("knot_512x32"), bvhs("knot_512x32"), poses[idx], threads=16)
+    assert_contract(got, ref, 1e-4)
+    for a, b in FIELDS:
+        assert np.array_equal(got[a], ref[b]), a

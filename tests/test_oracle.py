@@ -1,0 +1,138 @@
+"""CPU tests of the oracle: the port (oracle/c2a_oracle.cpp) against the reference's own object code
+(oracle/_ref, when it was built here), against the committed golden fixtures that object code
+produced, and against the closed-form known answers of SURVEY.md section 4."""
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN_CASES
+
+needs_ref = pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+
+
+def rand_rot(rng):
+    q = rng.normal(size=4); q /= np.linalg.norm(q)
+    x, y, z, w = q
+    return np.array([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
+                     2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+                     2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)])
+
+
+def rect_cases(rng, n):
+    """Random rectangle pairs at mixed scales: far, near, overlapping, axis-aligned, degenerate."""
+    out = []
+    for i in range(n):
+        R = rand_rot(rng) if i % 5 else np.eye(3).ravel()
+        scale = 10.0 ** rng.uniform(-1, 1.5)
+        T = rng.normal(size=3) * scale * rng.choice([0.05, 0.5, 2.0])
+        a = rng.uniform(0, 4, 2) * (i % 7 != 0)
+        b = rng.uniform(0, 4, 2) * (i % 11 != 0)
+        out.append((R, T, a, b))
+    return out
+
+
+def test_rect_dist_known_answers():
+    """a=b=(1,1), Rab=I."""
+    P = oracle.port()
+    I = np.eye(3).ravel(); ab = np.array([1.0, 1.0])
+    d, p, q, s = P.rect_dist(I, [0, 0, 2], ab, ab)
+    assert d == 2 and list(s) == [0, 0, 2] and list(p) == [0, 0, 0] and list(q) == [0, 0, 2]
+    d, p, q, s = P.rect_dist(I, [3, 0, 0], ab, ab)
+    assert d == 2 and list(s) == [2, 0, 0] and list(p) == [1, 0, 0] and list(q) == [3, 0, 0]
+    d, p, q, s = P.rect_dist(I, [3, 4, 12], ab, ab)
+    assert d == math.sqrt(157.0) and list(s) == [2, 3, 12]
+    d, p, q, s = P.rect_dist(I, [0.25, 0.25, 0], ab, ab)
+    assert d == 0 and list(s) == [0, 0, 0]
+
+
+@needs_ref
+def test_rect_dist_port_vs_reference_header():
+    """bit-exact against C2ARectDist compiled from /root/reference/C2A/C2A_RectDist.h"""
+    P, R = oracle.port(), oracle.ref()
+    rng = np.random.default_rng(11)
+    for Rab, T, a, b in rect_cases(rng, 4000):
+        d0, p0, q0, s0 = R.rect_dist(Rab, T, a, b)
+        d1, p1, q1, s1 = P.rect_dist(Rab, T, a, b)
+        assert d0 == d1
+        assert np.array_equal(s0, s1, equal_nan=True)
+        if d0 > 0:
+            assert np.array_equal(p0, p1) and np.array_equal(q0, q1)
+
+
+def tri_cases(rng, n):
+    out = []
+    for i in range(n):
+        t1 = rng.normal(size=9)
+        t2 = rng.normal(size=9)
+        if i % 6 == 0:
+            t2[:3] = t1[:3]                      # shared vertex
+        if i % 10 == 0:
+            t2 = t1 + np.tile(rng.normal(size=3) * 0.1, 3)   # parallel copies
+        if i % 13 == 0:
+            t1[3:6] = t1[0:3]                    # degenerate triangle
+        R = rand_rot(rng)
+        T = rng.normal(size=3) * rng.choice([0.0, 0.3, 3.0])
+        out.append((R, T, t1, t2))
+    return out
+
+
+@needs_ref
+def test_tri_distance_port_vs_reference_intree():
+    """The PQP TriDistance restatement against the reference's in-tree copy (C2A.cpp:165-424)."""
+    P, R = oracle.port(), oracle.ref()
+    rng = np.random.default_rng(5)
+    n_overlap = 0
+    for Rm, T, t1, t2 in tri_cases(rng, 4000):
+        d0, p0, q0, col = R.tri_distance_intree(Rm, T, t1, t2)
+        d1, p1, q1 = P.tri_distance(Rm, T, t1, t2)
+        assert d0 == d1 or (math.isnan(d0) and math.isnan(d1))
+        assert np.array_equal(p0, p1, equal_nan=True) and np.array_equal(q0, q1, equal_nan=True)
+        n_overlap += col
+    assert n_overlap > 50  # the overlap branch was exercised
+
+
+@needs_ref
+def test_port_vs_reference_fresh_batch(bunny_tris):
+    """Port and reference on a batch that is NOT in the fixtures, bit-exact, including the full
+    unmodified C2A_Solve (printf + contact pass) on a few queries."""
+    from c2a_b200 import workloads
+    R = oracle.ref()
+    m = R.model(bunny_tris)
+    b = m.export()
+    poses = workloads.approach_batch(64, 424242)
+    r = R.solve_batch(m, m, poses, threads=4)
+    p = oracle.port().solve_batch(b, b, poses, threads=4)
+    for k in ("collisionfree", "numCA", "num_bv_tests", "num_tri_tests", "toc", "distance", "mint", "pose_toc"):
+        assert np.array_equal(r[k], p[k]), k
+    full, ncont = R.solve_batch(m, m, poses[:6], mode=1)
+    for k in ("collisionfree", "numCA", "toc", "distance", "pose_toc"):
+        assert np.array_equal(full[k], r[k][:6]), k
+
+
+@pytest.mark.parametrize("case,ma,mb", GOLDEN_CASES)
+def test_port_matches_golden(case, ma, mb, golden, bvhs):
+    """The port reproduces the reference's committed outputs bit for bit (a slice, to stay fast)."""
+    g = golden(case)
+    n = min(160, len(g["toc"]))
+    sl = slice(0, n)
+    out = oracle.port().solve_batch(bvhs(ma), bvhs(mb), g["poses"][sl],
+                                    g["seed_a"][sl] if "seed_a" in g else None,
+                                    g["seed_b"][sl] if "seed_b" in g else None,
+                                    float(g["tol_d"]), float(g["tol_t"]), threads=8)
+    for k in ("collisionfree", "numCA", "num_bv_tests", "num_tri_tests", "toc", "distance", "mint", "pose_toc"):
+        assert np.array_equal(out[k], g[k][sl]), (case, k)
+    upd = (out["p1"] != 0).any(1)  # p1/p2 are only defined once a leaf updated them
+    assert np.array_equal(np.concatenate([out["p1"], out["p2"]], 1)[upd], g["p1p2"][sl][upd])
+
+
+def test_golden_fixtures_are_sane(golden):
+    """Verdict semantics: toc == 0 for free queries, hits end within tolerance."""
+    for case, _, _ in GOLDEN_CASES:
+        g = golden(case)
+        free = g["collisionfree"] == 1
+        assert (g["toc"][free] == 0).all()
+        assert ((g["toc"] >= 0) & (g["toc"] < 1)).all()
+        assert (g["numCA"] >= 1).all() and (g["numCA"] <= 152).all()
+        assert free.sum() > 0 and (~free).sum() > 0
