@@ -6,7 +6,7 @@ import subprocess
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libc2a_b200.so")
-CU_SOURCES = ["c2a_kernels.cu", "c2a_host_model.cpp"]
+CU_SOURCES = ["c2a_kernels.cu", "c2a_host_model.cpp", "c2a_dropin.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-ffp-contract=off",  # host half (motion constants) must not fuse either
               "-fmad=false",  # bit-parity with the reference's -ffp-contract=off CPU build

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -204,16 +205,19 @@ int c2a_b200_model_info(const c2a_b200_model *m, int32_t *device, int32_t *n_nod
   return C2A_B200_OK;
 }
 
+static unsigned long long *g_stats_dev = nullptr;  // phase statistics (c2a_b200_phase_stats), off by default
+
 // per-device scratch: the claim counter
 static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses, const int32_t *sa,
                         const int32_t *sb, int64_t n, double tol_d, double tol_t, const c2a_b200_results *out,
-                        unsigned long long *counter, cudaStream_t stream)
+                        unsigned long long *counter, cudaStream_t stream, const double *step_in = nullptr)
 {
   BatchArgs args;
   args.A = DevModel{a->geom, a->rloc, a->meta, a->tris, a->n_nodes, a->n_tris};
   args.B = DevModel{b->geom, b->rloc, b->meta, b->tris, b->n_nodes, b->n_tris};
   args.motions = poses; args.seedA = sa; args.seedB = sb; args.n = n;
   args.tol_d = tol_d; args.tol_t = tol_t; args.out = *out; args.counter = counter;
+  args.step_in = step_in;
 
   static std::atomic<bool> attr_set{false};
   if (!attr_set.exchange(true))
@@ -225,6 +229,8 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   long long blocks = (long long)sms * per_sm;  // persistent: one resident wave (a multiple of the SM count)
   const long long need = (n + WARPS_PER_BLOCK * Q - 1) / (WARPS_PER_BLOCK * Q);
   if (blocks > need) blocks = need;
+  if (const char *cap = getenv("C2A_B200_MAX_BLOCKS"))  // development aid: profile a slice of the GPU
+    if (atoll(cap) > 0 && blocks > atoll(cap)) blocks = atoll(cap);
   if (blocks < 1) blocks = 1;
   // traversal stacks: one per query slot, depth(A)+depth(B)+2 entries of 128 B
   args.stack_entries = a->depth + b->depth + 2;
@@ -232,6 +238,7 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   double *stacks = nullptr;
   CUDA_TRY(cudaMallocAsync(&stacks, stack_bytes, stream));
   args.stacks = stacks;
+  args.stats = g_stats_dev;
   CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
   c2a_solve_kernel<<<(unsigned)blocks, BLOCK_THREADS, BLOCK_SMEM_BYTES, stream>>>(args);
   g_launches.fetch_add(1);
@@ -276,11 +283,13 @@ int c2a_b200_solve_batch_device(const c2a_b200_model *a, const c2a_b200_model *b
   return rc;
 }
 
-int c2a_b200_solve_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses,
-                         const int32_t *seed_a, const int32_t *seed_b, int64_t n, double tol_d, double tol_t,
-                         const c2a_b200_results *out)
+// host-buffer path shared by the three public host entries: inputs are poses (motion constants computed
+// here) or ready motion records; step_in != NULL selects single-step mode
+static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses, const double *motions,
+                      const double *step_in, const int32_t *seed_a, const int32_t *seed_b, int64_t n, double tol_d,
+                      double tol_t, const c2a_b200_results *out)
 {
-  int rc = check_pair(a, b, n, poses, out);
+  int rc = check_pair(a, b, n, poses ? poses : motions, out);
   if (rc) return rc;
   if (n == 0) return C2A_B200_OK;
   CUDA_TRY(cudaSetDevice(a->device));
@@ -299,6 +308,7 @@ int c2a_b200_solve_batch(const c2a_b200_model *a, const c2a_b200_model *b, const
   const size_t o_toc = out->toc ? take(N * 8) : 0, o_dist = out->distance ? take(N * 8) : 0;
   const size_t o_mint = out->mint ? take(N * 8) : 0, o_pp = out->p1p2 ? take(N * 48) : 0;
   const size_t o_pt = out->pose_toc ? take(N * 192) : 0;
+  const size_t o_step = step_in ? take(N * STEP_IN_DOUBLES * 8) : 0;
   const size_t o_cnt = take(8);
   char *arena = nullptr;
   cudaError_t e = cudaMallocAsync(&arena, off, stream);
@@ -327,7 +337,12 @@ int c2a_b200_solve_batch(const c2a_b200_model *a, const c2a_b200_model *b, const
   // motion constants on the host (libm acos), straight into pinned staging memory
   double *staging = nullptr;
   STEP(cudaMallocHost(&staging, N * 48 * 8));
-  if (rc == C2A_B200_OK) motions_from_poses_mt(poses, n, staging, 0);
+  if (rc == C2A_B200_OK)
+  {
+    if (poses) motions_from_poses_mt(poses, n, staging, 0);
+    else memcpy(staging, motions, N * 48 * 8);
+  }
+  if (step_in) STEP(cudaMemcpyAsync(arena + o_step, step_in, N * STEP_IN_DOUBLES * 8, cudaMemcpyHostToDevice, stream));
   STEP(cudaMemcpyAsync(arena + o_pose, staging, N * 48 * 8, cudaMemcpyHostToDevice, stream));
   if (seed_a) STEP(cudaMemcpyAsync(arena + o_sa, seed_a, N * 4, cudaMemcpyHostToDevice, stream));
   if (seed_b) STEP(cudaMemcpyAsync(arena + o_sb, seed_b, N * 4, cudaMemcpyHostToDevice, stream));
@@ -335,7 +350,7 @@ int c2a_b200_solve_batch(const c2a_b200_model *a, const c2a_b200_model *b, const
   if (rc == C2A_B200_OK)
     rc = launch_batch(a, b, (const double *)(arena + o_pose), seed_a ? (const int32_t *)(arena + o_sa) : nullptr,
                       seed_b ? (const int32_t *)(arena + o_sb) : nullptr, n, tol_d, tol_t, &d,
-                      (unsigned long long *)(arena + o_cnt), stream);
+                      (unsigned long long *)(arena + o_cnt), stream, step_in ? (const double *)(arena + o_step) : nullptr);
 #define BACK(field, ofs, bytes) \
   if (out->field) STEP(cudaMemcpyAsync(out->field, arena + ofs, bytes, cudaMemcpyDeviceToHost, stream));
   BACK(status, o_status, N * 4) BACK(collisionfree, o_cf, N * 4) BACK(num_ca, o_nca, N * 4)
@@ -349,6 +364,30 @@ int c2a_b200_solve_batch(const c2a_b200_model *a, const c2a_b200_model *b, const
   if (staging) cudaFreeHost(staging);
   cudaStreamDestroy(stream);
   return rc;
+}
+
+int c2a_b200_solve_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses,
+                         const int32_t *seed_a, const int32_t *seed_b, int64_t n, double tol_d, double tol_t,
+                         const c2a_b200_results *out)
+{
+  if (n > 0 && !poses) return fail(C2A_B200_ERR_ARG, "NULL argument");
+  return solve_host(a, b, poses, nullptr, nullptr, seed_a, seed_b, n, tol_d, tol_t, out);
+}
+
+int c2a_b200_solve_batch_motions(const c2a_b200_model *a, const c2a_b200_model *b, const double *motions,
+                                 const int32_t *seed_a, const int32_t *seed_b, int64_t n, double tol_d, double tol_t,
+                                 const c2a_b200_results *out)
+{
+  if (n > 0 && !motions) return fail(C2A_B200_ERR_ARG, "NULL argument");
+  return solve_host(a, b, nullptr, motions, nullptr, seed_a, seed_b, n, tol_d, tol_t, out);
+}
+
+int c2a_b200_toc_step_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *motions,
+                            const double *step_in, const int32_t *seed_a, const int32_t *seed_b, int64_t n,
+                            double tol_t, double tol_d, const c2a_b200_results *out)
+{
+  if (n > 0 && (!motions || !step_in)) return fail(C2A_B200_ERR_ARG, "NULL argument");
+  return solve_host(a, b, nullptr, motions, step_in, seed_a, seed_b, n, tol_d, tol_t, out);
 }
 
 }  // extern "C"
@@ -465,6 +504,22 @@ int c2a_b200_test_sincos(const double *x, int64_t n, double *s, double *c)
   CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaMemcpy(s, ds, n * 8, cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(c, dc, n * 8, cudaMemcpyDeviceToHost));
+  return C2A_B200_OK;
+}
+
+// Development aid: enable (enable != 0) or disable phase statistics of the solve kernel on the current
+// device and read them back: out[0..5] = {expand passes, expand lanes, leaf passes, leaf lanes, advance
+// passes, advance lanes} accumulated since the last enable.
+int c2a_b200_phase_stats(int32_t enable, uint64_t *out6)
+{
+  if (out6 && g_stats_dev)
+  {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out6, g_stats_dev, 6 * 8, cudaMemcpyDeviceToHost));
+  }
+  if (enable && !g_stats_dev) CUDA_TRY(cudaMalloc(&g_stats_dev, 8 * 8));
+  if (enable) CUDA_TRY(cudaMemset(g_stats_dev, 0, 8 * 8));
+  if (!enable && g_stats_dev) { cudaFree(g_stats_dev); g_stats_dev = nullptr; }
   return C2A_B200_OK;
 }
 

@@ -65,7 +65,15 @@ struct BatchArgs
   unsigned long long *counter;
   double *stacks;         // [n_slots][stack_entries][ENTRY_DOUBLES]
   int stack_entries;
+  const double *step_in;  // optional [n][STEP_IN_DOUBLES]: single-step mode (C2A_TimeOfContactStep), see below
+  unsigned long long *stats;  // optional [8]: per phase {passes, lanes used}: expand, leaf, advance; NULL = off
 };
+
+// Single-step mode (the device side of C2A_TimeOfContactStep, C2A.cpp:1778-1931): per query the caller
+// supplies the current poses and the CA-loop state the step reads -- R1(9) T1(3) R2(9) T2(3) numCA
+// res->mint(previous step) res->UpboundTOC pad -- and one traversal is run; distance, mint, p1p2 and
+// the two counters are written, nothing else.
+constexpr int STEP_IN_DOUBLES = 28;
 
 enum SlotState { ST_ADVANCE = 0, ST_TRAVERSE = 1, ST_LEAF = 2, ST_EXIT = 3 };
 
@@ -82,12 +90,13 @@ enum
   F_CUR = 43,    // 12 current entry: R(9) T(3) of the node pair to visit next
   F_LAMDA = 55, F_LASTL = 56,
   F_P1 = 57, F_P2 = 60,
-  F_NDBL = 63
+  F_CURSZ1 = 63, F_CURSZ2 = 64,  // GetSize() of the current entry's two nodes (with I_CURFC1/2: their NodeMeta)
+  F_NDBL = 65
 };
 enum
 {
   I_STATE = 0, I_SP, I_NBV, I_NTRI, I_NUMCA, I_NITRS, I_CURB1, I_CURB2, I_LEAFB1, I_LEAFB2, I_SEEDA, I_SEEDB,
-  I_QLO, I_QHI, I_PENDING, I_NINT = 16
+  I_QLO, I_QHI, I_PENDING, I_CURFC1, I_CURFC2, I_NINT = 18
 };
 constexpr size_t WARP_SMEM_BYTES = (size_t)F_NDBL * Q * 8 + (size_t)I_NINT * Q * 4;
 constexpr size_t BLOCK_SMEM_BYTES = WARP_SMEM_BYTES * WARPS_PER_BLOCK;
@@ -98,6 +107,7 @@ C2A_DEV void load9(double d[9], const double *s)
   for (int i = 0; i < 9; i++) d[i] = __ldg(s + i);
 }
 C2A_DEV void load3(double d[3], const double *s) { d[0] = __ldg(s); d[1] = __ldg(s + 1); d[2] = __ldg(s + 2); }
+C2A_DEV void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __device__ __noinline__ double tri_distance_nl(const double R[9], const double T[3], const double *t1,
                                                const double *t2, double p[3], double q[3])
@@ -135,16 +145,20 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
     const unsigned mA = __ballot_sync(FULL, st == ST_ADVANCE);
     if ((mT | mL | mA) == 0) break;
     const int nT = __popc(mT), nL = __popc(mL), nA = __popc(mA);
-    // run the phase that fills the most lanes (an expansion uses two lanes per slot)
+    // Phase choice: a full expansion pass (16 slots x 2 lanes) whenever one is available; otherwise
+    // first turn waiting slots back into traversable ones (the larger of the LEAF / ADVANCE groups),
+    // and only run a partial expansion pass when nothing is waiting.
     int phase;
-    {
-      const int fT = nT >= 16 ? 64 : 2 * nT;  // a full expansion pass always wins
-      phase = ST_TRAVERSE;
-      int best = fT;
-      if (nL > best) { best = nL; phase = ST_LEAF; }
-      if (nA > best) { best = nA; phase = ST_ADVANCE; }
-    }
+    if (nT >= 16) phase = ST_TRAVERSE;
+    else if (nL > 0 || nA > 0) phase = (nL >= nA) ? ST_LEAF : ST_ADVANCE;
+    else phase = ST_TRAVERSE;
 
+    if (args.stats && lane == 0)
+    {
+      const int k = phase == ST_TRAVERSE ? 0 : (phase == ST_LEAF ? 2 : 4);
+      atomicAdd(args.stats + k, 1ull);
+      atomicAdd(args.stats + k + 1, (unsigned long long)(phase == ST_TRAVERSE ? 2 * min(nT, 16) : (phase == ST_LEAF ? nL : nA)));
+    }
     if (phase == ST_TRAVERSE)
     {
       // -------------------------------------------------------------------- EXPAND ----------
@@ -159,7 +173,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
         const double dist = SD(F_DIST, slot), abs_err = SD(F_ABS, slot), rel_err = SD(F_REL, slot), upbound = SD(F_UPB, slot);
         double mint = SD(F_MINT, slot);
         double R[9], T[3];
-        if (b1 >= 0)
+        const bool from_cur = b1 >= 0;
+        if (from_cur)
         {
 #pragma unroll
           for (int i = 0; i < 9; i++) R[i] = SD(F_CUR + i, slot);
@@ -200,7 +215,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
         }
         else
         {
-          const NodeMeta ma = A.meta[b1], mb = B.meta[b2];
+          NodeMeta ma, mb;
+          if (from_cur)
+          {
+            ma.size = SD(F_CURSZ1, slot); ma.first_child = SI(I_CURFC1, slot);
+            mb.size = SD(F_CURSZ2, slot); mb.first_child = SI(I_CURFC2, slot);
+          }
+          else { ma = A.meta[b1]; mb = B.meta[b2]; }
           const bool l1 = ma.first_child < 0, l2 = mb.first_child < 0;
           if (l1 && l2)
           {
@@ -216,9 +237,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
             int n1, n2;  // node ids of my child pair
             double Rc[9], Tc[3];
             const double *gs, *gt, *rl;  // side-1 node geom, side-2 node geom, R_loc of the side-1 node
+            NodeMeta cm1 = ma, cm2 = mb;  // NodeMeta of my child pair: loaded now, consumed at commit
             if (l2 || (!l1 && (ma.size > mb.size)))
             {
               n1 = ma.first_child + c; n2 = b2;
+              cm1 = A.meta[n1];
               gs = A.geom + (size_t)n1 * GEOM_STRIDE; gt = B.geom + (size_t)b2 * GEOM_STRIDE;
               rl = A.rloc + (size_t)n1 * 9;
               double Rn[9], Tn[3], Tt[3];
@@ -228,12 +251,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
             else
             {
               n1 = b1; n2 = mb.first_child + c;
+              cm2 = B.meta[n2];
               gs = A.geom + (size_t)b1 * GEOM_STRIDE; gt = B.geom + (size_t)n2 * GEOM_STRIDE;
               rl = A.rloc + (size_t)b1 * 9;
               double Rn[9], Tn[3];
               load9(Rn, gt); load3(Tn, gt + 9);
               m_m(Rc, R, Rn); m_v_p(Tc, R, Tn, T);
             }
+            prefetch_l1(rl); prefetch_l1(rl + 8);  // R_loc is only consumed after the rectangle distance
             // child BV test (C2A.cpp:1237-1276): RSS distance, direction to world frame, the two
             // directional motion bounds, the child's conservative step bound
             double d, mt = 0.0;
@@ -284,6 +309,16 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
 #pragma unroll
                 for (int i = 0; i < 3; i++) SD(F_CUR + 9 + i, slot) = Tc[i];
                 SI(I_CURB1, slot) = n1; SI(I_CURB2, slot) = n2;
+                SD(F_CURSZ1, slot) = cm1.size; SI(I_CURFC1, slot) = cm1.first_child;
+                SD(F_CURSZ2, slot) = cm2.size; SI(I_CURFC2, slot) = cm2.first_child;
+                // warm L1 with the node pair the next expansion of this slot will fetch
+                const bool nl1 = cm1.first_child < 0, nl2 = cm2.first_child < 0;
+                if (!(nl1 && nl2))
+                {
+                  const double *nx = (nl2 || (!nl1 && (cm1.size > cm2.size))) ? A.geom + (size_t)cm1.first_child * GEOM_STRIDE
+                                                                              : B.geom + (size_t)cm2.first_child * GEOM_STRIDE;
+                  prefetch_l1(nx); prefetch_l1(nx + GEOM_STRIDE);
+                }
               }
               else
               {
@@ -366,6 +401,22 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
         int numCA = SI(I_NUMCA, slot);
         double lamda = SD(F_LAMDA, slot);
         Motion m1, m2;
+        if (q >= 0 && !pending && args.step_in)
+        {
+          // single-step mode: report this traversal and release the slot
+          const c2a_b200_results &o = args.out;
+          if (o.status) o.status[q] = C2A_B200_QUERY_OK;
+          if (o.num_bv_tests) o.num_bv_tests[q] = SI(I_NBV, slot);
+          if (o.num_tri_tests) o.num_tri_tests[q] = SI(I_NTRI, slot);
+          if (o.distance) o.distance[q] = SD(F_DIST, slot);
+          if (o.mint) o.mint[q] = SD(F_MINT, slot);
+          if (o.p1p2)
+          {
+#pragma unroll
+            for (int i = 0; i < 3; i++) { o.p1p2[6 * q + i] = SD(F_P1 + i, slot); o.p1p2[6 * q + 3 + i] = SD(F_P2 + i, slot); }
+          }
+          q = -1;
+        }
         if (q >= 0 && !pending)
         {
           // a step just ended: C2A_QueryTimeOfContact's loop, C2A.cpp:2053-2123
@@ -454,7 +505,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
             q = nq;
             const double *rec = args.motions + (size_t)(2 * MOTION_DOUBLES) * q;
             const double w1 = __ldg(rec + 18), w2 = __ldg(rec + MOTION_DOUBLES + 18);
-            if (w1 < 1e-8 && w2 < 1e-8)
+            if (!args.step_in && w1 < 1e-8 && w2 < 1e-8)
             {
               // translation-only branch of the reference (C2A.cpp:2391-2395): not implemented
               if (args.out.status) args.out.status[q] = C2A_B200_QUERY_TRANSLATION_ONLY;
@@ -474,6 +525,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
               numCA = 0; lamda = 0;
               SI(I_NITRS, slot) = 0; SI(I_NBV, slot) = 0; SI(I_NTRI, slot) = 0;
               SD(F_LASTL, slot) = 0; SD(F_UPB, slot) = 1; SD(F_MINT, slot) = 1; SD(F_DIST, slot) = 0;
+              if (args.step_in)
+              {
+                const double *si_ = args.step_in + (size_t)STEP_IN_DOUBLES * q;
+                numCA = (int)__ldg(si_ + 24); SD(F_MINT, slot) = __ldg(si_ + 25); SD(F_UPB, slot) = __ldg(si_ + 26);
+              }
 #pragma unroll
               for (int i = 0; i < 3; i++) { SD(F_P1 + i, slot) = 0; SD(F_P2 + i, slot) = 0; }
               pending = true;
@@ -487,7 +543,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
           // C2A_TimeOfContactStep, C2A.cpp:1791-1894
           const double *rec = args.motions + (size_t)(2 * MOTION_DOUBLES) * q;
           double r1[9], tt1[3], R2[9], T2[3], Tt[3], Rt[9], g1[12], g2[12], R[9], T[3], Rrel[9], Trel[3];
-          if (numCA == 0)
+          if (args.step_in)
+          {
+            const double *si_ = args.step_in + (size_t)STEP_IN_DOUBLES * q;
+            load9(r1, si_); load3(tt1, si_ + 9); load9(R2, si_ + 12); load3(T2, si_ + 21);
+          }
+          else if (numCA == 0)
           {
             load9(r1, rec); load3(tt1, rec + 9);
             load9(R2, rec + MOTION_DOUBLES); load3(T2, rec + MOTION_DOUBLES + 9);
@@ -525,6 +586,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
           for (int i = 0; i < 3; i++) { SD(F_TT1 + i, slot) = tt1[i]; SD(F_TREL + i, slot) = Trel[i]; SD(F_CUR + 9 + i, slot) = T[i]; }
           // the root pair is descended unconditionally
           SI(I_CURB1, slot) = 0; SI(I_CURB2, slot) = 0; SI(I_SP, slot) = 0;
+          {
+            const NodeMeta ra = A.meta[0], rb = B.meta[0];
+            SD(F_CURSZ1, slot) = ra.size; SI(I_CURFC1, slot) = ra.first_child;
+            SD(F_CURSZ2, slot) = rb.size; SI(I_CURFC2, slot) = rb.first_child;
+          }
           pending = false;
           SI(I_STATE, slot) = ST_TRAVERSE;
         }

@@ -114,6 +114,22 @@ int c2a_b200_solve_batch(const c2a_b200_model *a, const c2a_b200_model *b, const
 #define C2A_B200_MOTION_DOUBLES 48
 int c2a_b200_motions_from_poses(const double *poses, int64_t n, double *motions, int32_t n_threads);
 
+/* Batched C2A_QueryTimeOfContact (C2A/C2A.h:274-281) from ready motion records (host buffers): what
+ * c2a_b200_solve_batch does after its motion set-up.  Used by the C++ shim of C2A_QueryTimeOfContact,
+ * whose CInterpMotion arguments already hold cv / m_axis / m_angVel. */
+int c2a_b200_solve_batch_motions(const c2a_b200_model *a, const c2a_b200_model *b, const double *motions,
+                                 const int32_t *seed_a, const int32_t *seed_b, int64_t n, double tol_d, double tol_t,
+                                 const c2a_b200_results *out);
+
+/* Batched C2A_TimeOfContactStep (C2A/src/C2A.cpp:1778-1931; note its argument order: tolerance_t, then
+ * tolerance_d): ONE conservative-advancement iteration per query.  step_in [n][28] = the current poses
+ * R1(9) T1(3) R2(9) T2(3), then res->numCA, res->mint (of the previous step) and res->UpboundTOC as the
+ * step reads them, then a pad.  Writes distance, mint, p1p2, num_bv_tests, num_tri_tests, status. */
+#define C2A_B200_STEP_IN_DOUBLES 28
+int c2a_b200_toc_step_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *motions,
+                            const double *step_in, const int32_t *seed_a, const int32_t *seed_b, int64_t n,
+                            double tol_t, double tol_d, const c2a_b200_results *out);
+
 /* Batched C2A_QueryTimeOfContact (+ the pose outputs of C2A_Solve) with everything already resident
  * on the models' device: motions_dev [n][C2A_B200_MOTION_DOUBLES] from c2a_b200_motions_from_poses,
  * seeds and outputs device pointers.  Enqueued on `cuda_stream` (a cudaStream_t; NULL = default

@@ -1,0 +1,48 @@
+"""The C++ drop-in API (include/C2A/C2A.h) exercised by a program written the way the reference's demo
+uses the reference (tests/cpp/dropin_demo.cpp): C2A_Model build, per-frame C2A_Solve, and the
+C2A_QueryTimeOfContact / C2A_TimeOfContactStep / C2A_SolveBatch entries, against the reference fixture."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from c2a_b200 import meshes
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cpp_dropin_matches_reference_fixture(tmp_path, golden):
+    g = golden("ref_knot_128x16")
+    n = 48
+    verts = meshes.torus_knot_verts(128, 16)
+    _, vidx = meshes.torus_knot(128, 16)
+    with open(tmp_path / "mesh.txt", "w") as f:
+        f.write(f"{len(verts)} {len(vidx)}\n")
+        for v in verts:
+            f.write("%.17g %.17g %.17g\n" % tuple(v))
+        for t in vidx:
+            f.write("%d %d %d\n" % tuple(t))
+    with open(tmp_path / "poses.txt", "w") as f:
+        for p in g["poses"][:n]:
+            f.write(" ".join("%.17g" % x for x in p) + "\n")
+    exe = tmp_path / "dropin_demo"
+    lib = os.path.join(ROOT, "c2a_b200", "csrc")
+    subprocess.run(["g++", "-std=c++14", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests/cpp/dropin_demo.cpp"),
+                    "-o", str(exe), "-L" + lib, "-lc2a_b200", "-Wl,-rpath," + lib], check=True)
+    out = subprocess.run([str(exe), str(tmp_path / "mesh.txt"), str(tmp_path / "poses.txt"), str(n)], capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "end model" not in out.stdout and "dres.distance" not in out.stdout  # the drop-in does not print
+    rows = [l.split() for l in out.stdout.splitlines() if l.startswith("F ")]
+    assert len(rows) == n
+    for i, r in enumerate(rows):
+        assert int(r[1]) == g["collisionfree"][i]
+        assert float.fromhex(r[2]) == g["toc"][i]
+        assert float.fromhex(r[3]) == g["distance"][i]
+        assert int(r[4]) == g["numCA"][i] and int(r[5]) == g["num_bv_tests"][i] and int(r[6]) == g["num_tri_tests"][i]
+        if not g["collisionfree"][i]:
+            assert [float.fromhex(x) for x in r[7:16]] == list(g["pose_toc"][i][:9])
+    assert "BATCH_MISMATCH 0" in out.stdout
+    assert "STEP_MISMATCH 0" in out.stdout
