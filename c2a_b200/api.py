@@ -161,8 +161,17 @@ def motions_from_poses(poses, threads=0, out=None):
     return out
 
 
+def schedule_order(model_a, model_b, motions):
+    """Claim order (longest-expected queries first) for ``solve_batch_device``: int32 [n]."""
+    motions = np.ascontiguousarray(motions, dtype=np.float64).reshape(-1, 48)
+    order = np.empty(motions.shape[0], dtype=np.int32)
+    _check(lib().c2a_b200_schedule_order(model_a.h, model_b.h, motions.ctypes.data_as(C.c_void_p),
+                                         C.c_int64(motions.shape[0]), order.ctypes.data_as(C.c_void_p)))
+    return order
+
+
 def solve_batch_device(model_a, model_b, poses_ptr, n, out_ptrs, seed_a_ptr=None, seed_b_ptr=None,
-                       tol_d=1e-4, tol_t=1e-4, stream=None):
+                       tol_d=1e-4, tol_t=1e-4, stream=None, order_ptr=None):
     """Device-pointer entry: ``poses_ptr`` (MOTION RECORDS from ``motions_from_poses``, resident on the
     device) and the values of ``out_ptrs`` (dict field -> int address) are CUDA device addresses (e.g. ``torch.Tensor.data_ptr()``); enqueues on ``stream`` (a
     cudaStream_t address or None) and returns without synchronising."""
@@ -173,5 +182,6 @@ def solve_batch_device(model_a, model_b, poses_ptr, n, out_ptrs, seed_a_ptr=None
     _check(lib().c2a_b200_solve_batch_device(model_a.h, model_b.h, C.c_void_p(poses_ptr),
                                              C.c_void_p(seed_a_ptr) if seed_a_ptr else None,
                                              C.c_void_p(seed_b_ptr) if seed_b_ptr else None,
+                                             C.c_void_p(order_ptr) if order_ptr else None,
                                              C.c_int64(n), C.c_double(tol_d), C.c_double(tol_t), C.byref(res),
                                              C.c_void_p(stream) if stream else None))

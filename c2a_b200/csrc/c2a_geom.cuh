@@ -103,10 +103,11 @@ C2A_DEV bool in_voronoi(double a, double b, double AnB, double AnT, double AdB, 
 // are negative S is left untouched, exactly as the reference.
 //
 // SIMT reshaping: the reference tests 16 edge pairs in a fixed if-ladder.  Here the 16 cheap
-// entry predicates are evaluated first into a bit mask; each lane then visits only ITS OWN
-// candidate pairs in ladder order, selecting that pair's operands in a short switch and running
-// the expensive Voronoi tests (two FP64 divisions) in code common to all lanes.  The expressions
-// and the acceptance order are the reference's, so the result is bit-identical.
+// entry predicates (and the trivially-true halves of the acceptance tests) are evaluated first into
+// bit masks; each lane then visits only ITS OWN candidate pairs in ladder order, two per trip, forming
+// each pair's operands with selects (no 16-way branch) and running the Voronoi tests (the FP64
+// divisions) in code common to all lanes.  The expressions and the acceptance order are the
+// reference's, so the result is bit-identical.
 C2A_DEV double rss_rect_dist(const double R[9], const double T[3], double a0, double a1, double b0, double b1,
                              double S[3])
 {
@@ -160,63 +161,83 @@ C2A_DEV double rss_rect_dist(const double R[9], const double T[3], double a0, do
   mask |= ((LA0_uy > b1) && (UB0_ly < 0)) ? 1u << 14 : 0u;
   mask |= ((LA0_ly < 0) && (LB0_ly < 0)) ? 1u << 15 : 0u;
 
+  // trivially-true halves of each pair's acceptance test (the left operand of each || in the ladder)
+  unsigned trivA = 0, trivB = 0;
+  trivA |= (UA1_lx > b0) ? 1u << 0 : 0u;   trivB |= (UB1_lx > a0) ? 1u << 0 : 0u;
+  trivA |= (UA1_ux < 0) ? 1u << 1 : 0u;    trivB |= (LB1_lx > a0) ? 1u << 1 : 0u;
+  trivA |= (LA1_lx > b0) ? 1u << 2 : 0u;   trivB |= (UB1_ux < 0) ? 1u << 2 : 0u;
+  trivA |= (LA1_ux < 0) ? 1u << 3 : 0u;    trivB |= (LB1_ux < 0) ? 1u << 3 : 0u;
+  trivA |= (UA1_ly > b1) ? 1u << 4 : 0u;   trivB |= (UB0_lx > a0) ? 1u << 4 : 0u;
+  trivA |= (UA1_uy < 0) ? 1u << 5 : 0u;    trivB |= (LB0_lx > a0) ? 1u << 5 : 0u;
+  trivA |= (LA1_ly > b1) ? 1u << 6 : 0u;   trivB |= (UB0_ux < 0) ? 1u << 6 : 0u;
+  trivA |= (LA1_uy < 0) ? 1u << 7 : 0u;    trivB |= (LB0_ux < 0) ? 1u << 7 : 0u;
+  trivA |= (UA0_lx > b0) ? 1u << 8 : 0u;   trivB |= (UB1_ly > a1) ? 1u << 8 : 0u;
+  trivA |= (UA0_ux < 0) ? 1u << 9 : 0u;    trivB |= (LB1_ly > a1) ? 1u << 9 : 0u;
+  trivA |= (LA0_lx > b0) ? 1u << 10 : 0u;  trivB |= (UB1_uy < 0) ? 1u << 10 : 0u;
+  trivA |= (LA0_ux < 0) ? 1u << 11 : 0u;   trivB |= (LB1_uy < 0) ? 1u << 11 : 0u;
+  trivA |= (UA0_ly > b1) ? 1u << 12 : 0u;  trivB |= (UB0_ly > a1) ? 1u << 12 : 0u;
+  trivA |= (UA0_uy < 0) ? 1u << 13 : 0u;   trivB |= (LB0_ly > a1) ? 1u << 13 : 0u;
+  trivA |= (LA0_ly > b1) ? 1u << 14 : 0u;  trivB |= (UB0_uy < 0) ? 1u << 14 : 0u;
+  trivA |= (LA0_uy < 0) ? 1u << 15 : 0u;   trivB |= (LB0_uy < 0) ? 1u << 15 : 0u;
+
+  // Operands of pair k without a 16-way branch.  With ea/eb the edge axes of the pair (group bits) and
+  // ua/ub its upper/lower sides, every operand of the ladder is one of a few expressions over scalars
+  // chosen by (ea, eb); the handful of pairs whose source spells a sum in another order (which rounds
+  // differently) are selected explicitly, so each value is bit-identical to the ladder's.
+  struct PairOps { double la, lb, AdB, nA, tA, dA, eA, nB, tB, dB, eB; };
+  auto pair_ops = [&](int k, PairOps &o) {
+    const int g = k >> 2;
+    const bool ea = g < 2, eb = !(g & 1), ua = !(k & 2), ub = !(k & 1);
+    o.la = ea ? a1 : a0; o.lb = eb ? b1 : b0;
+    const double aO = ea ? a0 : a1, bO = eb ? b0 : b1;
+    o.AdB = ea ? (eb ? A1B1 : A1B0) : (eb ? A0B1 : A0B0);                 // R[ea][eb]
+    const double Reo = ea ? (eb ? A1B0 : A1B1) : (eb ? A0B0 : A0B1);      // R[ea][ob]
+    const double Roe = ea ? (eb ? A0B1 : A0B0) : (eb ? A1B1 : A1B0);      // R[oa][eb]
+    const double aRoo = ea ? (eb ? aA0B0 : aA0B1) : (eb ? aA1B0 : aA1B1);  // a[oa]*R[oa][ob]
+    const double aRoe = ea ? (eb ? aA0B1 : aA0B0) : (eb ? aA1B1 : aA1B0);  // a[oa]*R[oa][eb]
+    const double bReo = ea ? (eb ? bA1B0 : bA1B1) : (eb ? bA0B0 : bA0B1);  // b[ob]*R[ea][ob]
+    const double bRoo = ea ? (eb ? bA0B0 : bA0B1) : (eb ? bA1B0 : bA1B1);  // b[ob]*R[oa][ob]
+    const double TE = ea ? T[1] : T[0], TO = ea ? T[0] : T[1];
+    const double TbaE = eb ? Tba[1] : Tba[0], TbaO = eb ? Tba[0] : Tba[1];
+    o.nA = ub ? Reo : -Reo;
+    o.nB = ua ? Roe : -Roe;
+    const double tA_uu = (g == 0) ? (aRoo - bO - TbaO) : (aRoo - TbaO - bO);
+    const double tA_lu = (g == 2) ? (-bO - TbaO) : (-TbaO - bO);
+    o.tA = ua ? (ub ? tA_uu : (TbaO - aRoo)) : (ub ? tA_lu : TbaO);
+    o.dA = ua ? (aRoe - TbaE) : -TbaE;
+    const double eA_u = (g == 2 && !ua) ? (-bReo - TE) : (-TE - bReo);
+    o.eA = ub ? eA_u : -TE;
+    const double tB_uu = (g == 0) ? (TO + bRoo - aO) : (TO - aO + bRoo);
+    o.tB = ua ? (ub ? tB_uu : (TO - aO)) : (ub ? (-TO - bRoo) : -TO);
+    o.dB = ub ? (TE + bReo) : TE;
+    o.eB = ua ? (TbaE - aRoe) : TbaE;
+  };
+
+  // Each lane walks ITS candidate pairs in ladder order, two per trip: the four Voronoi tests of a trip
+  // are independent (instruction-level parallelism for the FP64 divisions), and the second pair only
+  // counts when the first is rejected, so the accepted pair is the ladder's.
   int kf = -1;
   double t = 0, u = 0;
   while (mask)
   {
-    const int k = __ffs(mask) - 1;
+    const int k1 = __ffs(mask) - 1;
     mask &= mask - 1;
-    // operands of the pair: la/lb edge lengths, AdB = A_edge . B_edge, then for the A-side and
-    // B-side Voronoi tests (AnB, AnT, AdT, BdT); the B-side (AdT, BdT) also feed seg_params.
-    double la, lb, AdB, nA, tA, dA, eA, nB, tB, dB, eB;
-    bool trivA, trivB;
-#define C2A_RD(K, TRIVA, NA, TA, DA, EA, TRIVB, NB, TB, DB, EB, LA, LB, ADB) \
-  case K: trivA = (TRIVA); nA = (NA); tA = (TA); dA = (DA); eA = (EA);        \
-          trivB = (TRIVB); nB = (NB); tB = (TB); dB = (DB); eB = (EB);        \
-          la = (LA); lb = (LB); AdB = (ADB); break;
-    switch (k)
+    const int k2 = mask ? __ffs(mask) - 1 : k1;
+    const bool two = mask != 0;
+    mask &= mask - 1;
+    PairOps o1, o2;
+    pair_ops(k1, o1);
+    pair_ops(k2, o2);
+    const bool a1ok = ((trivA >> k1) & 1) | in_voronoi(o1.lb, o1.la, o1.nA, o1.tA, o1.AdB, o1.dA, o1.eA);
+    const bool b1ok = ((trivB >> k1) & 1) | in_voronoi(o1.la, o1.lb, o1.nB, o1.tB, o1.AdB, o1.dB, o1.eB);
+    const bool a2ok = ((trivA >> k2) & 1) | in_voronoi(o2.lb, o2.la, o2.nA, o2.tA, o2.AdB, o2.dA, o2.eA);
+    const bool b2ok = ((trivB >> k2) & 1) | in_voronoi(o2.la, o2.lb, o2.nB, o2.tB, o2.AdB, o2.dB, o2.eB);
+    const bool ok1 = a1ok && b1ok, ok2 = two && a2ok && b2ok;
+    if (ok1 || ok2)
     {
-      C2A_RD(0, UA1_lx > b0, A1B0, aA0B0 - b0 - Tba[0], aA0B1 - Tba[1], -T[1] - bA1B0,
-             UB1_lx > a0, A0B1, T[0] + bA0B0 - a0, T[1] + bA1B0, Tba[1] - aA0B1, a1, b1, A1B1)
-      C2A_RD(1, UA1_ux < 0, -A1B0, Tba[0] - aA0B0, aA0B1 - Tba[1], -T[1],
-             LB1_lx > a0, A0B1, T[0] - a0, T[1], Tba[1] - aA0B1, a1, b1, A1B1)
-      C2A_RD(2, LA1_lx > b0, A1B0, -Tba[0] - b0, -Tba[1], -T[1] - bA1B0,
-             UB1_ux < 0, -A0B1, -T[0] - bA0B0, T[1] + bA1B0, Tba[1], a1, b1, A1B1)
-      C2A_RD(3, LA1_ux < 0, -A1B0, Tba[0], -Tba[1], -T[1],
-             LB1_ux < 0, -A0B1, -T[0], T[1], Tba[1], a1, b1, A1B1)
-      C2A_RD(4, UA1_ly > b1, A1B1, aA0B1 - Tba[1] - b1, aA0B0 - Tba[0], -T[1] - bA1B1,
-             UB0_lx > a0, A0B0, T[0] - a0 + bA0B1, T[1] + bA1B1, Tba[0] - aA0B0, a1, b0, A1B0)
-      C2A_RD(5, UA1_uy < 0, -A1B1, Tba[1] - aA0B1, aA0B0 - Tba[0], -T[1],
-             LB0_lx > a0, A0B0, T[0] - a0, T[1], Tba[0] - aA0B0, a1, b0, A1B0)
-      C2A_RD(6, LA1_ly > b1, A1B1, -Tba[1] - b1, -Tba[0], -T[1] - bA1B1,
-             UB0_ux < 0, -A0B0, -T[0] - bA0B1, T[1] + bA1B1, Tba[0], a1, b0, A1B0)
-      C2A_RD(7, LA1_uy < 0, -A1B1, Tba[1], -Tba[0], -T[1],
-             LB0_ux < 0, -A0B0, -T[0], T[1], Tba[0], a1, b0, A1B0)
-      C2A_RD(8, UA0_lx > b0, A0B0, aA1B0 - Tba[0] - b0, aA1B1 - Tba[1], -T[0] - bA0B0,
-             UB1_ly > a1, A1B1, T[1] - a1 + bA1B0, T[0] + bA0B0, Tba[1] - aA1B1, a0, b1, A0B1)
-      C2A_RD(9, UA0_ux < 0, -A0B0, Tba[0] - aA1B0, aA1B1 - Tba[1], -T[0],
-             LB1_ly > a1, A1B1, T[1] - a1, T[0], Tba[1] - aA1B1, a0, b1, A0B1)
-      C2A_RD(10, LA0_lx > b0, A0B0, -b0 - Tba[0], -Tba[1], -bA0B0 - T[0],
-             UB1_uy < 0, -A1B1, -T[1] - bA1B0, T[0] + bA0B0, Tba[1], a0, b1, A0B1)
-      C2A_RD(11, LA0_ux < 0, -A0B0, Tba[0], -Tba[1], -T[0],
-             LB1_uy < 0, -A1B1, -T[1], T[0], Tba[1], a0, b1, A0B1)
-      C2A_RD(12, UA0_ly > b1, A0B1, aA1B1 - Tba[1] - b1, aA1B0 - Tba[0], -T[0] - bA0B1,
-             UB0_ly > a1, A1B0, T[1] - a1 + bA1B1, T[0] + bA0B1, Tba[0] - aA1B0, a0, b0, A0B0)
-      C2A_RD(13, UA0_uy < 0, -A0B1, Tba[1] - aA1B1, aA1B0 - Tba[0], -T[0],
-             LB0_ly > a1, A1B0, T[1] - a1, T[0], Tba[0] - aA1B0, a0, b0, A0B0)
-      C2A_RD(14, LA0_ly > b1, A0B1, -Tba[1] - b1, -Tba[0], -T[0] - bA0B1,
-             UB0_uy < 0, -A1B0, -T[1] - bA1B1, T[0] + bA0B1, Tba[0], a0, b0, A0B0)
-      default:
-      C2A_RD(15, LA0_uy < 0, -A0B1, Tba[1], -Tba[0], -T[0],
-             LB0_uy < 0, -A1B0, -T[1], T[0], Tba[0], a0, b0, A0B0)
-    }
-#undef C2A_RD
-    const bool okA = trivA | in_voronoi(lb, la, nA, tA, AdB, dA, eA);
-    const bool okB = trivB | in_voronoi(la, lb, nB, tB, AdB, dB, eB);
-    if (okA && okB)
-    {
-      seg_params(t, u, la, lb, AdB, dB, eB);
-      kf = k;
+      const PairOps &o = ok1 ? o1 : o2;
+      seg_params(t, u, o.la, o.lb, o.AdB, o.dB, o.eB);
+      kf = ok1 ? k1 : k2;
       break;
     }
   }

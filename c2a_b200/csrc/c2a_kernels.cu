@@ -39,6 +39,7 @@ struct c2a_b200_model
 {
   int device;
   int n_nodes, n_tris, depth;
+  double root_ang_radius;
   double *geom, *rloc, *tris;
   c2a::NodeMeta *meta;
 };
@@ -74,6 +75,31 @@ static void motion_record_from_pose(const double *pose, double *rec)
   }
   rec[19] = qs[0]; rec[20] = qs[1]; rec[21] = qs[2]; rec[22] = qs[3];
   rec[23] = 0.0;
+}
+
+// Claim order for the persistent kernel: queries expected to run long first, so that their sequential
+// CA chains start early instead of forming the tail of the launch.  Results do not depend on the order.
+// Cost proxy: how much of the conservative motion bound is rotation rather than closing translation,
+//   key = (w1*r1 + w2*r2 + |cv1 - cv2|) / |cv1 - cv2|   (r = angular radius of the root BV)
+// -- a small closing speed relative to the bound means small CA steps, i.e. many of them.  Counting sort
+// into 256 log-spaced buckets, descending, stable.
+static void schedule_order(const double *motions, int64_t n, double ra, double rb, int32_t *order)
+{
+  std::vector<uint8_t> bucket((size_t)n);
+  int64_t count[257] = {0};
+  for (int64_t i = 0; i < n; i++)
+  {
+    const double *m = motions + 48 * i;
+    const double dx = m[12] - m[36], dy = m[13] - m[37], dz = m[14] - m[38];
+    const double dcv = sqrt(dx * dx + dy * dy + dz * dz);
+    const double key = (m[18] * ra + m[42] * rb + dcv) / (dcv > 1e-300 ? dcv : 1e-300);
+    double l = 24.0 * log2(key > 1.0 ? key : 1.0);
+    const int b = 255 - (l < 255.0 ? (int)l : 255);  // bucket 0 = largest key
+    bucket[i] = (uint8_t)b;
+    count[b + 1]++;
+  }
+  for (int b = 0; b < 256; b++) count[b + 1] += count[b];
+  for (int64_t i = 0; i < n; i++) order[count[bucket[i]]++] = (int32_t)i;
 }
 
 static void motions_from_poses_mt(const double *poses, int64_t n, double *motions, int n_threads)
@@ -168,6 +194,7 @@ int c2a_b200_model_upload(const c2a_b200_bvh *bvh, int32_t device, c2a_b200_mode
   CUDA_TRY(cudaSetDevice(device));
   c2a_b200_model *m = new c2a_b200_model();
   m->device = device; m->n_nodes = n; m->n_tris = nt; m->depth = depth;
+  m->root_ang_radius = bvh->ang_radius[0];
   m->geom = m->rloc = m->tris = nullptr; m->meta = nullptr;
   cudaError_t e;
   if ((e = cudaMalloc(&m->geom, geom.size() * sizeof(double))) != cudaSuccess ||
@@ -210,7 +237,8 @@ static unsigned long long *g_stats_dev = nullptr;  // phase statistics (c2a_b200
 // per-device scratch: the claim counter
 static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses, const int32_t *sa,
                         const int32_t *sb, int64_t n, double tol_d, double tol_t, const c2a_b200_results *out,
-                        unsigned long long *counter, cudaStream_t stream, const double *step_in = nullptr)
+                        unsigned long long *counter, cudaStream_t stream, const double *step_in = nullptr,
+                        const int32_t *order = nullptr)
 {
   BatchArgs args;
   args.A = DevModel{a->geom, a->rloc, a->meta, a->tris, a->n_nodes, a->n_tris};
@@ -218,6 +246,7 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   args.motions = poses; args.seedA = sa; args.seedB = sb; args.n = n;
   args.tol_d = tol_d; args.tol_t = tol_t; args.out = *out; args.counter = counter;
   args.step_in = step_in;
+  args.order = order;
 
   static std::atomic<bool> attr_set{false};
   if (!attr_set.exchange(true))
@@ -267,9 +296,18 @@ int c2a_b200_motions_from_poses(const double *poses, int64_t n, double *motions,
   return C2A_B200_OK;
 }
 
+int c2a_b200_schedule_order(const c2a_b200_model *a, const c2a_b200_model *b, const double *motions, int64_t n,
+                            int32_t *order)
+{
+  if (!a || !b || n < 0 || (n > 0 && (!motions || !order))) return fail(C2A_B200_ERR_ARG, "NULL argument");
+  if (n > 0x7fffffff) return fail(C2A_B200_ERR_ARG, "batch too large for a 32-bit order");
+  schedule_order(motions, n, a->root_ang_radius, b->root_ang_radius, order);
+  return C2A_B200_OK;
+}
+
 int c2a_b200_solve_batch_device(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses_dev,
-                                const int32_t *seed_a_dev, const int32_t *seed_b_dev, int64_t n, double tol_d,
-                                double tol_t, const c2a_b200_results *out_dev, void *cuda_stream)
+                                const int32_t *seed_a_dev, const int32_t *seed_b_dev, const int32_t *order_dev, int64_t n,
+                                double tol_d, double tol_t, const c2a_b200_results *out_dev, void *cuda_stream)
 {
   int rc = check_pair(a, b, n, poses_dev, out_dev);
   if (rc) return rc;
@@ -278,7 +316,7 @@ int c2a_b200_solve_batch_device(const c2a_b200_model *a, const c2a_b200_model *b
   cudaStream_t stream = (cudaStream_t)cuda_stream;
   unsigned long long *counter = nullptr;
   CUDA_TRY(cudaMallocAsync(&counter, sizeof(unsigned long long), stream));
-  rc = launch_batch(a, b, poses_dev, seed_a_dev, seed_b_dev, n, tol_d, tol_t, out_dev, counter, stream);
+  rc = launch_batch(a, b, poses_dev, seed_a_dev, seed_b_dev, n, tol_d, tol_t, out_dev, counter, stream, nullptr, order_dev);
   cudaFreeAsync(counter, stream);
   return rc;
 }
@@ -309,6 +347,8 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
   const size_t o_mint = out->mint ? take(N * 8) : 0, o_pp = out->p1p2 ? take(N * 48) : 0;
   const size_t o_pt = out->pose_toc ? take(N * 192) : 0;
   const size_t o_step = step_in ? take(N * STEP_IN_DOUBLES * 8) : 0;
+  const bool use_order = !step_in && n >= 4096 && n <= 0x7fffffff;
+  const size_t o_order = use_order ? take(N * 4) : 0;
   const size_t o_cnt = take(8);
   char *arena = nullptr;
   cudaError_t e = cudaMallocAsync(&arena, off, stream);
@@ -343,6 +383,13 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
     else memcpy(staging, motions, N * 48 * 8);
   }
   if (step_in) STEP(cudaMemcpyAsync(arena + o_step, step_in, N * STEP_IN_DOUBLES * 8, cudaMemcpyHostToDevice, stream));
+  std::vector<int32_t> order_host;
+  if (use_order && rc == C2A_B200_OK)
+  {
+    order_host.resize(N);
+    schedule_order(staging, n, a->root_ang_radius, b->root_ang_radius, order_host.data());
+    STEP(cudaMemcpyAsync(arena + o_order, order_host.data(), N * 4, cudaMemcpyHostToDevice, stream));
+  }
   STEP(cudaMemcpyAsync(arena + o_pose, staging, N * 48 * 8, cudaMemcpyHostToDevice, stream));
   if (seed_a) STEP(cudaMemcpyAsync(arena + o_sa, seed_a, N * 4, cudaMemcpyHostToDevice, stream));
   if (seed_b) STEP(cudaMemcpyAsync(arena + o_sb, seed_b, N * 4, cudaMemcpyHostToDevice, stream));
@@ -350,7 +397,8 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
   if (rc == C2A_B200_OK)
     rc = launch_batch(a, b, (const double *)(arena + o_pose), seed_a ? (const int32_t *)(arena + o_sa) : nullptr,
                       seed_b ? (const int32_t *)(arena + o_sb) : nullptr, n, tol_d, tol_t, &d,
-                      (unsigned long long *)(arena + o_cnt), stream, step_in ? (const double *)(arena + o_step) : nullptr);
+                      (unsigned long long *)(arena + o_cnt), stream, step_in ? (const double *)(arena + o_step) : nullptr,
+                      use_order ? (const int32_t *)(arena + o_order) : nullptr);
 #define BACK(field, ofs, bytes) \
   if (out->field) STEP(cudaMemcpyAsync(out->field, arena + ofs, bytes, cudaMemcpyDeviceToHost, stream));
   BACK(status, o_status, N * 4) BACK(collisionfree, o_cf, N * 4) BACK(num_ca, o_nca, N * 4)
@@ -509,16 +557,21 @@ int c2a_b200_test_sincos(const double *x, int64_t n, double *s, double *c)
 
 // Development aid: enable (enable != 0) or disable phase statistics of the solve kernel on the current
 // device and read them back: out[0..5] = {expand passes, expand lanes, leaf passes, leaf lanes, advance
-// passes, advance lanes} accumulated since the last enable.
-int c2a_b200_phase_stats(int32_t enable, uint64_t *out6)
+// passes, advance lanes} accumulated since the last enable; out[6..8] = globaltimer ns at launch start, at
+// the first failed claim (batch drained) and at the last slot retirement (one launch between enables).
+int c2a_b200_phase_stats(int32_t enable, uint64_t *out9)
 {
-  if (out6 && g_stats_dev)
+  if (out9 && g_stats_dev)
   {
     CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpy(out6, g_stats_dev, 6 * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out9, g_stats_dev, 9 * 8, cudaMemcpyDeviceToHost));
   }
-  if (enable && !g_stats_dev) CUDA_TRY(cudaMalloc(&g_stats_dev, 8 * 8));
-  if (enable) CUDA_TRY(cudaMemset(g_stats_dev, 0, 8 * 8));
+  if (enable && !g_stats_dev) CUDA_TRY(cudaMalloc(&g_stats_dev, 16 * 8));
+  if (enable)
+  {
+    const unsigned long long init[9] = {0, 0, 0, 0, 0, 0, ~0ull, ~0ull, 0};
+    CUDA_TRY(cudaMemcpy(g_stats_dev, init, sizeof(init), cudaMemcpyHostToDevice));
+  }
   if (!enable && g_stats_dev) { cudaFree(g_stats_dev); g_stats_dev = nullptr; }
   return C2A_B200_OK;
 }

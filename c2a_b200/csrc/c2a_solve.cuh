@@ -65,6 +65,7 @@ struct BatchArgs
   unsigned long long *counter;
   double *stacks;         // [n_slots][stack_entries][ENTRY_DOUBLES]
   int stack_entries;
+  const int *order;       // optional [n]: the k-th claim takes query order[k] (longest-expected first); NULL = identity
   const double *step_in;  // optional [n][STEP_IN_DOUBLES]: single-step mode (C2A_TimeOfContactStep), see below
   unsigned long long *stats;  // optional [8]: per phase {passes, lanes used}: expand, leaf, advance; NULL = off
 };
@@ -107,6 +108,7 @@ C2A_DEV void load9(double d[9], const double *s)
   for (int i = 0; i < 9; i++) d[i] = __ldg(s + i);
 }
 C2A_DEV void load3(double d[3], const double *s) { d[0] = __ldg(s); d[1] = __ldg(s + 1); d[2] = __ldg(s + 2); }
+C2A_DEV unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 C2A_DEV void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __device__ __noinline__ double tri_distance_nl(const double R[9], const double T[3], const double *t1,
@@ -116,6 +118,15 @@ __device__ __noinline__ double tri_distance_nl(const double R[9], const double T
   load9(a, t1);
   load9(b, t2);
   return tri_distance(R, T, a, b, p, q);
+}
+
+// pose integration is only used by the (rare) ADVANCE phase; keeping it out of line keeps the libm
+// sin/cos bodies (~600 SASS instructions per call site) out of the hot loop's instruction footprint
+__device__ __noinline__ void motion_pose_nl(const double *rec, double t, double R[9], double T[3])
+{
+  Motion m;
+  motion_load(m, rec);
+  motion_pose(m, t, R, T);
 }
 
 __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const BatchArgs args)
@@ -132,6 +143,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
 #define SD(f, s) sd[(f) * Q + (s)]
 #define SI(f, s) si[(f) * Q + (s)]
 
+  if (args.stats && threadIdx.x == 0) atomicMin(args.stats + 6, global_ns());  // launch start
   SI(I_STATE, lane) = ST_ADVANCE;
   SI(I_QLO, lane) = -1; SI(I_QHI, lane) = -1;
   SI(I_PENDING, lane) = 0;
@@ -157,7 +169,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
     {
       const int k = phase == ST_TRAVERSE ? 0 : (phase == ST_LEAF ? 2 : 4);
       atomicAdd(args.stats + k, 1ull);
-      atomicAdd(args.stats + k + 1, (unsigned long long)(phase == ST_TRAVERSE ? 2 * min(nT, 16) : (phase == ST_LEAF ? nL : nA)));
+      atomicAdd(args.stats + k + 1, (unsigned long long)(phase == ST_TRAVERSE ? 2 * min(nT, 16) : (phase == ST_LEAF ? nL : nA)));  // LEAF: slots served (9 lanes each, 3 per round)
     }
     if (phase == ST_TRAVERSE)
     {
@@ -400,7 +412,6 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
         bool pending = SI(I_PENDING, slot) != 0;
         int numCA = SI(I_NUMCA, slot);
         double lamda = SD(F_LAMDA, slot);
-        Motion m1, m2;
         if (q >= 0 && !pending && args.step_in)
         {
           // single-step mode: report this traversal and release the slot
@@ -464,14 +475,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
               if (o.pose_toc)
               {
                 double R[9], T[3];
-                motion_load(m1, rec);
-                motion_pose(m1, toc, R, T);
+                motion_pose_nl(rec, toc, R, T);
 #pragma unroll
                 for (int i = 0; i < 9; i++) o.pose_toc[24 * q + i] = R[i];
 #pragma unroll
                 for (int i = 0; i < 3; i++) o.pose_toc[24 * q + 9 + i] = T[i];
-                motion_load(m2, rec + MOTION_DOUBLES);
-                motion_pose(m2, toc, R, T);
+                motion_pose_nl(rec + MOTION_DOUBLES, toc, R, T);
 #pragma unroll
                 for (int i = 0; i < 9; i++) o.pose_toc[24 * q + 12 + i] = R[i];
 #pragma unroll
@@ -499,10 +508,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
         {
           // claim the next query
           const long long nq = (long long)atomicAdd(args.counter, 1ull);
-          if (nq >= args.n) SI(I_STATE, slot) = ST_EXIT;
+          if (nq >= args.n)
+          {
+            SI(I_STATE, slot) = ST_EXIT;
+            if (args.stats) { atomicMin(args.stats + 7, global_ns()); atomicMax(args.stats + 8, global_ns()); }  // batch drained / last slot retired
+          }
           else
           {
-            q = nq;
+            q = args.order ? (long long)__ldg(args.order + nq) : nq;
             const double *rec = args.motions + (size_t)(2 * MOTION_DOUBLES) * q;
             const double w1 = __ldg(rec + 18), w2 = __ldg(rec + MOTION_DOUBLES + 18);
             if (!args.step_in && w1 < 1e-8 && w2 < 1e-8)
@@ -555,10 +568,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
           }
           else
           {
-            motion_load(m1, rec);
-            motion_pose(m1, lamda, r1, tt1);
-            motion_load(m2, rec + MOTION_DOUBLES);
-            motion_pose(m2, lamda, R2, T2);
+            motion_pose_nl(rec, lamda, r1, tt1);
+            motion_pose_nl(rec + MOTION_DOUBLES, lamda, R2, T2);
           }
           mt_m(Rrel, r1, R2);
           v_sub(Tt, T2, tt1);

@@ -132,11 +132,20 @@ int c2a_b200_toc_step_batch(const c2a_b200_model *a, const c2a_b200_model *b, co
 
 /* Batched C2A_QueryTimeOfContact (+ the pose outputs of C2A_Solve) with everything already resident
  * on the models' device: motions_dev [n][C2A_B200_MOTION_DOUBLES] from c2a_b200_motions_from_poses,
- * seeds and outputs device pointers.  Enqueued on `cuda_stream` (a cudaStream_t; NULL = default
+ * seeds, the optional claim order and outputs device pointers.  Enqueued on `cuda_stream` (a cudaStream_t; NULL = default
  * stream) without synchronising. */
 int c2a_b200_solve_batch_device(const c2a_b200_model *a, const c2a_b200_model *b, const double *motions_dev,
-                                const int32_t *seed_a_dev, const int32_t *seed_b_dev, int64_t n, double tol_d,
-                                double tol_t, const c2a_b200_results *out_dev, void *cuda_stream);
+                                const int32_t *seed_a_dev, const int32_t *seed_b_dev, const int32_t *order_dev,
+                                int64_t n, double tol_d, double tol_t, const c2a_b200_results *out_dev,
+                                void *cuda_stream);
+
+/* Claim order for a batch (host): order[k] = the query the k-th free worker takes.  Queries expected to
+ * need many conservative-advancement steps (small closing speed relative to their motion bound) come
+ * first, so their sequential chains do not form the tail of the launch.  Purely a scheduling hint:
+ * results are independent of it.  The host-buffer entries compute it internally; pass it (uploaded) as
+ * order_dev to c2a_b200_solve_batch_device, or NULL for index order. */
+int c2a_b200_schedule_order(const c2a_b200_model *a, const c2a_b200_model *b, const double *motions, int64_t n,
+                            int32_t *order);
 
 /* Number of kernel launches issued by this library on the calling process so far. */
 int64_t c2a_b200_launch_count(void);

@@ -1,0 +1,15 @@
+"""Exactly the bench workload, one c2a_solve_kernel launch over --batch queries (after a tiny warm-up launch).
+For single-metric ncu passes over the real launch (e.g. DRAM traffic):  ncu --launch-skip 1 -c 1 ..."""
+import argparse, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from c2a_b200 import api, meshes, workloads
+ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=1000000)
+a = ap.parse_args()
+bvh = api.build_bvh(meshes.torus_knot(512, 32)[0]); model = api.Model(bvh, 0)
+poses = workloads.approach_batch(a.batch, 20260002, radius=workloads.KNOT_RADIUS)
+f = ("status", "num_bv_tests", "num_tri_tests", "num_ca")
+api.solve_batch(model, model, poses[:256], fields=f)
+out = api.solve_batch(model, model, poses, fields=f)
+nbv, ntri = int(out["num_bv_tests"].sum()), int(out["num_tri_tests"].sum())
+print("launch:", a.batch, "queries nbv", nbv, "ntri", ntri, "algorithmic bytes", 208 * nbv + 144 * ntri + 448 * a.batch)
