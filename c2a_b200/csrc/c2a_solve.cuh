@@ -169,16 +169,27 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
     {
       const int k = phase == ST_TRAVERSE ? 0 : (phase == ST_LEAF ? 2 : 4);
       atomicAdd(args.stats + k, 1ull);
-      atomicAdd(args.stats + k + 1, (unsigned long long)(phase == ST_TRAVERSE ? 2 * min(nT, 16) : (phase == ST_LEAF ? nL : nA)));  // LEAF: slots served (9 lanes each, 3 per round)
+      atomicAdd(args.stats + k + 1, (unsigned long long)(phase == ST_TRAVERSE ? (nT >= 5 ? 2 * min(nT, 16) : (nT >= 3 ? 6 * nT : (nT == 2 ? 28 : 30))) : (phase == ST_LEAF ? nL : nA)));  // LEAF: slots served (9 lanes each, 3 per round)
     }
     if (phase == ST_TRAVERSE)
     {
       // -------------------------------------------------------------------- EXPAND ----------
-      const int j = lane >> 1, c = lane & 1;
-      if (j < nT)
+      // G lanes per slot.  G = 2 (16 slots per pass) is the plain expansion: lane c runs child test c.
+      // With few traversable slots (the tail of a launch, or a single-query call) the idle lanes
+      // look ahead: G = 8 / 16 / 32 lanes evaluate the child tests of the next D = 2 / 3 / 4 levels
+      // below the slot's node pair (2 + 4 + ... tests, every lane walking its own path of child
+      // choices), and the group then replays the reference's decisions level by level along the
+      // path actually taken.  A child test is a pure function of (node pair, transform, poses) and
+      // the distance cannot change before the next leaf, so the replay is exact; tests off the
+      // taken path are discarded and not counted.
+      const int G = nT >= 5 ? 2 : (nT >= 3 ? 8 : (nT == 2 ? 16 : 32));
+      const int D = nT >= 5 ? 1 : (nT >= 3 ? 2 : (nT == 2 ? 3 : 4));
+      const int grp = lane / G, t = lane - grp * G;
+      if (grp < nT)
       {
-        const int slot = __fns(mT, 0, j + 1);
-        const unsigned pair = 3u << (lane & ~1);
+        const int slot = __fns(mT, 0, grp + 1);
+        const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << (grp * G));
+        const int gbase = grp * G;
         double *stk = stack_base + (size_t)slot * stack_stride;
         int b1 = SI(I_CURB1, slot), b2 = SI(I_CURB2, slot);
         int sp = SI(I_SP, slot);
@@ -196,7 +207,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
         else
         {
           // pop until an entry passes the descend test with the CURRENT distance (C2A.cpp:1281-1351);
-          // entries that fail contribute their BV-level step bound.  Both lanes of the pair do this
+          // entries that fail contribute their BV-level step bound.  All lanes of the group do this
           // redundantly on identical data.
           while (sp > 0)
           {
@@ -223,7 +234,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
         if (b1 < 0)
         {
           // stack drained: this CA step's traversal is over
-          if (c == 0) { SD(F_MINT, slot) = mint; SI(I_SP, slot) = 0; SI(I_STATE, slot) = ST_ADVANCE; }
+          if (t == 0) { SD(F_MINT, slot) = mint; SI(I_SP, slot) = 0; SI(I_STATE, slot) = ST_ADVANCE; }
         }
         else
         {
@@ -234,10 +245,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
             mb.size = SD(F_CURSZ2, slot); mb.first_child = SI(I_CURFC2, slot);
           }
           else { ma = A.meta[b1]; mb = B.meta[b2]; }
-          const bool l1 = ma.first_child < 0, l2 = mb.first_child < 0;
-          if (l1 && l2)
+          if (ma.first_child < 0 && mb.first_child < 0)
           {
-            if (c == 0)
+            if (t == 0)
             {
               SD(F_MINT, slot) = mint; SI(I_SP, slot) = sp; SI(I_CURB1, slot) = -1;
               SI(I_LEAFB1, slot) = b1; SI(I_LEAFB2, slot) = b2; SI(I_STATE, slot) = ST_LEAF;
@@ -245,40 +255,60 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
           }
           else
           {
-            // expansion, C2A.cpp:1192-1279: child pairs 'a' (lane c=0) and 'c' (lane c=1)
-            int n1, n2;  // node ids of my child pair
-            double Rc[9], Tc[3];
-            const double *gs, *gt, *rl;  // side-1 node geom, side-2 node geom, R_loc of the side-1 node
-            NodeMeta cm1 = ma, cm2 = mb;  // NodeMeta of my child pair: loaded now, consumed at commit
-            if (l2 || (!l1 && (ma.size > mb.size)))
+            // ---- my test: level L (0-based), index i within the level; bit (L-l) of i picks the
+            // child ('a' = 0, 'c' = 1) at level l of my walk
+            const int ntests = (2 << D) - 2;
+            const int L = 30 - __clz(t + 2);       // floor(log2(t+2)) - 1
+            const int idx = t + 2 - (2 << L);
+            bool valid = t < ntests;
+            int n1 = b1, n2 = b2;
+            NodeMeta cm1 = ma, cm2 = mb;           // NodeMeta of the node pair reached so far
+            const double *gs = nullptr, *gt = nullptr, *rl = nullptr;
+            if (valid)
             {
-              n1 = ma.first_child + c; n2 = b2;
-              cm1 = A.meta[n1];
-              gs = A.geom + (size_t)n1 * GEOM_STRIDE; gt = B.geom + (size_t)b2 * GEOM_STRIDE;
-              rl = A.rloc + (size_t)n1 * 9;
-              double Rn[9], Tn[3], Tt[3];
-              load9(Rn, gs); load3(Tn, gs + 9);
-              mt_m(Rc, Rn, R); v_sub(Tt, T, Tn); mt_v(Tc, Rn, Tt);
+              for (int l = 0; l <= L; l++)
+              {
+                const bool l1 = cm1.first_child < 0, l2 = cm2.first_child < 0;
+                if (l1 && l2) { valid = false; break; }  // my path runs through a leaf pair
+                const int bit = (idx >> (L - l)) & 1;
+                double Rc[9], Tc[3];
+                if (l2 || (!l1 && (cm1.size > cm2.size)))
+                {
+                  // expansion of side 1, C2A.cpp:1194-1209
+                  n1 = cm1.first_child + bit;
+                  cm1 = A.meta[n1];
+                  gs = A.geom + (size_t)n1 * GEOM_STRIDE; gt = B.geom + (size_t)n2 * GEOM_STRIDE;
+                  rl = A.rloc + (size_t)n1 * 9;
+                  double Rn[9], Tn[3], Tt[3];
+                  load9(Rn, gs); load3(Tn, gs + 9);
+                  mt_m(Rc, Rn, R); v_sub(Tt, T, Tn); mt_v(Tc, Rn, Tt);
+                }
+                else
+                {
+                  // expansion of side 2, C2A.cpp:1211-1225
+                  n2 = cm2.first_child + bit;
+                  cm2 = B.meta[n2];
+                  gs = A.geom + (size_t)n1 * GEOM_STRIDE; gt = B.geom + (size_t)n2 * GEOM_STRIDE;
+                  rl = A.rloc + (size_t)n1 * 9;
+                  double Rn[9], Tn[3];
+                  load9(Rn, gt); load3(Tn, gt + 9);
+                  m_m(Rc, R, Rn); m_v_p(Tc, R, Tn, T);
+                }
+#pragma unroll
+                for (int i = 0; i < 9; i++) R[i] = Rc[i];
+                T[0] = Tc[0]; T[1] = Tc[1]; T[2] = Tc[2];
+              }
             }
-            else
-            {
-              n1 = b1; n2 = mb.first_child + c;
-              cm2 = B.meta[n2];
-              gs = A.geom + (size_t)b1 * GEOM_STRIDE; gt = B.geom + (size_t)n2 * GEOM_STRIDE;
-              rl = A.rloc + (size_t)b1 * 9;
-              double Rn[9], Tn[3];
-              load9(Rn, gt); load3(Tn, gt + 9);
-              m_m(Rc, R, Rn); m_v_p(Tc, R, Tn, T);
-            }
-            prefetch_l1(rl); prefetch_l1(rl + 8);  // R_loc is only consumed after the rectangle distance
             // child BV test (C2A.cpp:1237-1276): RSS distance, direction to world frame, the two
-            // directional motion bounds, the child's conservative step bound
-            double d, mt = 0.0;
+            // directional motion bounds, the child's conservative step bound.  (R, T) now place my child pair.
+            double d = 0.0, mt = 0.0;
+            if (valid)
             {
+              prefetch_l1(rl); prefetch_l1(rl + 8);  // R_loc is only consumed after the rectangle distance
               double S[3];
               const double a0 = __ldg(gs + 12), a1 = __ldg(gs + 13), ra = __ldg(gs + 14);
               const double e0 = __ldg(gt + 12), e1 = __ldg(gt + 13), rb = __ldg(gt + 14);
-              d = rss_rect_dist(Rc, Tc, a0, a1, e0, e1, S);
+              d = rss_rect_dist(R, T, a0, a1, e0, e1, S);
               d -= (ra + rb);
               d = (d < 0.0) ? 0.0 : d;
               if (d != 0.0)
@@ -303,53 +333,83 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
                 if (mt <= 0) mt = 0.0;
               }
             }
-            // commit in the reference's order: the child with the smaller d is visited first; ties
-            // visit 'a' first (the test is d2 < d1)
-            const double d_o = __shfl_xor_sync(pair, d, 1), mt_o = __shfl_xor_sync(pair, mt, 1);
+            const bool my_leafpair = valid && cm1.first_child < 0 && cm2.first_child < 0;
             const bool v = mt < upbound && ((d < (dist - abs_err)) || (d * (1 + rel_err) < dist));
-            const bool v_o = mt_o < upbound && ((d_o < (dist - abs_err)) || (d_o * (1 + rel_err) < dist));
-            const double d1 = c ? d_o : d, d2 = c ? d : d_o;
-            const bool c_first = d2 < d1;
-            const bool near = (c == 1) == c_first;
-            const bool v_near = near ? v : v_o, v_far = near ? v_o : v;
-            if (v)
+            const int flags = (valid ? 1 : 0) | (my_leafpair ? 2 : 0) | (v ? 4 : 0);
+
+            // ---- replay the reference's decisions level by level (C2A.cpp:1281-1351): every lane of
+            // the group computes the same walk from the shuffled (d, mint, flags)
+            int P = 0;             // index (within its level) of the node pair being expanded
+            int levels = 0;        // expansions committed
+            int write_cur = -1;    // group lane whose child becomes the current entry
+            int write_leaf = -1;   // group lane whose child is a leaf pair to hand to the LEAF phase
+            bool me_push = false; int my_push_sp = 0;
+            for (int l = 0; l < D; l++)
             {
-              if (near || !v_near)
+              const int la = (2 << l) - 2 + 2 * P, lc = la + 1;  // group lanes of children 'a' and 'c'
+              const double d_a = __shfl_sync(gmask, d, gbase + la), d_c = __shfl_sync(gmask, d, gbase + lc);
+              const double m_a = __shfl_sync(gmask, mt, gbase + la), m_c = __shfl_sync(gmask, mt, gbase + lc);
+              const int f_a = __shfl_sync(gmask, flags, gbase + la), f_c = __shfl_sync(gmask, flags, gbase + lc);
+              // (both children of an inner node exist together, so f_a and f_c are valid together)
+              levels++;
+              const bool v_a = f_a & 4, v_c = f_c & 4;
+              const bool c_first = d_c < d_a;  // ties visit 'a' first (the test is d2 < d1)
+              const bool v_near = c_first ? v_c : v_a, v_far = c_first ? v_a : v_c;
+              const int near_lane = c_first ? lc : la, far_lane = c_first ? la : lc;
+              if (!v_a && m_a < mint) mint = m_a;
+              if (!v_c && m_c < mint) mint = m_c;
+              if (!v_near && !v_far) { write_cur = -1; break; }
+              int next_lane;
+              if (v_near)
               {
-#pragma unroll
-                for (int i = 0; i < 9; i++) SD(F_CUR + i, slot) = Rc[i];
-#pragma unroll
-                for (int i = 0; i < 3; i++) SD(F_CUR + 9 + i, slot) = Tc[i];
-                SI(I_CURB1, slot) = n1; SI(I_CURB2, slot) = n2;
-                SD(F_CURSZ1, slot) = cm1.size; SI(I_CURFC1, slot) = cm1.first_child;
-                SD(F_CURSZ2, slot) = cm2.size; SI(I_CURFC2, slot) = cm2.first_child;
-                // warm L1 with the node pair the next expansion of this slot will fetch
-                const bool nl1 = cm1.first_child < 0, nl2 = cm2.first_child < 0;
-                if (!(nl1 && nl2))
+                next_lane = near_lane;
+                if (v_far)
                 {
-                  const double *nx = (nl2 || (!nl1 && (cm1.size > cm2.size))) ? A.geom + (size_t)cm1.first_child * GEOM_STRIDE
-                                                                              : B.geom + (size_t)cm2.first_child * GEOM_STRIDE;
-                  prefetch_l1(nx); prefetch_l1(nx + GEOM_STRIDE);
+                  if (t == far_lane) { me_push = true; my_push_sp = sp; }
+                  sp++;
                 }
               }
-              else
-              {
-                double *e = stk + (size_t)sp * ENTRY_DOUBLES;
-                double2 *e2 = reinterpret_cast<double2 *>(e);
-                e2[0] = make_double2(Rc[0], Rc[1]); e2[1] = make_double2(Rc[2], Rc[3]);
-                e2[2] = make_double2(Rc[4], Rc[5]); e2[3] = make_double2(Rc[6], Rc[7]);
-                e2[4] = make_double2(Rc[8], Tc[0]); e2[5] = make_double2(Tc[1], Tc[2]);
-                e2[6] = make_double2(d, mt); e2[7] = make_double2(__hiloint2double(n1, n2), 0.0);
-              }
+              else next_lane = far_lane;
+              const int f_next = (next_lane == la) ? f_a : f_c;
+              if (f_next & 2) { write_leaf = next_lane; write_cur = -1; break; }
+              write_cur = next_lane;
+              P = 2 * P + (next_lane == lc ? 1 : 0);
             }
-            if (c == 0)
+
+            if (me_push)
             {
-              if (!v && mt < mint) mint = mt;
-              if (!v_o && mt_o < mint) mint = mt_o;
+              double *e = stk + (size_t)my_push_sp * ENTRY_DOUBLES;
+              double2 *e2 = reinterpret_cast<double2 *>(e);
+              e2[0] = make_double2(R[0], R[1]); e2[1] = make_double2(R[2], R[3]);
+              e2[2] = make_double2(R[4], R[5]); e2[3] = make_double2(R[6], R[7]);
+              e2[4] = make_double2(R[8], T[0]); e2[5] = make_double2(T[1], T[2]);
+              e2[6] = make_double2(d, mt); e2[7] = make_double2(__hiloint2double(n1, n2), 0.0);
+            }
+            if (t == write_cur)
+            {
+#pragma unroll
+              for (int i = 0; i < 9; i++) SD(F_CUR + i, slot) = R[i];
+#pragma unroll
+              for (int i = 0; i < 3; i++) SD(F_CUR + 9 + i, slot) = T[i];
+              SI(I_CURB1, slot) = n1; SI(I_CURB2, slot) = n2;
+              SD(F_CURSZ1, slot) = cm1.size; SI(I_CURFC1, slot) = cm1.first_child;
+              SD(F_CURSZ2, slot) = cm2.size; SI(I_CURFC2, slot) = cm2.first_child;
+              // warm L1 with the node pair the next expansion of this slot will fetch
+              const bool nl1 = cm1.first_child < 0, nl2 = cm2.first_child < 0;
+              const double *nx = (nl2 || (!nl1 && (cm1.size > cm2.size))) ? A.geom + (size_t)cm1.first_child * GEOM_STRIDE
+                                                                          : B.geom + (size_t)cm2.first_child * GEOM_STRIDE;
+              prefetch_l1(nx); prefetch_l1(nx + GEOM_STRIDE);
+            }
+            if (t == write_leaf)
+            {
+              SI(I_LEAFB1, slot) = n1; SI(I_LEAFB2, slot) = n2; SI(I_STATE, slot) = ST_LEAF;
+            }
+            if (t == 0)
+            {
               SD(F_MINT, slot) = mint;
-              SI(I_SP, slot) = sp + ((v_near && v_far) ? 1 : 0);
-              SI(I_NBV, slot) = SI(I_NBV, slot) + 2;
-              if (!v && !v_o) SI(I_CURB1, slot) = -1;
+              SI(I_SP, slot) = sp;
+              SI(I_NBV, slot) = SI(I_NBV, slot) + 2 * levels;
+              if (write_cur < 0) SI(I_CURB1, slot) = -1;
             }
           }
         }
