@@ -24,11 +24,18 @@ class Bvh(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("n_tris", C.c_int32),
                 ("R", C.c_void_p), ("Tr", C.c_void_p), ("l", C.c_void_p), ("r", C.c_void_p),
                 ("R_loc", C.c_void_p), ("ang_radius", C.c_void_p), ("first_child", C.c_void_p),
-                ("tris", C.c_void_p)]
+                ("tris", C.c_void_p), ("tri_vidx", C.c_void_p)]
+
+
+# mirrors struct c2a_b200_contact
+CONTACT_DTYPE = np.dtype([("type_a", np.int32), ("type_b", np.int32), ("fid_a", np.int32, 3), ("fid_b", np.int32, 3),
+                          ("tri_a", np.int32), ("tri_b", np.int32), ("pa", np.float64, 3), ("pb", np.float64, 3),
+                          ("dist", np.float64)], align=True)
 
 
 class Results(C.Structure):
-    _fields_ = [(name, C.c_void_p) for name, _, _ in RESULT_FIELDS]
+    _fields_ = [(name, C.c_void_p) for name, _, _ in RESULT_FIELDS] + [("num_contact", C.c_void_p), ("contacts", C.c_void_p),
+                                                                       ("max_contacts", C.c_int32)]
 
 
 def lib():
@@ -59,13 +66,16 @@ def launch_count():
     return int(lib().c2a_b200_launch_count())
 
 
-def build_bvh(tris9):
-    """Host-side RSS BVH build (the product's own builder, c2a_host_model.cpp).  tris9: [n,9] float64.
+def build_bvh(tris9, vidx=None):
+    """Host-side RSS BVH build (the product's own builder, c2a_host_model.cpp).  tris9: [n,9] float64;
+    vidx: optional [n,3] int32 vertex indices per triangle (labels of contact features).
     Returns a dict of numpy arrays with the keys of ``struct c2a_b200_bvh`` plus ``tri_ids``/``depth``."""
     tris9 = np.ascontiguousarray(tris9, dtype=np.float64).reshape(-1, 9)
     n = tris9.shape[0]
     h = C.c_void_p()
-    _check(lib().c2a_b200_bvh_build(tris9.ctypes.data_as(C.c_void_p), C.c_int32(n), C.byref(h)))
+    vi = None if vidx is None else np.ascontiguousarray(vidx, dtype=np.int32).reshape(n, 3)
+    _check(lib().c2a_b200_bvh_build_indexed(tris9.ctypes.data_as(C.c_void_p),
+                                            vi.ctypes.data_as(C.c_void_p) if vi is not None else None, C.c_int32(n), C.byref(h)))
     try:
         v = Bvh()
         ids = C.c_void_p()
@@ -85,6 +95,8 @@ def build_bvh(tris9):
                "tris": arr(v.tris, 9 * n, C.c_double, np.float64).reshape(n, 9),
                "tri_ids": arr(ids, n, C.c_int32, np.int32),
                "depth": depth.value}
+        if v.tri_vidx:
+            out["tri_vidx"] = arr(v.tri_vidx, 3 * n, C.c_int32, np.int32).reshape(n, 3)
     finally:
         lib().c2a_b200_bvh_free(h)
     return out
@@ -106,6 +118,10 @@ class Model:
         fc = np.ascontiguousarray(bvh["first_child"], dtype=np.int32)
         keep.append(fc)
         s.first_child = fc.ctypes.data
+        if bvh.get("tri_vidx") is not None:
+            tv = np.ascontiguousarray(bvh["tri_vidx"], dtype=np.int32)
+            keep.append(tv)
+            s.tri_vidx = tv.ctypes.data
         h = C.c_void_p()
         _check(lib().c2a_b200_model_upload(C.byref(s), C.c_int32(device), C.byref(h)))
         self.h = h
@@ -129,8 +145,10 @@ class Model:
             pass
 
 
-def solve_batch(model_a, model_b, poses, seed_a=None, seed_b=None, tol_d=1e-4, tol_t=1e-4, fields=None):
-    """Host-buffer entry (H2D + kernel + D2H inside the call).  Returns a dict of numpy arrays."""
+def solve_batch(model_a, model_b, poses, seed_a=None, seed_b=None, tol_d=1e-4, tol_t=1e-4, fields=None, max_contacts=0):
+    """Host-buffer entry (H2D + kernel + D2H inside the call).  Returns a dict of numpy arrays.
+    max_contacts > 0 also runs the contact pass of C2A_Solve: ``num_contact`` [n] and ``contacts``
+    [n, max_contacts] (CONTACT_DTYPE, visiting order)."""
     poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 48)
     n = poses.shape[0]
     res = Results()
@@ -141,6 +159,12 @@ def solve_batch(model_a, model_b, poses, seed_a=None, seed_b=None, tol_d=1e-4, t
         a = np.zeros((n,) + shape, dtype=dt)
         out[name] = a
         setattr(res, name, a.ctypes.data)
+    if max_contacts > 0:
+        out["num_contact"] = np.zeros(n, dtype=np.int32)
+        out["contacts"] = np.zeros((n, max_contacts), dtype=CONTACT_DTYPE)
+        res.num_contact = out["num_contact"].ctypes.data
+        res.contacts = out["contacts"].ctypes.data
+        res.max_contacts = max_contacts
     sa = None if seed_a is None else np.ascontiguousarray(seed_a, dtype=np.int32)
     sb = None if seed_b is None else np.ascontiguousarray(seed_b, dtype=np.int32)
     _check(lib().c2a_b200_solve_batch(model_a.h, model_b.h, poses.ctypes.data_as(C.c_void_p),
@@ -148,6 +172,19 @@ def solve_batch(model_a, model_b, poses, seed_a=None, seed_b=None, tol_d=1e-4, t
                                       sb.ctypes.data_as(C.c_void_p) if sb is not None else None,
                                       C.c_int64(n), C.c_double(tol_d), C.c_double(tol_t), C.byref(res)))
     return out
+
+
+def contacts_batch(model_a, model_b, poses24, threshold, max_contacts=64):
+    """Batched C2A_QueryContact: poses24 [n,24] (pose of A, pose of B), threshold [n]."""
+    poses24 = np.ascontiguousarray(poses24, dtype=np.float64).reshape(-1, 24)
+    n = poses24.shape[0]
+    thr = np.ascontiguousarray(np.broadcast_to(np.asarray(threshold, dtype=np.float64), (n,)))
+    num = np.zeros(n, dtype=np.int32)
+    recs = np.zeros((n, max_contacts), dtype=CONTACT_DTYPE)
+    _check(lib().c2a_b200_contacts_batch(model_a.h, model_b.h, poses24.ctypes.data_as(C.c_void_p), thr.ctypes.data_as(C.c_void_p),
+                                         C.c_int64(n), C.c_int32(max_contacts), num.ctypes.data_as(C.c_void_p),
+                                         recs.ctypes.data_as(C.c_void_p)))
+    return num, recs
 
 
 def motions_from_poses(poses, threads=0, out=None):

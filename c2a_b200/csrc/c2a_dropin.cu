@@ -132,7 +132,10 @@ int C2A_Model::EndModel()
   std::vector<double> t9((size_t)9 * num_tris);
   for (int i = 0; i < num_tris; i++)
     for (int k = 0; k < 3; k++) { t9[9 * (size_t)i + k] = storage_[i].p1[k]; t9[9 * (size_t)i + 3 + k] = storage_[i].p2[k]; t9[9 * (size_t)i + 6 + k] = storage_[i].p3[k]; }
-  int rc = c2a_b200_bvh_build(t9.data(), num_tris, &host_bvh);
+  std::vector<int32_t> vi((size_t)3 * num_tris);
+  for (int i = 0; i < num_tris; i++)
+    for (int k = 0; k < 3; k++) vi[3 * (size_t)i + k] = storage_[i].index_[k];
+  int rc = c2a_b200_bvh_build_indexed(t9.data(), vi.data(), num_tris, &host_bvh);
   if (rc) return PQP_ERR_MODEL_OUT_OF_MEMORY;
   c2a_b200_bvh view;
   const int32_t *ids = 0;
@@ -345,6 +348,41 @@ PQP_REAL C2A_QueryTimeOfContact(CInterpMotion *objmotion1, CInterpMotion *objmot
   return toc;
 }
 
+// C2A/src/C2A.cpp:1937-1966: contact features at the motions' CURRENT poses
+PQP_REAL C2A_QueryContact(CInterpMotion *objmotion1, CInterpMotion *objmotion2, C2A_TimeOfContactResult *res, C2A_Model *o1,
+                          C2A_Model *o2, double threshold)
+{
+  res->num_contact = 0;
+  res->UpboundTOC = 1;
+  if (!o1 || !o2 || !o1->gpu || !o2->gpu) return 0;
+  double poses[24];
+  pose12(objmotion1->transform, poses);
+  pose12(objmotion2->transform, poses + 12);
+  const int cap = 256;
+  std::vector<c2a_b200_contact> recs(cap);
+  int32_t n = 0;
+  int rc = c2a_b200_contacts_batch(o1->gpu, o2->gpu, poses, &threshold, 1, cap, &n, recs.data());
+  if (rc == 0 && n > cap)
+  {
+    recs.resize(n);
+    rc = c2a_b200_contacts_batch(o1->gpu, o2->gpu, poses, &threshold, 1, n, &n, recs.data());
+  }
+  if (rc != 0) { fprintf(stderr, "c2a_b200: %s\n", c2a_b200_last_error()); return 0; }
+  // the reference push_front()s in visiting order
+  for (int i = 0; i < n; i++)
+  {
+    const c2a_b200_contact &c = recs[i];
+    ContactF f;
+    f.FeatureType_A = c.type_a; f.FeatureType_B = c.type_b;
+    for (int k = 0; k < 3; k++) { f.FeatureID_A[k] = c.fid_a[k]; f.FeatureID_B[k] = c.fid_b[k]; f.P_A[k] = c.pa[k]; f.P_B[k] = c.pb[k]; }
+    f.TriangleID_A = c.tri_a; f.TriangleID_B = c.tri_b;
+    f.Distance = c.dist;
+    res->cont_l.push_front(f);
+  }
+  res->num_contact = n;
+  return 0;
+}
+
 // C2A/src/C2A.cpp:1778-1931 (rotational branch)
 int C2A_TimeOfContactStep(CInterpMotion *objmotion1, CInterpMotion *objmotion2, C2A_TimeOfContactResult *res,
                           PQP_REAL R1[3][3], PQP_REAL T1[3], C2A_Model *o1, PQP_REAL R2[3][3], PQP_REAL T2[3],
@@ -414,6 +452,8 @@ C2A_Result C2A_Solve(Transform *trans00, Transform *trans01, C2A_Model *obj1_tes
     motion2.integrate(dres.toc, qua);
     trans1.Set_Rotation(Quaternion(qua[1], qua[2], qua[3], qua[0]));
     trans1.Set_Translation(Coord3D(qua[4], qua[5], qua[6]));
+    const double threshold = 2 * dres.distance + 0.001;  // C2A.cpp:2433
+    C2A_QueryContact(&motion1, &motion2, &dres, obj1_tested, obj2_tested, threshold);
   }
   time_of_contact = dres.toc;
   number_of_contact = dres.num_contact;

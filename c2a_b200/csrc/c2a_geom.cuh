@@ -439,6 +439,71 @@ C2A_DEV double tri_dist(double P[3], double Q[3], const double S[9], const doubl
   return 0;
 }
 
+// TriDist with contact features: the reference's in-tree variant (C2A/src/C2A.cpp:165-405) used by the
+// contact pass.  f?_type: 0 vertex, 1 edge, 2 face; f?_fid: vertex / edge index (-1 for a face).
+C2A_DEV double tri_dist_features(double P[3], double Q[3], const double S[9], const double T[9], int &f1_type,
+                                 int &f1_fid, int &f2_type, int &f2_fid)
+{
+  double Sv[9], Tv[9], VEC[3], V[3], Z[3];
+  v_sub(&Sv[0], &S[3], &S[0]); v_sub(&Sv[3], &S[6], &S[3]); v_sub(&Sv[6], &S[0], &S[6]);
+  v_sub(&Tv[0], &T[3], &T[0]); v_sub(&Tv[3], &T[6], &T[3]); v_sub(&Tv[6], &T[0], &T[6]);
+  double minP[3], minQ[3], mindd;
+  int shown_disjoint = 0;
+  mindd = v_dist2(&S[0], &T[0]) + 1;
+#pragma unroll 1
+  for (int i = 0; i < 3; i++)
+  {
+#pragma unroll 1
+    for (int j = 0; j < 3; j++)
+    {
+      seg_points(VEC, P, Q, &S[3 * i], &Sv[3 * i], &T[3 * j], &Tv[3 * j]);
+      v_sub(V, Q, P);
+      const double dd = v_dot(V, V);
+      if (dd <= mindd)
+      {
+        v_cpy(minP, P); v_cpy(minQ, Q); mindd = dd;
+        f1_type = 1; f1_fid = i; f2_type = 1; f2_fid = j;
+        v_sub(Z, &S[3 * ((i + 2) % 3)], P);
+        double a = v_dot(Z, VEC);
+        v_sub(Z, &T[3 * ((j + 2) % 3)], Q);
+        double b = v_dot(Z, VEC);
+        if ((a <= 0) && (b >= 0)) return sqrt(dd);
+        const double p = v_dot(V, VEC);
+        if (a < 0) a = 0;
+        if (b > 0) b = 0;
+        if ((p - a + b) > 0) shown_disjoint = 1;
+      }
+    }
+  }
+  // which vertex the vertex-face cases pick (the feature id): the same choice face_vertex_case makes
+  auto pick_vertex = [&](const double *F, const double *Fv, const double *Gt) {
+    double n[3], W[3], proj[3];
+    v_cross(n, &Fv[0], &Fv[3]);
+    v_sub(W, &F[0], &Gt[0]); proj[0] = v_dot(W, n);
+    v_sub(W, &F[0], &Gt[3]); proj[1] = v_dot(W, n);
+    v_sub(W, &F[0], &Gt[6]); proj[2] = v_dot(W, n);
+    int point = -1;
+    if ((proj[0] > 0) && (proj[1] > 0) && (proj[2] > 0)) { point = (proj[0] < proj[1]) ? 0 : 1; if (proj[2] < (point ? proj[1] : proj[0])) point = 2; }
+    else if ((proj[0] < 0) && (proj[1] < 0) && (proj[2] < 0)) { point = (proj[0] > proj[1]) ? 0 : 1; if (proj[2] > (point ? proj[1] : proj[0])) point = 2; }
+    return point;
+  };
+  double onFace[3], vert[3];
+  if (face_vertex_case(S, Sv, T, shown_disjoint, onFace, vert))
+  {
+    f1_type = 2; f1_fid = -1; f2_type = 0; f2_fid = pick_vertex(S, Sv, T);
+    v_cpy(P, onFace); v_cpy(Q, vert);
+    return sqrt(v_dist2(P, Q));
+  }
+  if (face_vertex_case(T, Tv, S, shown_disjoint, onFace, vert))
+  {
+    f1_type = 0; f1_fid = pick_vertex(T, Tv, S); f2_type = 2; f2_fid = -1;
+    v_cpy(P, vert); v_cpy(Q, onFace);
+    return sqrt(v_dist2(P, Q));
+  }
+  if (shown_disjoint) { v_cpy(P, minP); v_cpy(Q, minQ); return sqrt(mindd); }
+  return 0;
+}
+
 // PQP TriDistance: bring triangle 2 into triangle 1's frame, then TriDist.
 C2A_DEV double tri_distance(const double R[9], const double T[3], const double t1[9], const double t2[9],
                             double p[3], double q[3])

@@ -30,6 +30,7 @@ struct HostBvh
   std::vector<int32_t> first_child;
   std::vector<double> tris;      // permuted order
   std::vector<int32_t> tri_ids;  // original index of each permuted triangle
+  std::vector<int32_t> tri_vidx; // vertex indices per permuted triangle (empty if not given)
   int depth = 0;
 };
 
@@ -398,14 +399,25 @@ struct c2a_b200_host_bvh
 
 extern "C" {
 
-int c2a_b200_bvh_build(const double *tris9, int32_t n_tris, c2a_b200_host_bvh **out)
+int c2a_b200_bvh_build_indexed(const double *tris9, const int32_t *vidx3, int32_t n_tris, c2a_b200_host_bvh **out)
 {
   if (!tris9 || !out || n_tris <= 0) return C2A_B200_ERR_ARG;
   c2a_b200_host_bvh *h = new c2a_b200_host_bvh();
   h->n_tris = n_tris;
   c2a_host::build(tris9, n_tris, h->b);
+  if (vidx3)
+  {
+    h->b.tri_vidx.resize((size_t)3 * n_tris);
+    for (int i = 0; i < n_tris; i++)
+      for (int k = 0; k < 3; k++) h->b.tri_vidx[(size_t)3 * i + k] = vidx3[(size_t)3 * h->b.tri_ids[i] + k];
+  }
   *out = h;
   return C2A_B200_OK;
+}
+
+int c2a_b200_bvh_build(const double *tris9, int32_t n_tris, c2a_b200_host_bvh **out)
+{
+  return c2a_b200_bvh_build_indexed(tris9, nullptr, n_tris, out);
 }
 
 int c2a_b200_bvh_view(const c2a_b200_host_bvh *h, c2a_b200_bvh *view, const int32_t **tri_ids, int32_t *depth)
@@ -416,6 +428,7 @@ int c2a_b200_bvh_view(const c2a_b200_host_bvh *h, c2a_b200_bvh *view, const int3
   view->R = h->b.R.data(); view->Tr = h->b.Tr.data(); view->l = h->b.l.data(); view->r = h->b.r.data();
   view->R_loc = h->b.R_loc.data(); view->ang_radius = h->b.ang.data(); view->first_child = h->b.first_child.data();
   view->tris = h->b.tris.data();
+  view->tri_vidx = h->b.tri_vidx.empty() ? nullptr : h->b.tri_vidx.data();
   if (tri_ids) *tri_ids = h->b.tri_ids.data();
   if (depth) *depth = h->b.depth;
   return C2A_B200_OK;

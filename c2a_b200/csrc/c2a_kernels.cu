@@ -15,6 +15,7 @@
 
 #include "../../include/c2a_b200.h"
 #include "c2a_solve.cuh"
+#include "c2a_contact.cuh"
 
 namespace c2a {
 
@@ -42,6 +43,7 @@ struct c2a_b200_model
   double root_ang_radius;
   double *geom, *rloc, *tris;
   c2a::NodeMeta *meta;
+  int *tri_vidx;  // may be NULL
 };
 
 using namespace c2a;
@@ -195,7 +197,7 @@ int c2a_b200_model_upload(const c2a_b200_bvh *bvh, int32_t device, c2a_b200_mode
   c2a_b200_model *m = new c2a_b200_model();
   m->device = device; m->n_nodes = n; m->n_tris = nt; m->depth = depth;
   m->root_ang_radius = bvh->ang_radius[0];
-  m->geom = m->rloc = m->tris = nullptr; m->meta = nullptr;
+  m->geom = m->rloc = m->tris = nullptr; m->meta = nullptr; m->tri_vidx = nullptr;
   cudaError_t e;
   if ((e = cudaMalloc(&m->geom, geom.size() * sizeof(double))) != cudaSuccess ||
       (e = cudaMalloc(&m->rloc, (size_t)n * 9 * sizeof(double))) != cudaSuccess ||
@@ -204,7 +206,9 @@ int c2a_b200_model_upload(const c2a_b200_bvh *bvh, int32_t device, c2a_b200_mode
       (e = cudaMemcpy(m->geom, geom.data(), geom.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMemcpy(m->rloc, bvh->R_loc, (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMemcpy(m->meta, meta.data(), (size_t)n * sizeof(NodeMeta), cudaMemcpyHostToDevice)) != cudaSuccess ||
-      (e = cudaMemcpy(m->tris, bvh->tris, (size_t)nt * 9 * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess)
+      (e = cudaMemcpy(m->tris, bvh->tris, (size_t)nt * 9 * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (bvh->tri_vidx && ((e = cudaMalloc(&m->tri_vidx, (size_t)nt * 3 * sizeof(int))) != cudaSuccess ||
+                         (e = cudaMemcpy(m->tri_vidx, bvh->tri_vidx, (size_t)nt * 3 * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess)))
   {
     c2a_b200_model_free(m);
     return fail(C2A_B200_ERR_CUDA, std::string("model upload: ") + cudaGetErrorString(e));
@@ -217,7 +221,7 @@ int c2a_b200_model_free(c2a_b200_model *m)
 {
   if (!m) return C2A_B200_OK;
   cudaSetDevice(m->device);
-  cudaFree(m->geom); cudaFree(m->rloc); cudaFree(m->meta); cudaFree(m->tris);
+  cudaFree(m->geom); cudaFree(m->rloc); cudaFree(m->meta); cudaFree(m->tris); cudaFree(m->tri_vidx);
   delete m;
   return C2A_B200_OK;
 }
@@ -277,6 +281,32 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   return C2A_B200_OK;
 }
 
+// contact pass (c2a_contact.cuh) over n queries; all pointers device-resident
+static int launch_contacts(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses24, const double *threshold,
+                           const double *distance, const int *collisionfree, const int *status, int64_t n, int max_contacts,
+                           int *num_contact, c2a_b200_contact *contacts, unsigned long long *counter, cudaStream_t stream)
+{
+  if (a->depth + b->depth + 2 > CONTACT_STACK) return fail(C2A_B200_ERR_DEPTH, "BVH depths exceed the contact-pass stack");
+  ContactArgs args;
+  args.A = DevModel{a->geom, a->rloc, a->meta, a->tris, a->n_nodes, a->n_tris};
+  args.B = DevModel{b->geom, b->rloc, b->meta, b->tris, b->n_nodes, b->n_tris};
+  args.vidxA = a->tri_vidx; args.vidxB = b->tri_vidx;
+  args.poses = poses24; args.threshold = threshold; args.distance = distance; args.collisionfree = collisionfree;
+  args.status = status; args.n = n; args.max_contacts = max_contacts; args.num_contact = num_contact;
+  args.contacts = contacts; args.counter = counter;
+  int sms = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, a->device));
+  long long blocks = (long long)sms * 4;
+  const long long need = (n + 127) / 128;
+  if (blocks > need) blocks = need;
+  if (blocks < 1) blocks = 1;
+  CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+  c2a_contact_kernel<<<(unsigned)blocks, 128, 0, stream>>>(args);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return C2A_B200_OK;
+}
+
 static int check_pair(const c2a_b200_model *a, const c2a_b200_model *b, int64_t n, const void *poses,
                       const c2a_b200_results *out)
 {
@@ -287,6 +317,38 @@ static int check_pair(const c2a_b200_model *a, const c2a_b200_model *b, int64_t 
     return fail(C2A_B200_ERR_DEPTH, "BVH depths exceed the traversal stack (" + std::to_string(a->depth) + "+" +
                                         std::to_string(b->depth) + ")");
   return C2A_B200_OK;
+}
+
+int c2a_b200_contacts_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses24,
+                            const double *threshold, int64_t n, int32_t max_contacts, int32_t *num_contact,
+                            c2a_b200_contact *contacts)
+{
+  if (!a || !b || n < 0 || (n > 0 && (!poses24 || !threshold))) return fail(C2A_B200_ERR_ARG, "NULL argument");
+  if (contacts && max_contacts <= 0) return fail(C2A_B200_ERR_ARG, "contacts requested with max_contacts <= 0");
+  if (a->device != b->device) return fail(C2A_B200_ERR_DEVICE, "models live on different devices");
+  if (n == 0) return C2A_B200_OK;
+  CUDA_TRY(cudaSetDevice(a->device));
+  const size_t N = (size_t)n, cbytes = contacts ? N * (size_t)max_contacts * sizeof(c2a_b200_contact) : 0;
+  char *arena = nullptr;
+  const size_t o_thr = N * 192, o_nc = o_thr + ((N * 8 + 255) & ~(size_t)255), o_cnt = o_nc + ((N * 4 + 255) & ~(size_t)255),
+               o_ct = o_cnt + 256, total = o_ct + cbytes;
+  CUDA_TRY(cudaMalloc(&arena, total));
+  int rc = C2A_B200_OK;
+  cudaError_t e;
+  if ((e = cudaMemcpy(arena, poses24, N * 192, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(arena + o_thr, threshold, N * 8, cudaMemcpyHostToDevice)) != cudaSuccess)
+    rc = fail(C2A_B200_ERR_CUDA, cudaGetErrorString(e));
+  if (rc == C2A_B200_OK)
+    rc = launch_contacts(a, b, (const double *)arena, (const double *)(arena + o_thr), nullptr, nullptr, nullptr, n, max_contacts,
+                         (int *)(arena + o_nc), contacts ? (c2a_b200_contact *)(arena + o_ct) : nullptr,
+                         (unsigned long long *)(arena + o_cnt), 0);
+  if (rc == C2A_B200_OK && (e = cudaDeviceSynchronize()) != cudaSuccess) rc = fail(C2A_B200_ERR_CUDA, cudaGetErrorString(e));
+  if (rc == C2A_B200_OK && num_contact && (e = cudaMemcpy(num_contact, arena + o_nc, N * 4, cudaMemcpyDeviceToHost)) != cudaSuccess)
+    rc = fail(C2A_B200_ERR_CUDA, cudaGetErrorString(e));
+  if (rc == C2A_B200_OK && contacts && (e = cudaMemcpy(contacts, arena + o_ct, cbytes, cudaMemcpyDeviceToHost)) != cudaSuccess)
+    rc = fail(C2A_B200_ERR_CUDA, cudaGetErrorString(e));
+  cudaFree(arena);
+  return rc;
 }
 
 int c2a_b200_motions_from_poses(const double *poses, int64_t n, double *motions, int32_t n_threads)
@@ -330,6 +392,8 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
   int rc = check_pair(a, b, n, poses ? poses : motions, out);
   if (rc) return rc;
   if (n == 0) return C2A_B200_OK;
+  const bool want_contacts = !step_in && (out->num_contact || out->contacts);
+  if (want_contacts && out->contacts && out->max_contacts <= 0) return fail(C2A_B200_ERR_ARG, "contacts requested with max_contacts <= 0");
   CUDA_TRY(cudaSetDevice(a->device));
   cudaStream_t stream;
   CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -340,12 +404,15 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_pose = take(N * 48 * 8);
   const size_t o_sa = seed_a ? take(N * 4) : 0, o_sb = seed_b ? take(N * 4) : 0;
-  const size_t o_status = out->status ? take(N * 4) : 0, o_cf = out->collisionfree ? take(N * 4) : 0;
+  const size_t o_status = (out->status || want_contacts) ? take(N * 4) : 0, o_cf = (out->collisionfree || want_contacts) ? take(N * 4) : 0;
   const size_t o_nca = out->num_ca ? take(N * 4) : 0, o_nbv = out->num_bv_tests ? take(N * 4) : 0;
   const size_t o_ntri = out->num_tri_tests ? take(N * 4) : 0;
-  const size_t o_toc = out->toc ? take(N * 8) : 0, o_dist = out->distance ? take(N * 8) : 0;
+  const size_t o_toc = out->toc ? take(N * 8) : 0, o_dist = (out->distance || want_contacts) ? take(N * 8) : 0;
   const size_t o_mint = out->mint ? take(N * 8) : 0, o_pp = out->p1p2 ? take(N * 48) : 0;
-  const size_t o_pt = out->pose_toc ? take(N * 192) : 0;
+  const size_t o_pt = (out->pose_toc || want_contacts) ? take(N * 192) : 0;
+  const size_t o_nc = want_contacts ? take(N * 4) : 0;
+  const size_t o_ct = (want_contacts && out->contacts) ? take(N * (size_t)out->max_contacts * sizeof(c2a_b200_contact)) : 0;
+  const size_t o_cnt2 = want_contacts ? take(8) : 0;
   const size_t o_step = step_in ? take(N * STEP_IN_DOUBLES * 8) : 0;
   const bool use_order = !step_in && n >= 4096 && n <= 0x7fffffff;
   const size_t o_order = use_order ? take(N * 4) : 0;
@@ -359,16 +426,16 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
   }
   c2a_b200_results d;
   memset(&d, 0, sizeof(d));
-  if (out->status) d.status = (int32_t *)(arena + o_status);
-  if (out->collisionfree) d.collisionfree = (int32_t *)(arena + o_cf);
+  if (out->status || want_contacts) d.status = (int32_t *)(arena + o_status);
+  if (out->collisionfree || want_contacts) d.collisionfree = (int32_t *)(arena + o_cf);
   if (out->num_ca) d.num_ca = (int32_t *)(arena + o_nca);
   if (out->num_bv_tests) d.num_bv_tests = (int32_t *)(arena + o_nbv);
   if (out->num_tri_tests) d.num_tri_tests = (int32_t *)(arena + o_ntri);
   if (out->toc) d.toc = (double *)(arena + o_toc);
-  if (out->distance) d.distance = (double *)(arena + o_dist);
+  if (out->distance || want_contacts) d.distance = (double *)(arena + o_dist);
   if (out->mint) d.mint = (double *)(arena + o_mint);
   if (out->p1p2) d.p1p2 = (double *)(arena + o_pp);
-  if (out->pose_toc) d.pose_toc = (double *)(arena + o_pt);
+  if (out->pose_toc || want_contacts) d.pose_toc = (double *)(arena + o_pt);
 
   rc = C2A_B200_OK;
 #define STEP(x)                                                                              \
@@ -399,6 +466,13 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
                       seed_b ? (const int32_t *)(arena + o_sb) : nullptr, n, tol_d, tol_t, &d,
                       (unsigned long long *)(arena + o_cnt), stream, step_in ? (const double *)(arena + o_step) : nullptr,
                       use_order ? (const int32_t *)(arena + o_order) : nullptr);
+  if (want_contacts && rc == C2A_B200_OK)
+    rc = launch_contacts(a, b, d.pose_toc, nullptr, d.distance, d.collisionfree, d.status, n, out->max_contacts,
+                         (int *)(arena + o_nc), out->contacts ? (c2a_b200_contact *)(arena + o_ct) : nullptr,
+                         (unsigned long long *)(arena + o_cnt2), stream);
+  if (want_contacts && out->num_contact) STEP(cudaMemcpyAsync(out->num_contact, arena + o_nc, N * 4, cudaMemcpyDeviceToHost, stream));
+  if (want_contacts && out->contacts)
+    STEP(cudaMemcpyAsync(out->contacts, arena + o_ct, N * (size_t)out->max_contacts * sizeof(c2a_b200_contact), cudaMemcpyDeviceToHost, stream));
 #define BACK(field, ofs, bytes) \
   if (out->field) STEP(cudaMemcpyAsync(out->field, arena + ofs, bytes, cudaMemcpyDeviceToHost, stream));
   BACK(status, o_status, N * 4) BACK(collisionfree, o_cf, N * 4) BACK(num_ca, o_nca, N * 4)

@@ -13,8 +13,7 @@
 //
 // Deliberate differences (each documented in DESIGN.md):
 //   * nothing prints to stdout (the reference prints from EndModel and from every C2A_Solve call);
-//   * the contact pass of C2A_Solve (C2A_QueryContact, C2A/src/C2A.cpp:2433) is not implemented yet:
-//     number_of_contact is 0 and dres.cont_l stays empty;
+//   * contact features: FeatureID entries the reference leaves uninitialised are -1 here;
 //   * the translation-only branch (both angular speeds < 1e-8, C2A/src/C2A.cpp:2391-2395) is not
 //     implemented yet: such a query returns CollisionNotFound with dres.numCA = -1 instead of a result;
 //   * degenerate rotations do not exit(0) (C2A/LinearMath.h:768).
@@ -250,6 +249,9 @@ C2A_Result C2A_Solve(Transform *trans00, Transform *trans01, C2A_Model *obj1_tes
 
 PQP_REAL C2A_QueryTimeOfContact(CInterpMotion *objmotion1, CInterpMotion *objmotion2, C2A_TimeOfContactResult *res,
                                 C2A_Model *o1, C2A_Model *o2, PQP_REAL tolerance_d, PQP_REAL tolerance_t, int qsize = 2);
+
+PQP_REAL C2A_QueryContact(CInterpMotion *objmotion1, CInterpMotion *objmotion2, C2A_TimeOfContactResult *res, C2A_Model *o1,
+                          C2A_Model *o2, double threshold);
 
 int C2A_TimeOfContactStep(CInterpMotion *objmotion1, CInterpMotion *objmotion2, C2A_TimeOfContactResult *res,
                           PQP_REAL R1[3][3], PQP_REAL T1[3], C2A_Model *o1, PQP_REAL R2[3][3], PQP_REAL T2[3],

@@ -51,7 +51,20 @@ typedef struct c2a_b200_bvh
   const double *ang_radius;   /* [n_nodes]    C2A_BV::angularRadius */
   const int32_t *first_child; /* [n_nodes]    */
   const double *tris;         /* [n_tris][9]  p1,p2,p3 */
+  const int32_t *tri_vidx;    /* [n_tris][3]  vertex indices of each triangle (C2A_Tri::Index(), C2A/C2A_Tri.h:46-52),
+                                              builder order; only used to label contact features; may be NULL */
 } c2a_b200_bvh;
+
+/* One contact of the contact pass (ContactF, C2A/C2A.h:117-153). */
+typedef struct c2a_b200_contact
+{
+  int32_t type_a, type_b;     /* FeatureType_A/B: 1 vertex, 2 edge, 3 face */
+  int32_t fid_a[3], fid_b[3]; /* FeatureID_A/B: vertex indices of the feature; entries the reference leaves
+                                 uninitialised (2nd/3rd of a vertex, 3rd of an edge) are -1; all -1 without tri_vidx */
+  int32_t tri_a, tri_b;       /* TriangleID_A/B (builder order) */
+  double pa[3], pb[3];        /* P_A in model A's frame, P_B in model B's frame */
+  double dist;                /* Distance */
+} c2a_b200_contact;
 
 typedef struct c2a_b200_model c2a_b200_model; /* device-resident model, opaque */
 typedef struct c2a_b200_host_bvh c2a_b200_host_bvh; /* host-resident built hierarchy, opaque */
@@ -63,6 +76,8 @@ typedef struct c2a_b200_host_bvh c2a_b200_host_bvh; /* host-resident built hiera
  * c2a_b200_bvh_free); tri_ids [n_tris] maps the builder's permuted triangle order back to the AddTri
  * index (PQP Tri::id). */
 int c2a_b200_bvh_build(const double *tris9, int32_t n_tris, c2a_b200_host_bvh **out);
+/* same, keeping the vertex indices of each triangle (AddTri's i1,i2,i3) for contact-feature labels */
+int c2a_b200_bvh_build_indexed(const double *tris9, const int32_t *vidx3, int32_t n_tris, c2a_b200_host_bvh **out);
 int c2a_b200_bvh_view(const c2a_b200_host_bvh *h, struct c2a_b200_bvh *view, const int32_t **tri_ids,
                       int32_t *depth);
 int c2a_b200_bvh_free(c2a_b200_host_bvh *h);
@@ -82,6 +97,13 @@ typedef struct c2a_b200_results
   double *p1p2;           /* [n][6]  ::p1, ::p2 (closest points, model-1 frame)                        */
   double *pose_toc;       /* [n][24] trans0, trans1 of C2A_Solve as R(9)+T(3) each; only written when
                                      collisionfree == 0, like the reference                            */
+  /* contact pass of C2A_Solve (C2A_QueryContact at the TOC pose with threshold 2*distance + 0.001,
+   * C2A/src/C2A.cpp:2431-2434); run only when num_contact or contacts is non-NULL */
+  int32_t *num_contact;   /* [n]     ::num_contact == number_of_contact of C2A_Solve (0 for free queries) */
+  c2a_b200_contact *contacts; /* [n][max_contacts] in the traversal's visiting order (the reference's
+                                     std::list is this order reversed: it push_front()s); the first
+                                     min(num_contact, max_contacts) entries of each row are written */
+  int32_t max_contacts;
 } c2a_b200_results;
 
 int c2a_b200_device_count(int32_t *count);
@@ -104,6 +126,12 @@ int c2a_b200_model_info(const c2a_b200_model *m, int32_t *device, int32_t *n_nod
 int c2a_b200_solve_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses,
                          const int32_t *seed_a, const int32_t *seed_b, int64_t n, double tol_d, double tol_t,
                          const c2a_b200_results *out);
+
+/* Batched C2A_QueryContact (C2A/C2A.h:284-289, C2A/src/C2A.cpp:1937-1966): all triangle pairs within
+ * threshold[i] at the poses poses24[i] = pose of A, pose of B (R(9)+T(3) each).  Host buffers. */
+int c2a_b200_contacts_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses24,
+                            const double *threshold, int64_t n, int32_t max_contacts, int32_t *num_contact,
+                            c2a_b200_contact *contacts);
 
 /* Host half of the motion model: what constructing the two CInterpMotion_Linear objects does in
  * C2A_Solve (C2A/src/C2A.cpp:2378-2379 -> C2A/src/InterpMotion.cpp:148-168, 486-491, 228-270).

@@ -20,6 +20,12 @@ RESULT_DTYPE = np.dtype([
 OrcResult = RESULT_DTYPE
 
 
+# mirrors struct orc_contact
+CONTACT_DTYPE = np.dtype([("type_a", np.int32), ("type_b", np.int32), ("fid_a", np.int32, 3), ("fid_b", np.int32, 3),
+                          ("tri_a", np.int32), ("tri_b", np.int32), ("pa", np.float64, 3), ("pb", np.float64, 3),
+                          ("dist", np.float64)], align=True)
+
+
 class _Bvh(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("n_tris", C.c_int32),
                 ("R", C.c_void_p), ("Tr", C.c_void_p), ("l", C.c_void_p), ("r", C.c_void_p),
@@ -88,6 +94,19 @@ class _Port:
                                  _ptr(seedB) if seedB is not None else None,
                                  C.c_double(tol_d), C.c_double(tol_t), _ptr(out), C.c_int32(threads))
         return out
+
+    def contacts(self, bvhA, bvhB, pose1, pose2, threshold, vidx_a=None, vidx_b=None, max_out=4096):
+        """Contact pass at the given poses; records in visiting order. Returns (count, records)."""
+        sA, sB = bvh_struct(bvhA), bvh_struct(bvhB)
+        p1 = np.ascontiguousarray(pose1, np.float64); p2 = np.ascontiguousarray(pose2, np.float64)
+        va = None if vidx_a is None else np.ascontiguousarray(vidx_a, np.int32)
+        vb = None if vidx_b is None else np.ascontiguousarray(vidx_b, np.int32)
+        out = np.zeros(max_out, dtype=CONTACT_DTYPE)
+        self.lib.orc_contacts.restype = C.c_int64
+        n = self.lib.orc_contacts(C.byref(sA), C.byref(sB), _ptr(va) if va is not None else None,
+                                  _ptr(vb) if vb is not None else None, _ptr(p1), _ptr(p2), C.c_double(threshold),
+                                  C.c_int64(max_out), _ptr(out))
+        return int(n), out[:min(int(n), max_out)]
 
     def rect_dist(self, Rab, Tab, a, b):
         Rab = np.ascontiguousarray(Rab, np.float64); Tab = np.ascontiguousarray(Tab, np.float64)
@@ -159,6 +178,15 @@ class _Ref:
         P = np.zeros(3); Q = np.zeros(3); S = np.full(3, np.nan)
         d = self.lib.ref_rect_dist(_ptr(Rab), _ptr(Tab), _ptr(a), _ptr(b), _ptr(P), _ptr(Q), _ptr(S))
         return d, P, Q, S
+
+    def solve_contacts(self, mA, mB, poses48, seedA=0, seedB=0, max_out=4096):
+        """The full unmodified C2A_Solve for one query: (result record, num_contact, contact records in LIST order)."""
+        p = np.ascontiguousarray(poses48, np.float64)
+        res = np.zeros(1, dtype=RESULT_DTYPE)
+        out = np.zeros(max_out, dtype=CONTACT_DTYPE)
+        self.lib.ref_solve_contacts.restype = C.c_int64
+        n = self.lib.ref_solve_contacts(mA.h, mB.h, _ptr(p), C.c_int32(seedA), C.c_int32(seedB), _ptr(res), C.c_int64(max_out), _ptr(out))
+        return res[0], int(n), out[:min(int(n), max_out)]
 
     def tri_distance_intree(self, R, T, t1, t2):
         R = np.ascontiguousarray(R, np.float64); T = np.ascontiguousarray(T, np.float64)

@@ -826,3 +826,188 @@ extern "C" void orc_solve_batch(const orc_bvh *A, const orc_bvh *B, const double
   for (int t = 0; t < n_threads; t++) th.emplace_back(work, t);
   for (auto &t : th) t.join();
 }
+
+// ---- contact pass ------------------------------------------------------------------------
+// TriDist with contact features: the reference's in-tree copy, C2A/src/C2A.cpp:165-405.
+extern "C" double orc_tri_dist_features(double P[3], double Q[3], const double S[9], const double T[9],
+                                        int32_t *f1_type, int32_t *f1_fid, int32_t *f2_type, int32_t *f2_fid,
+                                        int32_t *collided)
+{
+  double Sv[9], Tv[9], VEC[3], V[3], Z[3];
+  v_sub(&Sv[0], &S[3], &S[0]); v_sub(&Sv[3], &S[6], &S[3]); v_sub(&Sv[6], &S[0], &S[6]);
+  v_sub(&Tv[0], &T[3], &T[0]); v_sub(&Tv[3], &T[6], &T[3]); v_sub(&Tv[6], &T[0], &T[6]);
+  double minP[3], minQ[3], mindd;
+  int shown_disjoint = 0;
+  mindd = v_dist2(&S[0], &T[0]) + 1;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+    {
+      orc_seg_points(VEC, P, Q, &S[3 * i], &Sv[3 * i], &T[3 * j], &Tv[3 * j]);
+      v_sub(V, Q, P);
+      double dd = v_dot(V, V);
+      if (dd <= mindd)
+      {
+        v_cpy(minP, P); v_cpy(minQ, Q); mindd = dd;
+        *f1_type = 1; *f1_fid = i; *f2_type = 1; *f2_fid = j;
+        v_sub(Z, &S[3 * ((i + 2) % 3)], P);
+        double a = v_dot(Z, VEC);
+        v_sub(Z, &T[3 * ((j + 2) % 3)], Q);
+        double b = v_dot(Z, VEC);
+        if ((a <= 0) && (b >= 0)) return sqrt(dd);
+        double p = v_dot(V, VEC);
+        if (a < 0) a = 0;
+        if (b > 0) b = 0;
+        if ((p - a + b) > 0) shown_disjoint = 1;
+      }
+    }
+  double onFace[3], vert[3];
+  {
+    // face of S against the vertices of T, :262-339 (the feature ids need the chosen vertex: redo the choice)
+    double n[3], nl, proj[3];
+    v_cross(n, &Sv[0], &Sv[3]); nl = v_dot(n, n);
+    if (nl > 1e-15)
+    {
+      v_sub(V, &S[0], &T[0]); proj[0] = v_dot(V, n);
+      v_sub(V, &S[0], &T[3]); proj[1] = v_dot(V, n);
+      v_sub(V, &S[0], &T[6]); proj[2] = v_dot(V, n);
+      int point = -1;
+      if ((proj[0] > 0) && (proj[1] > 0) && (proj[2] > 0)) { point = (proj[0] < proj[1]) ? 0 : 1; if (proj[2] < proj[point]) point = 2; }
+      else if ((proj[0] < 0) && (proj[1] < 0) && (proj[2] < 0)) { point = (proj[0] > proj[1]) ? 0 : 1; if (proj[2] > proj[point]) point = 2; }
+      if (face_vertex_case(S, Sv, T, shown_disjoint, onFace, vert))
+      {
+        *f1_type = 2; *f1_fid = -1; *f2_type = 0; *f2_fid = point;
+        v_cpy(P, onFace); v_cpy(Q, vert);
+        return sqrt(v_dist2(P, Q));
+      }
+    }
+  }
+  {
+    double n[3], nl, proj[3];
+    v_cross(n, &Tv[0], &Tv[3]); nl = v_dot(n, n);
+    if (nl > 1e-15)
+    {
+      v_sub(V, &T[0], &S[0]); proj[0] = v_dot(V, n);
+      v_sub(V, &T[0], &S[3]); proj[1] = v_dot(V, n);
+      v_sub(V, &T[0], &S[6]); proj[2] = v_dot(V, n);
+      int point = -1;
+      if ((proj[0] > 0) && (proj[1] > 0) && (proj[2] > 0)) { point = (proj[0] < proj[1]) ? 0 : 1; if (proj[2] < proj[point]) point = 2; }
+      else if ((proj[0] < 0) && (proj[1] < 0) && (proj[2] < 0)) { point = (proj[0] > proj[1]) ? 0 : 1; if (proj[2] > proj[point]) point = 2; }
+      if (face_vertex_case(T, Tv, S, shown_disjoint, onFace, vert))
+      {
+        *f1_type = 0; *f1_fid = point; *f2_type = 2; *f2_fid = -1;
+        v_cpy(P, vert); v_cpy(Q, onFace);
+        return sqrt(v_dist2(P, Q));
+      }
+    }
+  }
+  if (shown_disjoint) { v_cpy(P, minP); v_cpy(Q, minQ); return sqrt(mindd); }
+  *collided = 1;
+  return 0;
+}
+
+namespace {
+struct ContactCtx
+{
+  const orc_bvh *A, *B;
+  const int32_t *va, *vb;
+  double Rrel[9], Trel[3], threshold;
+  int64_t max_out, count;
+  orc_contact *out;
+};
+
+inline void feature_ids(int32_t out[3], int type, int fid, const int32_t *v)
+{
+  out[0] = out[1] = out[2] = -1;
+  if (!v) return;
+  if (type == 0) out[0] = v[fid];
+  else if (type == 1) { out[0] = v[fid]; out[1] = v[(fid + 1) % 3]; }
+  else if (type == 2) { out[0] = v[0]; out[1] = v[1]; out[2] = v[2]; }
+}
+
+// TOCStepRecurse_Dis_contact, C2A/src/C2A.cpp:1523-1725
+void contact_recurse(ContactCtx &cx, const double R[9], const double T[3], int b1, int b2)
+{
+  const orc_bvh *A = cx.A, *B = cx.B;
+  const int l1 = A->first_child[b1] < 0, l2 = B->first_child[b2] < 0;
+  if (l1 && l2)
+  {
+    const int ta = -A->first_child[b1] - 1, tb = -B->first_child[b2] - 1;
+    double p[3], q[3], tri2[9];
+    m_v_p(&tri2[0], cx.Rrel, &B->tris[9 * tb + 0], cx.Trel);
+    m_v_p(&tri2[3], cx.Rrel, &B->tris[9 * tb + 3], cx.Trel);
+    m_v_p(&tri2[6], cx.Rrel, &B->tris[9 * tb + 6], cx.Trel);
+    int32_t f1t = -1, f1f = 0, f2t = -1, f2f = 0, col = 0;
+    const double d = orc_tri_dist_features(p, q, &A->tris[9 * ta], tri2, &f1t, &f1f, &f2t, &f2f, &col);
+    if (f1t == -1 || f2t == -1) return;
+    if (d <= cx.threshold)
+    {
+      if (cx.count < cx.max_out)
+      {
+        orc_contact &c = cx.out[cx.count];
+        c.type_a = f1t + 1; c.type_b = f2t + 1;
+        feature_ids(c.fid_a, f1t, f1f, cx.va ? cx.va + 3 * ta : 0);
+        feature_ids(c.fid_b, f2t, f2f, cx.vb ? cx.vb + 3 * tb : 0);
+        c.tri_a = ta; c.tri_b = tb;
+        v_cpy(c.pa, p);
+        double tmp[3];
+        v_sub(tmp, q, cx.Trel);
+        mt_v(c.pb, cx.Rrel, tmp);
+        c.dist = d;
+      }
+      cx.count++;
+    }
+    return;
+  }
+  int a1, a2, c1, c2;
+  double R1[9], T1[3], R2[9], T2[3], Tt[3], S[3];
+  const double sz1 = bv_size(A, b1), sz2 = bv_size(B, b2);
+  if (l2 || (!l1 && (sz1 > sz2)))
+  {
+    a1 = A->first_child[b1]; a2 = b2; c1 = a1 + 1; c2 = b2;
+    mt_m(R1, &A->R[9 * a1], R); v_sub(Tt, T, &A->Tr[3 * a1]); mt_v(T1, &A->R[9 * a1], Tt);
+    mt_m(R2, &A->R[9 * c1], R); v_sub(Tt, T, &A->Tr[3 * c1]); mt_v(T2, &A->R[9 * c1], Tt);
+  }
+  else
+  {
+    a1 = b1; a2 = B->first_child[b2]; c1 = b1; c2 = a2 + 1;
+    m_m(R1, R, &B->R[9 * a2]); m_v_p(T1, R, &B->Tr[3 * a2], T);
+    m_m(R2, R, &B->R[9 * c2]); m_v_p(T2, R, &B->Tr[3 * c2], T);
+  }
+  const double d1 = bv_distance(R1, T1, A, a1, B, a2, S);
+  const double d2 = bv_distance(R2, T2, A, c1, B, c2, S);
+  // res->distance = threshold, abs_err = rel_err = 0 during this pass (:1755-1760)
+#define NEAR_ENOUGH(d) (((d) < (cx.threshold - 0)) || ((d) * (1.0 + 0) < cx.threshold))
+  if (d2 < d1)
+  {
+    if (NEAR_ENOUGH(d2)) contact_recurse(cx, R2, T2, c1, c2);
+    if (NEAR_ENOUGH(d1)) contact_recurse(cx, R1, T1, a1, a2);
+  }
+  else
+  {
+    if (NEAR_ENOUGH(d1)) contact_recurse(cx, R1, T1, a1, a2);
+    if (NEAR_ENOUGH(d2)) contact_recurse(cx, R2, T2, c1, c2);
+  }
+#undef NEAR_ENOUGH
+}
+}  // namespace
+
+// C2A_QueryContact -> C2A_TimeOfContactStep_Contact, C2A/src/C2A.cpp:1937-1966, 1727-1775
+extern "C" int64_t orc_contacts(const orc_bvh *A, const orc_bvh *B, const int32_t *vidx_a, const int32_t *vidx_b,
+                                const double pose1[12], const double pose2[12], double threshold, int64_t max_out,
+                                orc_contact *out)
+{
+  ContactCtx cx;
+  cx.A = A; cx.B = B; cx.va = vidx_a; cx.vb = vidx_b; cx.threshold = threshold; cx.max_out = max_out; cx.count = 0; cx.out = out;
+  const double *R1 = pose1, *T1 = pose1 + 9, *R2 = pose2, *T2 = pose2 + 9;
+  double Tt[3], Rt[9], R[9], T[3];
+  mt_m(cx.Rrel, R1, R2);
+  v_sub(Tt, T2, T1);
+  mt_v(cx.Trel, R1, Tt);
+  m_m(Rt, cx.Rrel, &B->R[0]);
+  mt_m(R, &A->R[0], Rt);
+  m_v_p(Tt, cx.Rrel, &B->Tr[0], cx.Trel);
+  v_sub(Tt, Tt, &A->Tr[0]);
+  mt_v(T, &A->R[0], Tt);
+  contact_recurse(cx, R, T, 0, 0);
+  return cx.count;
+}

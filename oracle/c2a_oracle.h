@@ -85,6 +85,28 @@ double orc_motion_bound_leaf(const orc_motion *m, double ang_radius, double S[3]
 void orc_solve(const orc_bvh *A, const orc_bvh *B, const double poses[48], int32_t seedA,
                int32_t seedB, double tol_d, double tol_t, orc_result *out);
 
+/* ---- contact pass of C2A_Solve (C2A_QueryContact, C2A/src/C2A.cpp:1937-1966) ---------------------- */
+typedef struct orc_contact
+{
+  int32_t type_a, type_b;   /* ContactF::FeatureType_A/B: 1 vertex, 2 edge, 3 face */
+  int32_t fid_a[3], fid_b[3]; /* vertex indices of the feature (entries the reference leaves uninitialised are -1) */
+  int32_t tri_a, tri_b;     /* triangle indices (builder order) */
+  double pa[3], pb[3];      /* closest points: on A in A's frame, on B in B's frame */
+  double dist;
+} orc_contact;
+
+/* the reference's in-tree TriDist with contact features, C2A/src/C2A.cpp:165-405 */
+double orc_tri_dist_features(double P[3], double Q[3], const double S[9], const double T[9], int32_t *f1_type,
+                             int32_t *f1_fid, int32_t *f2_type, int32_t *f2_fid, int32_t *collided);
+
+/* All triangle pairs within `threshold` at the given poses (R(9)+T(3) each), in the reference's visiting
+ * order (the reference push_front()s them, so its list is this order reversed).  vidx_a/b: [n_tris][3]
+ * vertex indices per triangle (builder order) or NULL.  Returns the number found; at most max_out are
+ * written. */
+int64_t orc_contacts(const orc_bvh *A, const orc_bvh *B, const int32_t *vidx_a, const int32_t *vidx_b,
+                     const double pose1[12], const double pose2[12], double threshold, int64_t max_out,
+                     orc_contact *out);
+
 /* Batch over n queries on n_threads std::threads (static interleave). */
 void orc_solve_batch(const orc_bvh *A, const orc_bvh *B, const double *poses, int64_t n,
                      const int32_t *seedA, const int32_t *seedB, double tol_d, double tol_t,

@@ -229,6 +229,51 @@ void ref_solve_batch(void *hA, void *hB, const double *poses, int64_t n, const i
   b_TanslationCCD = false;
 }
 
+// The full, unmodified C2A_Solve for one query, with its contact list exported.  The reference
+// push_front()s contacts, so list order = reverse visiting order; records are written in LIST order.
+// FeatureID entries the reference leaves uninitialised are copied as they are (garbage): compare only
+// the first 1 / 2 / 3 entries for a vertex / edge / face feature.
+int64_t ref_solve_contacts(void *hA, void *hB, const double *poses48, int32_t seedA, int32_t seedB, orc_result *res,
+                           int64_t max_out, orc_contact *out)
+{
+  C2A_Model *A = (C2A_Model *)hA, *B = (C2A_Model *)hB;
+  StdoutSilencer quiet;
+  Transform t00, t01, t10, t11, out0, out1;
+  Real v[12];
+  Transform *tt[4] = {&t00, &t01, &t10, &t11};
+  for (int k = 0; k < 4; k++)
+  {
+    const double *p = poses48 + 12 * k;
+    for (int i = 0; i < 3; i++) { v[4 * i + 0] = p[3 * i]; v[4 * i + 1] = p[3 * i + 1]; v[4 * i + 2] = p[3 * i + 2]; v[4 * i + 3] = p[9 + i]; }
+    tt[k]->Set_Value(v);
+  }
+  out0.Identity(); out1.Identity();
+  C2A_TimeOfContactResult dres;
+  dres.last_triA = A->GetTriangle(seedA);
+  dres.last_triB = B->GetTriangle(seedB);
+  PQP_REAL toc = 0;
+  int nIter = 0, nContact = 0;
+  C2A_Solve(&t00, &t01, A, &t10, &t11, B, out0, out1, toc, nIter, nContact, 0.0, dres);
+  memset(res, 0, sizeof(*res));
+  fill_common(res, dres);
+  if (!dres.collisionfree)
+  {
+    transform_to_pose(out0, &res->pose_toc[0]);
+    transform_to_pose(out1, &res->pose_toc[12]);
+  }
+  int64_t k = 0;
+  for (ContactFListIterator it = dres.cont_l.begin(); it != dres.cont_l.end(); ++it, ++k)
+  {
+    if (k >= max_out) continue;
+    orc_contact &c = out[k];
+    c.type_a = it->FeatureType_A; c.type_b = it->FeatureType_B;
+    for (int i = 0; i < 3; i++) { c.fid_a[i] = it->FeatureID_A[i]; c.fid_b[i] = it->FeatureID_B[i]; c.pa[i] = it->P_A[i]; c.pb[i] = it->P_B[i]; }
+    c.tri_a = it->TriangleID_A; c.tri_b = it->TriangleID_B;
+    c.dist = it->Distance;
+  }
+  return nContact;
+}
+
 // ---- unit-level entry points for pinning the port / the device functions ----
 double ref_rect_dist(const double Rab[9], const double Tab[3], const double a[2], const double b[2], double P[3],
                      double Q[3], double S[3])

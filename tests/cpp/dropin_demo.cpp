@@ -64,7 +64,10 @@ int main(int argc, char **argv)
     C2A_Result r = C2A_Solve(&t00[f], &t01[f], object1_tested, &t10[f], &t11[f], object2_tested, trans0, trans1, toc, nItr, NTr,
                              0.0, dres);
     if (r != TOCFound) return 6;
-    printf("F %d %a %a %d %d %d", dres.collisionfree ? 1 : 0, toc, dres.Distance(), nItr, dres.NumBVTests(), dres.NumTriTests());
+    printf("F %d %a %a %d %d %d %d %d", dres.collisionfree ? 1 : 0, toc, dres.Distance(), nItr, dres.NumBVTests(), dres.NumTriTests(), NTr,
+           (int)dres.cont_l.size());
+    if (NTr > 0) printf(" %d %d %a", dres.cont_l.front().TriangleID_A, dres.cont_l.front().TriangleID_B, dres.cont_l.front().Distance);
+    else printf(" -1 -1 0x0p+0");
     if (!dres.collisionfree)
       for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) printf(" %a", trans0.Rotation()[i][j]);

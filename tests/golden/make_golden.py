@@ -99,6 +99,22 @@ def main():
             res = R.solve_batch(bunny, knot, poses, seedA=sa, seedB=sb, tol_d=1e-3, tol_t=1e-5, threads=THREADS)
             save_results("ref_bunny_vs_knot_seeded.npz", res, poses, 1e-3, 1e-5, {"seed_a": sa, "seed_b": sb})
 
+    # --- contact pass: the full, unmodified C2A_Solve with its ContactF list exported (list order)
+    tris, vi = meshes.torus_knot(128, 16)
+    knot = R.model(tris, vi)
+    g = np.load(os.path.join(HERE, "ref_knot_128x16.npz"))
+    nq = 200
+    counts, recs = [], []
+    for i in range(nq):
+        res, n, rr = R.solve_contacts(knot, knot, g["poses"][i])
+        assert res["toc"] == g["toc"][i] and res["collisionfree"] == g["collisionfree"][i]
+        counts.append(n)
+        recs.append(rr.copy())
+    allr = np.concatenate(recs) if recs else np.zeros(0, dtype=oracle.CONTACT_DTYPE)
+    np.savez_compressed(os.path.join(HERE, "ref_contacts_knot_128x16.npz"), num_contact=np.array(counts, np.int32),
+                        **{k: allr[k] for k in allr.dtype.names})
+    print(f"ref_contacts_knot_128x16.npz: {nq} queries, {int(np.sum(counts))} contacts, max {int(np.max(counts))}")
+
     with open(os.path.join(HERE, "bvh_digest.json"), "w") as f:
         json.dump(digests, f, indent=1, sort_keys=True)
 

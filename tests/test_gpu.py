@@ -226,3 +226,31 @@ def test_large_batch_sample_against_oracle(models, bvhs):
     assert_contract(got, ref, 1e-4)
     for a, b in FIELDS:
         assert np.array_equal(got[a], ref[b]), a
+
+
+def test_contact_pass_matches_reference(models, golden):
+    """The contact pass of C2A_Solve (number_of_contact + ContactF list) fused behind c2a_b200_solve_batch,
+    and the standalone c2a_b200_contacts_batch, against the lists the unmodified reference produced."""
+    from test_oracle import contacts_equal, golden_contacts
+    counts, lists = golden_contacts(golden)
+    g = golden("ref_knot_128x16")
+    n = len(counts)
+    tris, vidx = meshes.torus_knot(128, 16)
+    m = api.Model(api.build_bvh(tris, vidx), 0)
+    got = api.solve_batch(m, m, g["poses"][:n], max_contacts=32)
+    assert np.array_equal(got["num_contact"], counts)
+    assert np.array_equal(got["toc"], g["toc"][:n])
+    for i in range(n):
+        recs = got["contacts"][i][:counts[i]][::-1]  # device order = visiting order; the reference's list is reversed
+        for a, c in zip(lists[i], recs):
+            assert contacts_equal(a, c), i
+    # truncation keeps the count
+    small = api.solve_batch(m, m, g["poses"][:n], max_contacts=2, fields=("status",))
+    assert np.array_equal(small["num_contact"], counts)
+    # standalone entry at the TOC poses
+    hits = np.where(g["collisionfree"][:n] == 0)[0]
+    num, recs = api.contacts_batch(m, m, g["pose_toc"][hits], 2 * g["distance"][hits] + 0.001, max_contacts=32)
+    assert np.array_equal(num, counts[hits])
+    for j, i in enumerate(hits[:40]):
+        for a, c in zip(lists[i], recs[j][:num[j]][::-1]):
+            assert contacts_equal(a, c), i

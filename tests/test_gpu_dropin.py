@@ -37,12 +37,19 @@ def test_cpp_dropin_matches_reference_fixture(tmp_path, golden):
     assert "end model" not in out.stdout and "dres.distance" not in out.stdout  # the drop-in does not print
     rows = [l.split() for l in out.stdout.splitlines() if l.startswith("F ")]
     assert len(rows) == n
+    gc = golden("ref_contacts_knot_128x16")
+    offs = np.concatenate([[0], np.cumsum(gc["num_contact"])])
     for i, r in enumerate(rows):
         assert int(r[1]) == g["collisionfree"][i]
         assert float.fromhex(r[2]) == g["toc"][i]
         assert float.fromhex(r[3]) == g["distance"][i]
         assert int(r[4]) == g["numCA"][i] and int(r[5]) == g["num_bv_tests"][i] and int(r[6]) == g["num_tri_tests"][i]
+        # contact pass: number_of_contact, list size, and the list's FRONT element (the reference push_front()s)
+        assert int(r[7]) == gc["num_contact"][i] and int(r[8]) == gc["num_contact"][i]
+        if gc["num_contact"][i] > 0:
+            k = offs[i]
+            assert int(r[9]) == gc["tri_a"][k] and int(r[10]) == gc["tri_b"][k] and float.fromhex(r[11]) == gc["dist"][k]
         if not g["collisionfree"][i]:
-            assert [float.fromhex(x) for x in r[7:16]] == list(g["pose_toc"][i][:9])
+            assert [float.fromhex(x) for x in r[12:21]] == list(g["pose_toc"][i][:9])
     assert "BATCH_MISMATCH 0" in out.stdout
     assert "STEP_MISMATCH 0" in out.stdout

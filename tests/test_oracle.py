@@ -136,3 +136,41 @@ def test_golden_fixtures_are_sane(golden):
         assert ((g["toc"] >= 0) & (g["toc"] < 1)).all()
         assert (g["numCA"] >= 1).all() and (g["numCA"] <= 152).all()
         assert free.sum() > 0 and (~free).sum() > 0
+
+
+def contacts_equal(a, c):
+    """Two contact records; FeatureID entries beyond the feature's arity are undefined in the reference."""
+    na, nb = int(a["type_a"]), int(a["type_b"])
+    return (a["type_a"] == c["type_a"] and a["type_b"] == c["type_b"] and a["tri_a"] == c["tri_a"] and a["tri_b"] == c["tri_b"]
+            and a["dist"] == c["dist"] and np.array_equal(a["pa"], c["pa"]) and np.array_equal(a["pb"], c["pb"])
+            and np.array_equal(a["fid_a"][:na], c["fid_a"][:na]) and np.array_equal(a["fid_b"][:nb], c["fid_b"][:nb]))
+
+
+def golden_contacts(golden):
+    g = golden("ref_contacts_knot_128x16")
+    names = [k for k in g if k != "num_contact"]
+    recs = np.zeros(len(g["dist"]), dtype=oracle.CONTACT_DTYPE)
+    for k in names:
+        recs[k] = g[k]
+    offs = np.concatenate([[0], np.cumsum(g["num_contact"])])
+    return g["num_contact"], [recs[offs[i]:offs[i + 1]] for i in range(len(g["num_contact"]))]
+
+
+def test_port_contact_pass_matches_golden(golden, bvhs):
+    """Contact pass of C2A_Solve: port vs the reference's exported ContactF lists (list order = reversed visiting order)."""
+    from c2a_b200 import api, meshes
+    counts, lists = golden_contacts(golden)
+    g = golden("ref_knot_128x16")
+    tris, vidx = meshes.torus_knot(128, 16)
+    b = api.build_bvh(tris, vidx)
+    P = oracle.port()
+    assert counts.sum() > 100
+    for i in range(len(counts)):
+        if g["collisionfree"][i]:
+            assert counts[i] == 0
+            continue
+        thr = 2 * g["distance"][i] + 0.001
+        n, recs = P.contacts(b, b, g["pose_toc"][i][:12], g["pose_toc"][i][12:], thr, b["tri_vidx"], b["tri_vidx"])
+        assert n == counts[i], i
+        for a, c in zip(lists[i], recs[::-1]):
+            assert contacts_equal(a, c), i
