@@ -108,6 +108,44 @@ C2A_DEV void motion_pose(const Motion &m, double t_in, double R[9], double T[3])
   matrix_from_quat(R, q);
 }
 
+// The reference normalises the direction inside each bound (Vnormalize, InterpMotion.cpp:837 / :752) and
+// calls the second object's bound with S2 = S1 * -1.  Squares are sign-blind and negation is exact, so
+// normalising S2 gives exactly -normalise(S1): the callers normalise once and pass the negated unit
+// vector to the second bound (one FP64 sqrt + division less per child test, same bits).
+C2A_DEV double motion_bound_bv_unit(const Motion &m, double ang_radius, const double N[3])
+{
+  double cross[3];
+  v_cross(cross, m.axis, N);
+  const double w_max = (ang_radius)*v_len(cross) * m.w;
+  double v_max = v_dot(m.cv, N);
+  if (v_max < 0) v_max = 0;
+  double path_max = v_max + w_max;
+  if (path_max <= 0) path_max = 1e-30;
+  return path_max;
+}
+C2A_DEV double motion_bound_leaf_unit(const Motion &m, double ang_radius, const double S[3])
+{
+  double v_max, w_max;
+  if (m.w == 0)
+  {
+    w_max = 0;
+    v_max = v_dot(m.cv, S);
+    if (v_max < 0) v_max = 0;
+  }
+  else
+  {
+    double cwc[3] = {m.axis[0], m.axis[1], m.axis[2]}, cross[3];
+    cwc[0] *= m.w; cwc[1] *= m.w; cwc[2] *= m.w;
+    v_cross(cross, cwc, S);
+    w_max = ang_radius * v_len(cross);
+    v_max = v_dot(m.cv, S);
+    if (v_max < 0) v_max = 0;
+  }
+  double path_max = w_max + v_max;
+  if (path_max == 0) path_max = 1e-30;
+  return path_max;
+}
+
 // directional motion bound of a BV; normalises N in place like the reference
 C2A_DEV double motion_bound_bv(const Motion &m, double ang_radius, double N[3])
 {
