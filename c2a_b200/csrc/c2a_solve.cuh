@@ -319,16 +319,17 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
 #pragma unroll
                 for (int i = 0; i < 9; i++) r1[i] = SD(F_R1 + i, slot);
                 m_v(S1, r1, tmp);
-                S2[0] = S1[0] * -1; S2[1] = S1[1] * -1; S2[2] = S1[2] * -1;
+                v_normalize(S1);  // S2 = S1 * -1 normalises to exactly -S1 (see c2a_motion.cuh)
+                S2[0] = -S1[0]; S2[1] = -S1[1]; S2[2] = -S1[2];
                 Motion m;  // only cv, axis, w are read by the bound
 #pragma unroll
                 for (int i = 0; i < 3; i++) { m.cv[i] = SD(F_CV1 + i, slot); m.axis[i] = SD(F_AX1 + i, slot); }
                 m.w = SD(F_W1, slot);
-                const double mb1 = motion_bound_bv(m, __ldg(gs + 15), S1);
+                const double mb1 = motion_bound_bv_unit(m, __ldg(gs + 15), S1);
 #pragma unroll
                 for (int i = 0; i < 3; i++) { m.cv[i] = SD(F_CV2 + i, slot); m.axis[i] = SD(F_AX2 + i, slot); }
                 m.w = SD(F_W2, slot);
-                const double mb2 = motion_bound_bv(m, __ldg(gt + 15), S2);
+                const double mb2 = motion_bound_bv_unit(m, __ldg(gt + 15), S2);
                 mt = (d) / (mb1 + mb2);
                 if (mt <= 0) mt = 0.0;
               }
@@ -441,18 +442,19 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
           m_v(tmp, r1, p); v_add(w1, tmp, tt1);
           m_v(tmp, r1, qq); v_add(w2, tmp, tt1);
           v_sub(S1, w2, w1);
-          S2[0] = S1[0] * -1; S2[1] = S1[1] * -1; S2[2] = S1[2] * -1;
+          v_normalize(S1);  // S2 = S1 * -1 normalises to exactly -S1 (see c2a_motion.cuh)
+          S2[0] = -S1[0]; S2[1] = -S1[1]; S2[2] = -S1[2];
 #pragma unroll
           for (int i = 0; i < 3; i++) { SD(F_P1 + i, slot) = p[i]; SD(F_P2 + i, slot) = qq[i]; }
           Motion m;
 #pragma unroll
           for (int i = 0; i < 3; i++) { m.cv[i] = SD(F_CV1 + i, slot); m.axis[i] = SD(F_AX1 + i, slot); }
           m.w = SD(F_W1, slot);
-          const double mb1 = motion_bound_leaf(m, __ldg(A.geom + (size_t)b1 * GEOM_STRIDE + 15), S1);
+          const double mb1 = motion_bound_leaf_unit(m, __ldg(A.geom + (size_t)b1 * GEOM_STRIDE + 15), S1);
 #pragma unroll
           for (int i = 0; i < 3; i++) { m.cv[i] = SD(F_CV2 + i, slot); m.axis[i] = SD(F_AX2 + i, slot); }
           m.w = SD(F_W2, slot);
-          const double mb2 = motion_bound_leaf(m, __ldg(B.geom + (size_t)b2 * GEOM_STRIDE + 15), S2);
+          const double mb2 = motion_bound_leaf_unit(m, __ldg(B.geom + (size_t)b2 * GEOM_STRIDE + 15), S2);
           double mt = (dTri) / (mb1 + mb2);
           if (mt < 0.0) mt = 0.0;
           if (mt <= SD(F_MINT, slot)) SD(F_MINT, slot) = mt;
