@@ -265,7 +265,7 @@ def run_gpu(args):
                 "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                              "kernel": "c2a_solve_kernel", "peak_source": peak_src,
-                             "note": "BVH working set (~18 MB) is L2-resident by design: DRAM traffic << algorithmic bytes; "
+                             "note": "BVH working set (16.5 MB) is L2-resident by design: DRAM traffic << algorithmic bytes; "
                                      "the binding resource is the FP64 pipe (see fp64)"},
                 "fp64": {"achieved_tflops_nominal": fl, "peak_tflops_fma": f1.value, "peak_tflops_mul_add": f2.value,
                          "frac_of_mul_add_peak": fl / f2.value if f2.value else None},

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -383,6 +384,47 @@ int c2a_b200_solve_batch_device(const c2a_b200_model *a, const c2a_b200_model *b
   return rc;
 }
 
+// Pinned staging memory for the host-buffer path: cudaMallocHost of a few hundred MB costs more than the
+// copy it serves, so one grow-only buffer is kept per process and handed to one call at a time
+// (concurrent callers fall back to a private allocation).
+namespace {
+std::mutex g_pin_mutex;
+void *g_pin_buf = nullptr;
+size_t g_pin_cap = 0;
+bool g_pin_busy = false;
+struct PinnedLease
+{
+  void *ptr = nullptr;
+  bool shared = false;
+  cudaError_t acquire(size_t bytes)
+  {
+    {
+      std::lock_guard<std::mutex> lk(g_pin_mutex);
+      if (!g_pin_busy)
+      {
+        if (g_pin_cap < bytes)
+        {
+          if (g_pin_buf) cudaFreeHost(g_pin_buf);
+          g_pin_buf = nullptr; g_pin_cap = 0;
+          cudaError_t e = cudaMallocHost(&g_pin_buf, bytes);
+          if (e != cudaSuccess) return e;
+          g_pin_cap = bytes;
+        }
+        g_pin_busy = true; shared = true; ptr = g_pin_buf;
+        return cudaSuccess;
+      }
+    }
+    return cudaMallocHost(&ptr, bytes);
+  }
+  ~PinnedLease()
+  {
+    if (!ptr) return;
+    if (shared) { std::lock_guard<std::mutex> lk(g_pin_mutex); g_pin_busy = false; }
+    else cudaFreeHost(ptr);
+  }
+};
+}  // namespace
+
 // host-buffer path shared by the three public host entries: inputs are poses (motion constants computed
 // here) or ready motion records; step_in != NULL selects single-step mode
 static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses, const double *motions,
@@ -440,10 +482,11 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
   rc = C2A_B200_OK;
 #define STEP(x)                                                                              \
   if (rc == C2A_B200_OK && (e = (x)) != cudaSuccess) rc = fail(C2A_B200_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e));
-  STEP(cudaMemsetAsync(arena, 0, off, stream));
+  STEP(cudaMemsetAsync(arena + o_pose + ((N * 48 * 8 + 255) & ~(size_t)255), 0, off - (o_pose + ((N * 48 * 8 + 255) & ~(size_t)255)), stream));  // outputs start zeroed
   // motion constants on the host (libm acos), straight into pinned staging memory
-  double *staging = nullptr;
-  STEP(cudaMallocHost(&staging, N * 48 * 8));
+  PinnedLease pin;
+  STEP(pin.acquire(N * 48 * 8));
+  double *staging = (double *)pin.ptr;
   if (rc == C2A_B200_OK)
   {
     if (poses) motions_from_poses_mt(poses, n, staging, 0);
@@ -483,7 +526,6 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
 #undef STEP
   cudaFreeAsync(arena, stream);
   cudaStreamSynchronize(stream);
-  if (staging) cudaFreeHost(staging);
   cudaStreamDestroy(stream);
   return rc;
 }
