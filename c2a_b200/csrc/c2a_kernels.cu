@@ -674,18 +674,19 @@ int c2a_b200_test_sincos(const double *x, int64_t n, double *s, double *c)
 // Development aid: enable (enable != 0) or disable phase statistics of the solve kernel on the current
 // device and read them back: out[0..5] = {expand passes, expand lanes, leaf passes, leaf lanes, advance
 // passes, advance lanes} accumulated since the last enable; out[6..8] = globaltimer ns at launch start, at
-// the first failed claim (batch drained) and at the last slot retirement (one launch between enables).
+// the first failed claim (batch drained) and at the last slot retirement (one launch between enables);
+// out[9..10] = 32-lane look-ahead passes and the expansion levels they committed (out must hold 11).
 int c2a_b200_phase_stats(int32_t enable, uint64_t *out9)
 {
   if (out9 && g_stats_dev)
   {
     CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpy(out9, g_stats_dev, 9 * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out9, g_stats_dev, 11 * 8, cudaMemcpyDeviceToHost));
   }
   if (enable && !g_stats_dev) CUDA_TRY(cudaMalloc(&g_stats_dev, 16 * 8));
   if (enable)
   {
-    const unsigned long long init[9] = {0, 0, 0, 0, 0, 0, ~0ull, ~0ull, 0};
+    const unsigned long long init[11] = {0, 0, 0, 0, 0, 0, ~0ull, ~0ull, 0, 0, 0};
     CUDA_TRY(cudaMemcpy(g_stats_dev, init, sizeof(init), cudaMemcpyHostToDevice));
   }
   if (!enable && g_stats_dev) { cudaFree(g_stats_dev); g_stats_dev = nullptr; }

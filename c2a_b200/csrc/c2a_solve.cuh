@@ -407,6 +407,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
             }
             if (t == 0)
             {
+              if (args.stats && G == 32) { atomicAdd(args.stats + 9, 1ull); atomicAdd(args.stats + 10, (unsigned long long)levels); }
               SD(F_MINT, slot) = mint;
               SI(I_SP, slot) = sp;
               SI(I_NBV, slot) = SI(I_NBV, slot) + 2 * levels;
