@@ -63,3 +63,23 @@ def demo_batch(R1f, T1f, R2f, T2f):
         out[i, 24:33] = R2f[i]; out[i, 33:36] = T2f[s1]
         out[i, 36:45] = R2f[i]; out[i, 45:48] = T2f[s2]
     return out
+
+
+def grazing_batch(poses, toc, pose_toc, p1p2, push, seed=0):
+    """Config 5 (adversarial near-contact sweep): from colliding queries (their poses, time of contact,
+    object poses at contact and closest points p1/p2 in model-1 frame) build new queries whose END pose of
+    object 1 is its TOC pose pushed ``push`` units (array, e.g. U(0, 1e-3)) past contact along the contact
+    normal; the start pose and object 2 are unchanged.  The motion then only just reaches contact at t ~ 1:
+    deep BVTT fronts and many conservative-advancement iterations."""
+    poses = np.asarray(poses, dtype=np.float64).reshape(-1, 48)
+    n = poses.shape[0]
+    out = poses.copy()
+    R1 = pose_toc[:, 0:9].reshape(n, 3, 3)
+    d = np.einsum("nij,nj->ni", R1, p1p2[:, 3:6] - p1p2[:, 0:3])  # contact direction in the world frame
+    nrm = np.linalg.norm(d, axis=1, keepdims=True)
+    rng = np.random.default_rng(seed)
+    fallback = rng.normal(size=(n, 3)); fallback /= np.linalg.norm(fallback, axis=1, keepdims=True)
+    d = np.where(nrm > 1e-12, d / np.maximum(nrm, 1e-300), fallback)
+    out[:, 12:21] = pose_toc[:, 0:9]
+    out[:, 21:24] = pose_toc[:, 9:12] + np.asarray(push, dtype=np.float64).reshape(n, 1) * d
+    return np.ascontiguousarray(out)

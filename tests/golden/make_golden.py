@@ -99,6 +99,17 @@ def main():
             res = R.solve_batch(bunny, knot, poses, seedA=sa, seedB=sb, tol_d=1e-3, tol_t=1e-5, threads=THREADS)
             save_results("ref_bunny_vs_knot_seeded.npz", res, poses, 1e-3, 1e-5, {"seed_a": sa, "seed_b": sb})
 
+    # --- config 5 (sample): grazing re-poses of colliding knot queries, tolerance_t swept
+    tris, vi = meshes.torus_knot(128, 16)
+    knot = R.model(tris, vi)
+    g = np.load(os.path.join(HERE, "ref_knot_128x16.npz"))
+    hit = np.where((g["collisionfree"] == 0) & (g["num_tri_tests"] > 0))[0][:240]
+    rng = np.random.default_rng(55)
+    gp = workloads.grazing_batch(g["poses"][hit], g["toc"][hit], g["pose_toc"][hit], g["p1p2"][hit], rng.uniform(0, 1e-3, len(hit)))
+    for tol_t in (1e-3, 1e-6):
+        res = R.solve_batch(knot, knot, gp, tol_d=1e-4, tol_t=tol_t, threads=THREADS)
+        save_results(f"ref_knot_128x16_grazing_tol{tol_t:g}.npz", res, gp, 1e-4, tol_t)
+
     # --- contact pass: the full, unmodified C2A_Solve with its ContactF list exported (list order)
     tris, vi = meshes.torus_knot(128, 16)
     knot = R.model(tris, vi)

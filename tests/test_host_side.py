@@ -167,3 +167,13 @@ def test_two_rank_gloo_shard_and_gather(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "GATHER_OK" in outs[0]
+
+
+def test_dropin_header_compiles_standalone(tmp_path):
+    """include/C2A/C2A.h and the alias headers a reference-style program includes are self-contained C++."""
+    src = tmp_path / "t.cpp"
+    src.write_text('#include "PQP.h"\n#include "C2A/C2A.h"\n#include "C2A/LinearMath.h"\n#include "C2A/InterpMotion.h"\n'
+                   '#include "C2A/C2A_Internal.h"\n#include "c2a_b200.h"\n#include "c2a_b200_testing.h"\nint main() { C2A_TimeOfContactResult r; (void)r; return 0; }\n')
+    out = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-Wall", "-I" + os.path.join(ROOT, "include"), str(src)],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
