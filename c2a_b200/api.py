@@ -35,7 +35,7 @@ CONTACT_DTYPE = np.dtype([("type_a", np.int32), ("type_b", np.int32), ("fid_a", 
 
 class Results(C.Structure):
     _fields_ = [(name, C.c_void_p) for name, _, _ in RESULT_FIELDS] + [("num_contact", C.c_void_p), ("contacts", C.c_void_p),
-                                                                       ("max_contacts", C.c_int32)]
+                                                                       ("max_contacts", C.c_int32), ("last_tri", C.c_void_p)]
 
 
 def lib():
@@ -159,6 +159,9 @@ def solve_batch(model_a, model_b, poses, seed_a=None, seed_b=None, tol_d=1e-4, t
         a = np.zeros((n,) + shape, dtype=dt)
         out[name] = a
         setattr(res, name, a.ctypes.data)
+    if fields is None or "last_tri" in fields:
+        out["last_tri"] = np.full((n, 2), -1, dtype=np.int32)
+        res.last_tri = out["last_tri"].ctypes.data
     if max_contacts > 0:
         out["num_contact"] = np.zeros(n, dtype=np.int32)
         out["contacts"] = np.zeros((n, max_contacts), dtype=CONTACT_DTYPE)

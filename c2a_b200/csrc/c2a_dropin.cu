@@ -326,12 +326,12 @@ PQP_REAL C2A_QueryTimeOfContact(CInterpMotion *objmotion1, CInterpMotion *objmot
   record_from_motion(objmotion1, rec);
   record_from_motion(objmotion2, rec + 24);
   int32_t sa = seed_index(o1, res->last_triA), sb = seed_index(o2, res->last_triB);
-  int32_t status = -1, cf = 0, nca = 0, nbv = 0, ntri = 0;
+  int32_t status = -1, cf = 0, nca = 0, nbv = 0, ntri = 0, last[2] = {-1, -1};
   double toc = 0, dist = 0, mint = 0, p1p2[6] = {0, 0, 0, 0, 0, 0};
   c2a_b200_results out;
   memset(&out, 0, sizeof(out));
   out.status = &status; out.collisionfree = &cf; out.num_ca = &nca; out.num_bv_tests = &nbv; out.num_tri_tests = &ntri;
-  out.toc = &toc; out.distance = &dist; out.mint = &mint; out.p1p2 = p1p2;
+  out.toc = &toc; out.distance = &dist; out.mint = &mint; out.p1p2 = p1p2; out.last_tri = last;
   const int rc = c2a_b200_solve_batch_motions(o1->gpu, o2->gpu, rec, &sa, &sb, 1, tolerance_d, tolerance_t, &out);
   if (rc != 0 || status != C2A_B200_QUERY_OK)
   {
@@ -344,6 +344,9 @@ PQP_REAL C2A_QueryTimeOfContact(CInterpMotion *objmotion1, CInterpMotion *objmot
   res->toc = toc; res->distance = dist; res->mint = mint; res->numCA = nca;
   res->num_bv_tests = nbv; res->num_tri_tests = ntri;
   for (int i = 0; i < 3; i++) { res->p1[i] = p1p2[i]; res->p2[i] = p1p2[3 + i]; }
+  // the traversal's side effect on the models (C2A.cpp:1175-1176); the demo feeds it back as the next seeds
+  if (last[0] >= 0) o1->last_tri = &o1->tris[last[0]];
+  if (last[1] >= 0) o2->last_tri = &o2->tris[last[1]];
   if (!res->collisionfree) objmotion1->integrate(toc, res->R_toc, res->T_toc);  // C2A.cpp:2143
   return toc;
 }
@@ -397,11 +400,12 @@ int C2A_TimeOfContactStep(CInterpMotion *objmotion1, CInterpMotion *objmotion2, 
   for (int i = 0; i < 3; i++) { step[9 + i] = T1[i]; step[21 + i] = T2[i]; }
   step[24] = (double)res->numCA; step[25] = res->mint; step[26] = res->UpboundTOC; step[27] = 0;
   int32_t sa = seed_index(o1, res->last_triA), sb = seed_index(o2, res->last_triB);
-  int32_t status = -1, nbv = 0, ntri = 0;
+  int32_t status = -1, nbv = 0, ntri = 0, last[2] = {-1, -1};
   double dist = 0, mint = 0, p1p2[6] = {0, 0, 0, 0, 0, 0};
   c2a_b200_results out;
   memset(&out, 0, sizeof(out));
   out.status = &status; out.num_bv_tests = &nbv; out.num_tri_tests = &ntri; out.distance = &dist; out.mint = &mint; out.p1p2 = p1p2;
+  out.last_tri = last;
   const int rc = c2a_b200_toc_step_batch(o1->gpu, o2->gpu, rec, step, &sa, &sb, 1, tolerance_t, tolerance_d, &out);
   if (rc != 0 || status != C2A_B200_QUERY_OK) return rc ? rc : PQP_ERR_UNPROCESSED_MODEL;
   // res->R, res->T: the relative transform the step computes (C2A.cpp:1793-1796)
@@ -413,6 +417,8 @@ int C2A_TimeOfContactStep(CInterpMotion *objmotion1, CInterpMotion *objmotion2, 
   }
   res->distance = dist; res->mint = mint;
   res->num_bv_tests += nbv; res->num_tri_tests += ntri;
+  if (last[0] >= 0) o1->last_tri = &o1->tris[last[0]];
+  if (last[1] >= 0) o2->last_tri = &o2->tris[last[1]];
   if (ntri > 0 && (p1p2[0] != 0 || p1p2[1] != 0 || p1p2[2] != 0 || p1p2[3] != 0 || p1p2[4] != 0 || p1p2[5] != 0))
     for (int i = 0; i < 3; i++) { res->p1[i] = p1p2[i]; res->p2[i] = p1p2[3 + i]; }
   return PQP_OK;

@@ -452,6 +452,7 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
   const size_t o_toc = out->toc ? take(N * 8) : 0, o_dist = (out->distance || want_contacts) ? take(N * 8) : 0;
   const size_t o_mint = out->mint ? take(N * 8) : 0, o_pp = out->p1p2 ? take(N * 48) : 0;
   const size_t o_pt = (out->pose_toc || want_contacts) ? take(N * 192) : 0;
+  const size_t o_lt = out->last_tri ? take(N * 8) : 0;
   const size_t o_nc = want_contacts ? take(N * 4) : 0;
   const size_t o_ct = (want_contacts && out->contacts) ? take(N * (size_t)out->max_contacts * sizeof(c2a_b200_contact)) : 0;
   const size_t o_cnt2 = want_contacts ? take(8) : 0;
@@ -478,6 +479,7 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
   if (out->mint) d.mint = (double *)(arena + o_mint);
   if (out->p1p2) d.p1p2 = (double *)(arena + o_pp);
   if (out->pose_toc || want_contacts) d.pose_toc = (double *)(arena + o_pt);
+  if (out->last_tri) d.last_tri = (int32_t *)(arena + o_lt);
 
   rc = C2A_B200_OK;
 #define STEP(x)                                                                              \
@@ -521,6 +523,7 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
   BACK(status, o_status, N * 4) BACK(collisionfree, o_cf, N * 4) BACK(num_ca, o_nca, N * 4)
   BACK(num_bv_tests, o_nbv, N * 4) BACK(num_tri_tests, o_ntri, N * 4) BACK(toc, o_toc, N * 8)
   BACK(distance, o_dist, N * 8) BACK(mint, o_mint, N * 8) BACK(p1p2, o_pp, N * 48) BACK(pose_toc, o_pt, N * 192)
+  BACK(last_tri, o_lt, N * 8)
 #undef BACK
   STEP(cudaStreamSynchronize(stream));
 #undef STEP

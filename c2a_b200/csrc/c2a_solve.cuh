@@ -97,7 +97,7 @@ enum
 enum
 {
   I_STATE = 0, I_SP, I_NBV, I_NTRI, I_NUMCA, I_NITRS, I_CURB1, I_CURB2, I_LEAFB1, I_LEAFB2, I_SEEDA, I_SEEDB,
-  I_QLO, I_QHI, I_PENDING, I_CURFC1, I_CURFC2, I_NINT = 18
+  I_QLO, I_QHI, I_PENDING, I_CURFC1, I_CURFC2, I_LASTA, I_LASTB, I_NINT = 20
 };
 constexpr size_t WARP_SMEM_BYTES = (size_t)F_NDBL * Q * 8 + (size_t)I_NINT * Q * 4;
 constexpr size_t BLOCK_SMEM_BYTES = WARP_SMEM_BYTES * WARPS_PER_BLOCK;
@@ -459,6 +459,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
           double mt = (dTri) / (mb1 + mb2);
           if (mt < 0.0) mt = 0.0;
           if (mt <= SD(F_MINT, slot)) SD(F_MINT, slot) = mt;
+          SI(I_LASTA, slot) = ta; SI(I_LASTB, slot) = tb;  // o1->last_tri = t1; o2->last_tri = t2 (C2A.cpp:1175-1176)
         }
         SI(I_NTRI, slot) = SI(I_NTRI, slot) + 1;
         SI(I_STATE, slot) = ST_TRAVERSE;
@@ -484,6 +485,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
           if (o.num_tri_tests) o.num_tri_tests[q] = SI(I_NTRI, slot);
           if (o.distance) o.distance[q] = SD(F_DIST, slot);
           if (o.mint) o.mint[q] = SD(F_MINT, slot);
+          if (o.last_tri) { o.last_tri[2 * q] = SI(I_LASTA, slot); o.last_tri[2 * q + 1] = SI(I_LASTB, slot); }
           if (o.p1p2)
           {
 #pragma unroll
@@ -558,6 +560,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
             if (o.toc) o.toc[q] = toc;
             if (o.distance) o.distance[q] = dist;
             if (o.mint) o.mint[q] = mint;
+            if (o.last_tri) { o.last_tri[2 * q] = SI(I_LASTA, slot); o.last_tri[2 * q + 1] = SI(I_LASTB, slot); }
             if (o.p1p2)
             {
 #pragma unroll
@@ -600,6 +603,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
               SI(I_SEEDB, slot) = args.seedB ? args.seedB[q] : 0;
               numCA = 0; lamda = 0;
               SI(I_NITRS, slot) = 0; SI(I_NBV, slot) = 0; SI(I_NTRI, slot) = 0;
+              SI(I_LASTA, slot) = -1; SI(I_LASTB, slot) = -1;
               SD(F_LASTL, slot) = 0; SD(F_UPB, slot) = 1; SD(F_MINT, slot) = 1; SD(F_DIST, slot) = 0;
               if (args.step_in)
               {

@@ -104,6 +104,10 @@ typedef struct c2a_b200_results
                                      std::list is this order reversed: it push_front()s); the first
                                      min(num_contact, max_contacts) entries of each row are written */
   int32_t max_contacts;
+  int32_t *last_tri;      /* [n][2]  triangle indices the traversal leaves in o1->last_tri / o2->last_tri
+                                     (C2A/src/C2A.cpp:1175-1176): the last leaf that improved the distance;
+                                     -1, -1 if none did.  The demo feeds them back as the next call's seeds
+                                     (CCDDemo/mainTorusknot.cpp:314-315). */
 } c2a_b200_results;
 
 int c2a_b200_device_count(int32_t *count);

@@ -16,6 +16,7 @@ RESULT_DTYPE = np.dtype([
     ("collisionfree", np.int32), ("numCA", np.int32), ("num_bv_tests", np.int32), ("num_tri_tests", np.int32),
     ("toc", np.float64), ("distance", np.float64), ("mint", np.float64),
     ("p1", np.float64, 3), ("p2", np.float64, 3), ("pose_toc", np.float64, 24),
+    ("last_tri_a", np.int32), ("last_tri_b", np.int32),
 ], align=True)
 OrcResult = RESULT_DTYPE
 

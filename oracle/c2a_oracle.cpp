@@ -597,6 +597,7 @@ struct Step
   double distance, mint;
   double p1[3], p2[3];
   int num_bv_tests, num_tri_tests;
+  int last_a, last_b;
 };
 
 inline double bv_size(const orc_bvh *M, int n)
@@ -642,6 +643,7 @@ void toc_recurse(Step &st, const double R[9], const double T[3], int b1, int b2)
       double mint = (dTri) / (mb1 + mb2);
       if (mint < 0.0) mint = 0.0;
       if (mint <= st.mint) st.mint = mint;
+      st.last_a = -A->first_child[b1] - 1; st.last_b = -B->first_child[b2] - 1;  // o1->last_tri = t1; o2->last_tri = t2
     }
     st.num_tri_tests++;
     return;
@@ -753,12 +755,14 @@ extern "C" void orc_solve(const orc_bvh *A, const orc_bvh *B, const double poses
   {
     // translation-only branch (C2A.cpp:2391-2395, :1362-1521) -- SURVEY.md section 8f rank 2, not restated yet
     out->collisionfree = -1;
+    out->last_tri_a = out->last_tri_b = -1;
     return;
   }
 
   Step st;
   st.A = A; st.B = B; st.m1 = &m1; st.m2 = &m2;
   st.num_bv_tests = 0; st.num_tri_tests = 0; st.upbound = 1; st.mint = 1; st.distance = 0;
+  st.last_a = -1; st.last_b = -1;
   st.p1[0] = st.p1[1] = st.p1[2] = st.p2[0] = st.p2[1] = st.p2[2] = 0;
   int numCA = 0;
   double lamda = 0.0, lastLamda = 0, dlamda = 0.0, toc = 0;
@@ -810,6 +814,7 @@ extern "C" void orc_solve(const orc_bvh *A, const orc_bvh *B, const double poses
   out->distance = st.distance;
   out->mint = st.mint;
   v_cpy(out->p1, st.p1); v_cpy(out->p2, st.p2);
+  out->last_tri_a = st.last_a; out->last_tri_b = st.last_b;
 }
 
 extern "C" void orc_solve_batch(const orc_bvh *A, const orc_bvh *B, const double *poses, int64_t n,

@@ -55,6 +55,8 @@ typedef struct orc_result
   double mint;            /* ::mint of the last step */
   double p1[3], p2[3];    /* ::p1, ::p2 (model-1 frame) */
   double pose_toc[24];    /* C2A_Solve's trans0, trans1 as R(9)+T(3) each; written only on a hit */
+  int32_t last_tri_a, last_tri_b; /* o1->last_tri / o2->last_tri as the traversal leaves them (C2A.cpp:1175-1176):
+                                     triangle indices of the last leaf that improved the distance, -1 if none */
 } orc_result;
 
 /* geometry kernels */

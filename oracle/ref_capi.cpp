@@ -73,6 +73,14 @@ inline void fill_common(orc_result *o, C2A_TimeOfContactResult &dres)
   o->distance = dres.distance;
   o->mint = dres.mint;
   for (int k = 0; k < 3; k++) { o->p1[k] = dres.p1[k]; o->p2[k] = dres.p2[k]; }
+  o->last_tri_a = o->last_tri_b = -1;
+}
+
+// o->last_tri after a query (only meaningful when queries run one at a time: it is model state)
+inline void fill_last_tri(orc_result *o, C2A_Model *A, C2A_Model *B)
+{
+  o->last_tri_a = A->last_tri ? (int)((C2A_Tri *)A->last_tri - (C2A_Tri *)A->tris) : -1;
+  o->last_tri_b = B->last_tri ? (int)((C2A_Tri *)B->last_tri - (C2A_Tri *)B->tris) : -1;
 }
 
 // The body of C2A_Solve (C2A/src/C2A.cpp:2315-2444) without its printf and contact
@@ -95,8 +103,10 @@ void query_toc(C2A_Model *A, C2A_Model *B, const double *poses, int seedA, int s
   C2A_TimeOfContactResult dres;
   dres.last_triA = A->GetTriangle(seedA);
   dres.last_triB = B->GetTriangle(seedB);
+  if (allow_translation) { A->last_tri = 0; B->last_tri = 0; }  // serial mode: observe the traversal's writes
   C2A_QueryTimeOfContact(&motion1, &motion2, &dres, A, B, tol_d, tol_t, 0);
   fill_common(o, dres);
+  if (allow_translation) fill_last_tri(o, A, B);
   if (!dres.collisionfree)
   {
     PQP_REAL qua[7];

@@ -52,15 +52,17 @@ int main(int argc, char **argv)
   C2A_TimeOfContactResult dres;
   std::vector<Transform> t00(nframes), t01(nframes), t10(nframes), t11(nframes);
   std::vector<double> toc_single(nframes), dist_single(nframes);
-  std::vector<int> free_single(nframes), it_single(nframes);
+  std::vector<int> free_single(nframes), it_single(nframes), seed_a(nframes), seed_b(nframes);
   for (int f = 0; f < nframes; f++)
   {
     Transform trans0, trans1;
     set_transform(t00[f], &poses[48 * f]); set_transform(t01[f], &poses[48 * f + 12]);
     set_transform(t10[f], &poses[48 * f + 24]); set_transform(t11[f], &poses[48 * f + 36]);
     PQP_REAL toc; int nItr, NTr;
-    dres.last_triA = object1_tested->last_tri;
+    dres.last_triA = object1_tested->last_tri;  // the demo carries the models' last_tri into every call
     dres.last_triB = object2_tested->last_tri;
+    seed_a[f] = (int)((C2A_Tri *)dres.last_triA - object1_tested->tris);
+    seed_b[f] = (int)((C2A_Tri *)dres.last_triB - object2_tested->tris);
     C2A_Result r = C2A_Solve(&t00[f], &t01[f], object1_tested, &t10[f], &t11[f], object2_tested, trans0, trans1, toc, nItr, NTr,
                              0.0, dres);
     if (r != TOCFound) return 6;
@@ -80,7 +82,7 @@ int main(int argc, char **argv)
   std::vector<double> tocs(nframes), dists(nframes);
   std::vector<int> its(nframes);
   bool *cf = new bool[nframes];
-  if (C2A_SolveBatch(nframes, t00.data(), t01.data(), object1_tested, t10.data(), t11.data(), object2_tested, 0, 0, cf, tocs.data(),
+  if (C2A_SolveBatch(nframes, t00.data(), t01.data(), object1_tested, t10.data(), t11.data(), object2_tested, seed_a.data(), seed_b.data(), cf, tocs.data(),
                      dists.data(), its.data(), 0, 0) != PQP_OK) return 7;
   int batch_bad = 0;
   for (int f = 0; f < nframes; f++)
@@ -97,14 +99,15 @@ int main(int argc, char **argv)
     t10[f].Rotation().Get_Value(R2); t10[f].Translation().Get_Value(T2); t11[f].Rotation().Get_Value(R2e); t11[f].Translation().Get_Value(T2e);
     CInterpMotion_Linear m1(R1, T1, R1e, T1e), m2(R2, T2, R2e, T2e);
     C2A_TimeOfContactResult res;
-    res.last_triA = object1_tested->last_tri; res.last_triB = object2_tested->last_tri;
+    Tri *const sa = object1_tested->tris, *const sb = object2_tested->tris;  // same seeds for both ways
+    res.last_triA = sa; res.last_triB = sb;
     const PQP_REAL tol = 0.0001;
     PQP_REAL whole = C2A_QueryTimeOfContact(&m1, &m2, &res, object1_tested, object2_tested, tol, tol, 0);
     const bool whole_free = res.collisionfree; const int whole_ca = res.numCA; const PQP_REAL whole_dist = res.distance;
 
     CInterpMotion_Linear s1(R1, T1, R1e, T1e), s2(R2, T2, R2e, T2e);
     C2A_TimeOfContactResult sr;
-    sr.last_triA = object1_tested->last_tri; sr.last_triB = object2_tested->last_tri;
+    sr.last_triA = sa; sr.last_triB = sb;
     sr.num_bv_tests = sr.num_tri_tests = 0; sr.UpboundTOC = 1; sr.numCA = 0; sr.mint = 1;
     C2A_TimeOfContactStep(&s1, &s2, &sr, R1, T1, object1_tested, R2, T2, object2_tested, tol, tol);
     PQP_REAL dist = sr.distance, mint = sr.mint, lamda = 0, lastLamda = mint, toc = 0;

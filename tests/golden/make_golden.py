@@ -29,7 +29,7 @@ THREADS = os.cpu_count() or 1
 
 
 def save_results(name, res, poses, tol_d, tol_t, extra=None):
-    d = {k: res[k] for k in res.dtype.names}
+    d = {k: res[k] for k in res.dtype.names if k not in ("last_tri_a", "last_tri_b")}
     d["p1p2"] = np.concatenate([res["p1"], res["p2"]], 1)
     del d["p1"], d["p2"]
     d["poses"] = poses
@@ -45,6 +45,23 @@ def save_results(name, res, poses, tol_d, tol_t, extra=None):
 
 def digest(bvh):
     return {k: hashlib.sha256(np.ascontiguousarray(bvh[k]).tobytes()).hexdigest() for k in sorted(bvh)}
+
+
+def carry_fixture(R, name, mA, mB, poses):
+    """Sequential single-thread calls; each call's seeds are the models' last_tri as the previous call left them."""
+    sa = sb = 0
+    rows, seeds = [], []
+    for i in range(len(poses)):
+        r = R.solve_batch(mA, mB, poses[i:i + 1], seedA=[sa], seedB=[sb], threads=1)
+        rows.append(r[0]); seeds.append((sa, sb))
+        if r["last_tri_a"][0] >= 0:
+            sa = int(r["last_tri_a"][0])
+        if r["last_tri_b"][0] >= 0:
+            sb = int(r["last_tri_b"][0])
+    rows = np.array(rows, dtype=oracle.RESULT_DTYPE)
+    save_results(name, rows, poses, 1e-4, 1e-4,
+                 {"seed_a": np.array([s[0] for s in seeds], np.int32), "seed_b": np.array([s[1] for s in seeds], np.int32),
+                  "last_tri": np.stack([rows["last_tri_a"], rows["last_tri_b"]], 1)})
 
 
 def main():
@@ -109,6 +126,15 @@ def main():
     for tol_t in (1e-3, 1e-6):
         res = R.solve_batch(knot, knot, gp, tol_d=1e-4, tol_t=tol_t, threads=THREADS)
         save_results(f"ref_knot_128x16_grazing_tol{tol_t:g}.npz", res, gp, 1e-4, tol_t)
+
+    # --- "demo mode": seeds carried from call to call through o->last_tri (CCDDemo/mainTorusknot.cpp:314-315),
+    # two separate model objects like the demo's object1_tested / object2_tested
+    tris, vi = meshes.torus_knot(128, 16)
+    g = np.load(os.path.join(HERE, "ref_knot_128x16.npz"))
+    carry_fixture(R, "ref_knot_128x16_carry.npz", R.model(tris, vi), R.model(tris, vi), g["poses"][:64])
+    # config 1 in demo mode: the 303 frames played twice (the second pass starts from the first pass's seeds)
+    carry_fixture(R, "ref_demo_bunny_carry.npz", R.model(bunny_tris, vidx), R.model(bunny_tris, vidx),
+                  np.concatenate([demo, demo]))
 
     # --- contact pass: the full, unmodified C2A_Solve with its ContactF list exported (list order)
     tris, vi = meshes.torus_knot(128, 16)

