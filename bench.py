@@ -227,6 +227,11 @@ def run_gpu(args):
     for _ in range(e2e_steps):
         host_out = api.solve_batch(model, model, poses, tol_d=TOL, tol_t=TOL, fields=fields)
     e2e_s = time.perf_counter() - t0
+    import ctypes as C
+    tb = (C.c_double * 8)()
+    api.lib().c2a_b200_host_timing(tb)  # wall-clock breakdown of the last e2e call
+    e2e_breakdown = {k: round(v, 4) for k, v in zip(("alloc_s", "motion_setup_s", "claim_order_s", "enqueue_s", "kernel_wait_s",
+                                                      "d2h_s", "release_s", "total_s"), tb)}
     h2d = B * 48 * 8
     d2h = sum(host_out[k].nbytes for k in fields)
     for k in ("collisionfree", "toc", "distance", "num_ca"):
@@ -249,7 +254,6 @@ def run_gpu(args):
         if os.path.exists(tp):
             with open(tp) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
-        import ctypes as C
         f1, f2 = C.c_double(0), C.c_double(0)
         api.lib().c2a_b200_fp64_peak(C.byref(f1), C.byref(f2))
         fl = nominal_flops(nbv, ntri, nca) / per_launch_s / 1e12
@@ -260,7 +264,8 @@ def run_gpu(args):
                            "l2": "inputs per step (%.0f MB motion records) exceed the 126 MB L2 and a 256 MB scrub buffer is "
                                  "written between timed steps" % (B * 384 / 1e6),
                            "parallelism": f"{world} independent shards, no collective"},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                        "breakdown_last_call": e2e_breakdown},
                 "gpu_launches": launches,
                 "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,

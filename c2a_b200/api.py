@@ -7,7 +7,8 @@ import os
 
 import numpy as np
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libc2a_b200.so")
+# C2A_B200_LIB: development override (A/B timing of two builds of the same library in one GPU session)
+_LIB_PATH = os.environ.get("C2A_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libc2a_b200.so")
 _lib = None
 
 RESULT_FIELDS = (("status", np.int32, ()), ("collisionfree", np.int32, ()), ("num_ca", np.int32, ()),

@@ -304,46 +304,53 @@ C2A_DEV double rss_rect_dist(const double R[9], const double T[3], double a0, do
 }
 
 // ---- triangle-triangle distance ----------------------------------------------------------
-// PQP SegPoints (in-tree copy C2A/src/C2A.cpp:59-163)
+// PQP SegPoints (in-tree copy C2A/src/C2A.cpp:59-163), reshaped for SIMT: the reference's nine-way
+// branch (u <= 0 | u >= 1 | inside) x (t <= 0 | t >= 1 | inside) becomes selects over values every
+// branch spells the same way, so the lanes of a LEAF pass stay converged:
+//   Y   = Q | Q + B | Q + B*u            X = P | P + A | P + A*t
+//   VEC = Y - X                          both parameters clamped (vertex-vertex)
+//       = W x ((TT) x W) reordered as the reference does (TMP = TT x W; VEC = W x TMP), with
+//         W = A, TT = Y - P   (u clamped, t inside;   Y = Q gives the reference's T = Q - P)
+//         W = B, TT = Q - X   (u inside,  t clamped;  X = P gives the reference's T = Q - P)
+//       = +-(A x B)                      both inside
+// Each value is computed by the same operations in the same order as in the branch that uses it.
 C2A_DEV void seg_points(double VEC[3], double X[3], double Y[3], const double P[3], const double A[3],
                         const double Q[3], const double B[3])
 {
-  double T[3], TMP[3];
+  double T[3], TT[3], TMP[3], W[3], Xm[3], Ym[3], Ve[3], Vx[3], Vm[3];
   v_sub(T, Q, P);
   const double AdA = v_dot(A, A), BdB = v_dot(B, B), AdB = v_dot(A, B);
   const double AdT = v_dot(A, T), BdT = v_dot(B, T);
   const double denom = AdA * BdB - AdB * AdB;
   double t = (AdT * BdB - BdT * AdB) / denom;
-  if ((t < 0) || (t != t)) t = 0; else if (t > 1) t = 1;
+  t = ((t < 0) || (t != t)) ? 0.0 : ((t > 1) ? 1.0 : t);
   const double u = (t * AdB - BdT) / BdB;
+  const bool u0 = (u <= 0) || (u != u), u1 = !u0 && (u >= 1), um = !u0 && !u1;
+  const double t2 = (u1 ? (AdB + AdT) : AdT) / AdA;
+  t = um ? t : t2;
+  const bool t0 = (t <= 0) || (t != t), t1 = !t0 && (t >= 1), tm = !t0 && !t1;
 
-  if ((u <= 0) || (u != u))
+  v_madd(Ym, Q, B, u);
+  v_madd(Xm, P, A, t);
+#pragma unroll
+  for (int k = 0; k < 3; k++)
   {
-    v_cpy(Y, Q);
-    t = AdT / AdA;
-    if ((t <= 0) || (t != t)) { v_cpy(X, P); v_sub(VEC, Q, P); }
-    else if (t >= 1) { v_add(X, P, A); v_sub(VEC, Q, X); }
-    else { v_madd(X, P, A, t); v_cross(TMP, T, A); v_cross(VEC, A, TMP); }
+    Y[k] = u0 ? Q[k] : (u1 ? (Q[k] + B[k]) : Ym[k]);
+    X[k] = t0 ? P[k] : (t1 ? (P[k] + A[k]) : Xm[k]);
+    W[k] = um ? B[k] : A[k];
   }
-  else if (u >= 1)
+  v_sub(Ve, Y, X);
+#pragma unroll
+  for (int k = 0; k < 3; k++) TT[k] = um ? (Q[k] - X[k]) : (Y[k] - P[k]);
+  v_cross(TMP, TT, W);
+  v_cross(Vx, W, TMP);
+  v_cross(Vm, A, B);
+  const bool flip = v_dot(Vm, T) < 0;
+#pragma unroll
+  for (int k = 0; k < 3; k++)
   {
-    v_add(Y, Q, B);
-    t = (AdB + AdT) / AdA;
-    if ((t <= 0) || (t != t)) { v_cpy(X, P); v_sub(VEC, Y, P); }
-    else if (t >= 1) { v_add(X, P, A); v_sub(VEC, Y, X); }
-    else { v_madd(X, P, A, t); v_sub(T, Y, P); v_cross(TMP, T, A); v_cross(VEC, A, TMP); }
-  }
-  else
-  {
-    v_madd(Y, Q, B, u);
-    if ((t <= 0) || (t != t)) { v_cpy(X, P); v_cross(TMP, T, B); v_cross(VEC, B, TMP); }
-    else if (t >= 1) { v_add(X, P, A); v_sub(T, Q, X); v_cross(TMP, T, B); v_cross(VEC, B, TMP); }
-    else
-    {
-      v_madd(X, P, A, t);
-      v_cross(VEC, A, B);
-      if (v_dot(VEC, T) < 0) { VEC[0] = VEC[0] * -1; VEC[1] = VEC[1] * -1; VEC[2] = VEC[2] * -1; }
-    }
+    const double vm = flip ? -Vm[k] : Vm[k];  // the reference multiplies by -1: the same value
+    VEC[k] = (um && tm) ? vm : ((!um && !tm) ? Ve[k] : Vx[k]);
   }
 }
 

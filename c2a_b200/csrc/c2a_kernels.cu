@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -425,6 +426,10 @@ struct PinnedLease
 };
 }  // namespace
 
+// wall-clock breakdown of the last host-buffer call on this thread (development aid, c2a_b200_testing.h)
+static thread_local double g_host_timing[8];
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 // host-buffer path shared by the three public host entries: inputs are poses (motion constants computed
 // here) or ready motion records; step_in != NULL selects single-step mode
 static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses, const double *motions,
@@ -437,6 +442,7 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
   const bool want_contacts = !step_in && (out->num_contact || out->contacts);
   if (want_contacts && out->contacts && out->max_contacts <= 0) return fail(C2A_B200_ERR_ARG, "contacts requested with max_contacts <= 0");
   CUDA_TRY(cudaSetDevice(a->device));
+  const double t_begin = now_s();
   cudaStream_t stream;
   CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
 
@@ -489,11 +495,13 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
   PinnedLease pin;
   STEP(pin.acquire(N * 48 * 8));
   double *staging = (double *)pin.ptr;
+  const double t_alloc = now_s();
   if (rc == C2A_B200_OK)
   {
     if (poses) motions_from_poses_mt(poses, n, staging, 0);
     else memcpy(staging, motions, N * 48 * 8);
   }
+  const double t_motions = now_s();
   if (step_in) STEP(cudaMemcpyAsync(arena + o_step, step_in, N * STEP_IN_DOUBLES * 8, cudaMemcpyHostToDevice, stream));
   std::vector<int32_t> order_host;
   if (use_order && rc == C2A_B200_OK)
@@ -502,6 +510,7 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
     schedule_order(staging, n, a->root_ang_radius, b->root_ang_radius, order_host.data());
     STEP(cudaMemcpyAsync(arena + o_order, order_host.data(), N * 4, cudaMemcpyHostToDevice, stream));
   }
+  const double t_order = now_s();
   STEP(cudaMemcpyAsync(arena + o_pose, staging, N * 48 * 8, cudaMemcpyHostToDevice, stream));
   if (seed_a) STEP(cudaMemcpyAsync(arena + o_sa, seed_a, N * 4, cudaMemcpyHostToDevice, stream));
   if (seed_b) STEP(cudaMemcpyAsync(arena + o_sb, seed_b, N * 4, cudaMemcpyHostToDevice, stream));
@@ -515,6 +524,9 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
     rc = launch_contacts(a, b, d.pose_toc, nullptr, d.distance, d.collisionfree, d.status, n, out->max_contacts,
                          (int *)(arena + o_nc), out->contacts ? (c2a_b200_contact *)(arena + o_ct) : nullptr,
                          (unsigned long long *)(arena + o_cnt2), stream);
+  const double t_launched = now_s();
+  if (rc == C2A_B200_OK) cudaStreamSynchronize(stream);
+  const double t_kernel = now_s();
   if (want_contacts && out->num_contact) STEP(cudaMemcpyAsync(out->num_contact, arena + o_nc, N * 4, cudaMemcpyDeviceToHost, stream));
   if (want_contacts && out->contacts)
     STEP(cudaMemcpyAsync(out->contacts, arena + o_ct, N * (size_t)out->max_contacts * sizeof(c2a_b200_contact), cudaMemcpyDeviceToHost, stream));
@@ -527,10 +539,22 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
 #undef BACK
   STEP(cudaStreamSynchronize(stream));
 #undef STEP
+  const double t_back = now_s();
   cudaFreeAsync(arena, stream);
   cudaStreamSynchronize(stream);
   cudaStreamDestroy(stream);
+  const double t_end = now_s();
+  g_host_timing[0] = t_alloc - t_begin; g_host_timing[1] = t_motions - t_alloc; g_host_timing[2] = t_order - t_motions;
+  g_host_timing[3] = t_launched - t_order; g_host_timing[4] = t_kernel - t_launched; g_host_timing[5] = t_back - t_kernel;
+  g_host_timing[6] = t_end - t_back; g_host_timing[7] = t_end - t_begin;
   return rc;
+}
+
+int c2a_b200_host_timing(double *out8)
+{
+  if (!out8) return fail(C2A_B200_ERR_ARG, "NULL argument");
+  memcpy(out8, g_host_timing, sizeof(g_host_timing));
+  return C2A_B200_OK;
 }
 
 int c2a_b200_solve_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses,
@@ -678,18 +702,20 @@ int c2a_b200_test_sincos(const double *x, int64_t n, double *s, double *c)
 // device and read them back: out[0..5] = {expand passes, expand lanes, leaf passes, leaf lanes, advance
 // passes, advance lanes} accumulated since the last enable; out[6..8] = globaltimer ns at launch start, at
 // the first failed claim (batch drained) and at the last slot retirement (one launch between enables);
-// out[9..10] = 32-lane look-ahead passes and the expansion levels they committed (out must hold 11).
-int c2a_b200_phase_stats(int32_t enable, uint64_t *out9)
+// out[9..10] = 32-lane look-ahead passes and the expansion levels they committed;
+// out[11..13] = warp cycles spent in EXPAND / LEAF / ADVANCE passes (out must hold 14).
+int c2a_b200_phase_stats(int32_t enable, uint64_t *out14)
 {
+  uint64_t *out9 = out14;
   if (out9 && g_stats_dev)
   {
     CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpy(out9, g_stats_dev, 11 * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out9, g_stats_dev, 14 * 8, cudaMemcpyDeviceToHost));
   }
   if (enable && !g_stats_dev) CUDA_TRY(cudaMalloc(&g_stats_dev, 16 * 8));
   if (enable)
   {
-    const unsigned long long init[11] = {0, 0, 0, 0, 0, 0, ~0ull, ~0ull, 0, 0, 0};
+    const unsigned long long init[14] = {0, 0, 0, 0, 0, 0, ~0ull, ~0ull, 0, 0, 0, 0, 0, 0};
     CUDA_TRY(cudaMemcpy(g_stats_dev, init, sizeof(init), cudaMemcpyHostToDevice));
   }
   if (!enable && g_stats_dev) { cudaFree(g_stats_dev); g_stats_dev = nullptr; }

@@ -67,7 +67,7 @@ struct BatchArgs
   int stack_entries;
   const int *order;       // optional [n]: the k-th claim takes query order[k] (longest-expected first); NULL = identity
   const double *step_in;  // optional [n][STEP_IN_DOUBLES]: single-step mode (C2A_TimeOfContactStep), see below
-  unsigned long long *stats;  // optional [8]: per phase {passes, lanes used}: expand, leaf, advance; NULL = off
+  unsigned long long *stats;  // optional [14], see c2a_b200_phase_stats; NULL = off
 };
 
 // Single-step mode (the device side of C2A_TimeOfContactStep, C2A.cpp:1778-1931): per query the caller
@@ -165,12 +165,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
     else if (nL > 0 || nA > 0) phase = (nL >= nA) ? ST_LEAF : ST_ADVANCE;
     else phase = ST_TRAVERSE;
 
-    if (args.stats && lane == 0)
+    const bool steady = (mT | mL | mA) == FULL;  // statistics cover warps whose 32 slots are all live (not the tail)
+    if (args.stats && lane == 0 && steady)
     {
       const int k = phase == ST_TRAVERSE ? 0 : (phase == ST_LEAF ? 2 : 4);
       atomicAdd(args.stats + k, 1ull);
       atomicAdd(args.stats + k + 1, (unsigned long long)(phase == ST_TRAVERSE ? (nT >= 5 ? 2 * min(nT, 16) : (nT >= 3 ? 6 * nT : (nT == 2 ? 28 : 30))) : (phase == ST_LEAF ? nL : nA)));  // LEAF: slots served (9 lanes each, 3 per round)
     }
+    const long long pass_t0 = args.stats ? clock64() : 0;
     if (phase == ST_TRAVERSE)
     {
       // -------------------------------------------------------------------- EXPAND ----------
@@ -678,6 +680,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
       }
     }
     __syncwarp();
+    if (args.stats && lane == 0 && steady) atomicAdd(args.stats + 11 + (phase == ST_TRAVERSE ? 0 : (phase == ST_LEAF ? 1 : 2)), (unsigned long long)(clock64() - pass_t0));
   }
 #undef SD
 #undef SI

@@ -30,11 +30,15 @@ int c2a_b200_test_sincos(const double *x, int64_t n, double *s, double *c);
 int c2a_b200_host_sincos(const double *x, int64_t n, double *s, double *c);
 
 /* Phase statistics of the solve kernel (development aid): see c2a_kernels.cu. */
-int c2a_b200_phase_stats(int32_t enable, uint64_t *out9);
+int c2a_b200_phase_stats(int32_t enable, uint64_t *out14);
 
 /* FP64 pipe peak of the current device in TFLOP/s: dependent-free DFMA chains, and the same with
  * separate DMUL + DADD (the product is built with -fmad=false, so that is its ceiling). */
 int c2a_b200_fp64_peak(double *tflops_fma, double *tflops_mul_add);
+
+/* Wall-clock breakdown (seconds) of this thread's last host-buffer call: stream+arena allocation, motion
+ * set-up, claim order, enqueue (H2D + launch), wait for the kernels, D2H of the results, release, total. */
+int c2a_b200_host_timing(double *out8);
 
 #ifdef __cplusplus
 }
