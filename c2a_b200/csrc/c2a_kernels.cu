@@ -270,9 +270,23 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   // traversal stacks: one per query slot, depth(A)+depth(B)+2 entries of 128 B
   args.stack_entries = a->depth + b->depth + 2;
   const size_t stack_bytes = (size_t)blocks * WARPS_PER_BLOCK * Q * args.stack_entries * ENTRY_DOUBLES * sizeof(double);
+  // tail hand-over mailbox (whole-query mode only): control words | ready flags | records
+  const bool handover = !step_in && getenv("C2A_B200_HANDOVER");  // experimental, off by default (no gain measured yet)
+  const size_t mb_cap = handover ? (size_t)blocks * WARPS_PER_BLOCK * Q : 0;
+  const size_t ctl_bytes = 64, ready_bytes = (mb_cap * sizeof(int) + 63) & ~(size_t)63, recs_bytes = mb_cap * MB_DOUBLES * sizeof(double);
   double *stacks = nullptr;
-  CUDA_TRY(cudaMallocAsync(&stacks, stack_bytes, stream));
+  CUDA_TRY(cudaMallocAsync(&stacks, stack_bytes + (handover ? ctl_bytes + ready_bytes + recs_bytes : 0), stream));
   args.stacks = stacks;
+  args.ctl = nullptr; args.mb_ready = nullptr; args.mb_recs = nullptr; args.mb_cap = 0;
+  if (handover)
+  {
+    char *extra = reinterpret_cast<char *>(stacks) + stack_bytes;
+    args.ctl = reinterpret_cast<unsigned long long *>(extra);
+    args.mb_ready = reinterpret_cast<int *>(extra + ctl_bytes);
+    args.mb_recs = reinterpret_cast<double *>(extra + ctl_bytes + ready_bytes);
+    args.mb_cap = (int)mb_cap;
+    CUDA_TRY(cudaMemsetAsync(extra, 0, ctl_bytes + ready_bytes, stream));
+  }
   args.stats = g_stats_dev;
   CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
   c2a_solve_kernel<<<(unsigned)blocks, BLOCK_THREADS, BLOCK_SMEM_BYTES, stream>>>(args);
@@ -703,19 +717,20 @@ int c2a_b200_test_sincos(const double *x, int64_t n, double *s, double *c)
 // passes, advance lanes} accumulated since the last enable; out[6..8] = globaltimer ns at launch start, at
 // the first failed claim (batch drained) and at the last slot retirement (one launch between enables);
 // out[9..10] = 32-lane look-ahead passes and the expansion levels they committed;
-// out[11..13] = warp cycles spent in EXPAND / LEAF / ADVANCE passes (out must hold 14).
-int c2a_b200_phase_stats(int32_t enable, uint64_t *out14)
+// out[11..13] = warp cycles spent in EXPAND / LEAF / ADVANCE passes; out[14..19] = {passes, cycles} of the
+// three phases for a query alone on its warp (out must hold 20).
+int c2a_b200_phase_stats(int32_t enable, uint64_t *out20)
 {
-  uint64_t *out9 = out14;
+  uint64_t *out9 = out20;
   if (out9 && g_stats_dev)
   {
     CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpy(out9, g_stats_dev, 14 * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out9, g_stats_dev, 20 * 8, cudaMemcpyDeviceToHost));
   }
-  if (enable && !g_stats_dev) CUDA_TRY(cudaMalloc(&g_stats_dev, 16 * 8));
+  if (enable && !g_stats_dev) CUDA_TRY(cudaMalloc(&g_stats_dev, 24 * 8));
   if (enable)
   {
-    const unsigned long long init[14] = {0, 0, 0, 0, 0, 0, ~0ull, ~0ull, 0, 0, 0, 0, 0, 0};
+    const unsigned long long init[24] = {0, 0, 0, 0, 0, 0, ~0ull, ~0ull};
     CUDA_TRY(cudaMemcpy(g_stats_dev, init, sizeof(init), cudaMemcpyHostToDevice));
   }
   if (!enable && g_stats_dev) { cudaFree(g_stats_dev); g_stats_dev = nullptr; }

@@ -52,7 +52,8 @@ struct DevModel
 constexpr int ENTRY_DOUBLES = 16;  // R(9) T(3) d mint {b1,b2} pad  -> 128 B
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr int BLOCK_THREADS = 32 * WARPS_PER_BLOCK;
-constexpr int Q = 32;              // query slots per warp
+constexpr int Q = 48;              // query slots per warp: more than one EXPAND pass (16) plus one LEAF pass can use,
+                                   // so that leaves pile up to a full 32-lane LEAF pass while expansion stays fed
 
 struct BatchArgs
 {
@@ -68,7 +69,15 @@ struct BatchArgs
   const int *order;       // optional [n]: the k-th claim takes query order[k] (longest-expected first); NULL = identity
   const double *step_in;  // optional [n][STEP_IN_DOUBLES]: single-step mode (C2A_TimeOfContactStep), see below
   unsigned long long *stats;  // optional [14], see c2a_b200_phase_stats; NULL = off
+  // Tail hand-over (NULL = off): once the claim queue is empty, a warp that still holds several queries
+  // passes one on, at a CA-step boundary (where a query's state is ~64 bytes: no stack), to a warp that
+  // has run out of work; alone on a warp, a query gets all 32 lanes for look-ahead.
+  unsigned long long *ctl;   // [0] hand-over tickets issued  [1] taken  [2] queries finished  [3] warps waiting for work
+  int *mb_ready;             // [mb_cap] record i is complete
+  double *mb_recs;           // [mb_cap][MB_DOUBLES]
+  int mb_cap;
 };
+constexpr int MB_DOUBLES = 8;  // q, lamda, lastLamda, mint, UpboundTOC, {numCA, nItrs}, {nbv, ntri}, {lastA, lastB}
 
 // Single-step mode (the device side of C2A_TimeOfContactStep, C2A.cpp:1778-1931): per query the caller
 // supplies the current poses and the CA-loop state the step reads -- R1(9) T1(3) R2(9) T2(3) numCA
@@ -90,9 +99,8 @@ enum
   F_DIST = 38, F_MINT = 39, F_ABS = 40, F_REL = 41, F_UPB = 42,
   F_CUR = 43,    // 12 current entry: R(9) T(3) of the node pair to visit next
   F_LAMDA = 55, F_LASTL = 56,
-  F_P1 = 57, F_P2 = 60,
-  F_CURSZ1 = 63, F_CURSZ2 = 64,  // GetSize() of the current entry's two nodes (with I_CURFC1/2: their NodeMeta)
-  F_NDBL = 65
+  F_CURSZ1 = 57, F_CURSZ2 = 58,  // GetSize() of the current entry's two nodes (with I_CURFC1/2: their NodeMeta)
+  F_NDBL = 59                    // (res->p1/p2 are outputs only: written straight to the result arrays)
 };
 enum
 {
@@ -110,6 +118,14 @@ C2A_DEV void load9(double d[9], const double *s)
 C2A_DEV void load3(double d[3], const double *s) { d[0] = __ldg(s); d[1] = __ldg(s + 1); d[2] = __ldg(s + 2); }
 C2A_DEV unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 C2A_DEV void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// index of the (n+1)-th set bit of a 64-bit slot mask
+C2A_DEV int nth_slot(unsigned long long m, int n)
+{
+  const unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
+  const int nlo = __popc(lo);
+  return n < nlo ? (int)__fns(lo, 0, n + 1) : 32 + (int)__fns(hi, 0, n - nlo + 1);
+}
 
 __device__ __noinline__ double tri_distance_nl(const double R[9], const double T[3], const double *t1,
                                                const double *t2, double p[3], double q[3])
@@ -144,28 +160,87 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
 #define SI(f, s) si[(f) * Q + (s)]
 
   if (args.stats && threadIdx.x == 0) atomicMin(args.stats + 6, global_ns());  // launch start
-  SI(I_STATE, lane) = ST_ADVANCE;
-  SI(I_QLO, lane) = -1; SI(I_QHI, lane) = -1;
-  SI(I_PENDING, lane) = 0;
+  for (int sl = lane; sl < Q; sl += 32)
+  {
+    SI(I_STATE, sl) = ST_ADVANCE;
+    SI(I_QLO, sl) = -1; SI(I_QHI, sl) = -1;
+    SI(I_PENDING, sl) = 0;
+  }
   __syncwarp();
 
+  unsigned pass_no = 0;
   while (true)
   {
-    const int st = SI(I_STATE, lane);
-    const unsigned mT = __ballot_sync(FULL, st == ST_TRAVERSE);
-    const unsigned mL = __ballot_sync(FULL, st == ST_LEAF);
-    const unsigned mA = __ballot_sync(FULL, st == ST_ADVANCE);
-    if ((mT | mL | mA) == 0) break;
-    const int nT = __popc(mT), nL = __popc(mL), nA = __popc(mA);
+    pass_no++;
+    const int st = SI(I_STATE, lane), st2 = (lane + 32 < Q) ? SI(I_STATE, lane + 32) : (int)ST_EXIT;
+    const unsigned long long mT = __ballot_sync(FULL, st == ST_TRAVERSE) | ((unsigned long long)__ballot_sync(FULL, st2 == ST_TRAVERSE) << 32);
+    const unsigned long long mL = __ballot_sync(FULL, st == ST_LEAF) | ((unsigned long long)__ballot_sync(FULL, st2 == ST_LEAF) << 32);
+    const unsigned long long mA = __ballot_sync(FULL, st == ST_ADVANCE) | ((unsigned long long)__ballot_sync(FULL, st2 == ST_ADVANCE) << 32);
+    const int n_live = __popcll(mT | mL | mA);
+    if (n_live == 0)
+    {
+      if (!args.ctl) break;
+      // out of work: wait for a query handed over by a busier warp, until every query of the batch is finished
+      long long got = -1;
+      if (lane == 0)
+      {
+        atomicAdd(args.ctl + 3, 1ull);
+        while (true)
+        {
+          if (*(volatile unsigned long long *)(args.ctl + 2) >= (unsigned long long)args.n) { got = -2; break; }
+          const unsigned long long h = *(volatile unsigned long long *)(args.ctl + 1), r = *(volatile unsigned long long *)(args.ctl + 0);
+          if (h < r && h < (unsigned long long)args.mb_cap && *(volatile int *)(args.mb_ready + h) != 0 &&
+              atomicCAS(args.ctl + 1, h, h + 1) == h)
+          {
+            got = (long long)h;
+            break;
+          }
+          __nanosleep(1000);
+        }
+        atomicAdd(args.ctl + 3, ~0ull);  // -1
+        if (got >= 0)
+        {
+          __threadfence();
+          const double *r = args.mb_recs + (size_t)got * MB_DOUBLES;
+          const long long q = __double_as_longlong(__ldcg(r + 0));
+          const double *rec = args.motions + (size_t)(2 * MOTION_DOUBLES) * q;
+          const int slot = 0;
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+          {
+            SD(F_CV1 + i, slot) = __ldg(rec + 12 + i); SD(F_AX1 + i, slot) = __ldg(rec + 15 + i);
+            SD(F_CV2 + i, slot) = __ldg(rec + MOTION_DOUBLES + 12 + i); SD(F_AX2 + i, slot) = __ldg(rec + MOTION_DOUBLES + 15 + i);
+          }
+          SD(F_W1, slot) = __ldg(rec + 18); SD(F_W2, slot) = __ldg(rec + MOTION_DOUBLES + 18);
+          SI(I_SEEDA, slot) = args.seedA ? args.seedA[q] : 0;
+          SI(I_SEEDB, slot) = args.seedB ? args.seedB[q] : 0;
+          SD(F_LAMDA, slot) = __ldcg(r + 1); SD(F_LASTL, slot) = __ldcg(r + 2); SD(F_MINT, slot) = __ldcg(r + 3); SD(F_UPB, slot) = __ldcg(r + 4);
+          const double c5 = __ldcg(r + 5), c6 = __ldcg(r + 6), c7 = __ldcg(r + 7);
+          SI(I_NUMCA, slot) = __double2hiint(c5); SI(I_NITRS, slot) = __double2loint(c5);
+          SI(I_NBV, slot) = __double2hiint(c6); SI(I_NTRI, slot) = __double2loint(c6);
+          SI(I_LASTA, slot) = __double2hiint(c7); SI(I_LASTB, slot) = __double2loint(c7);
+          SD(F_DIST, slot) = 0;
+          SI(I_QLO, slot) = (int)(unsigned)(q & 0xffffffffll); SI(I_QHI, slot) = (int)(q >> 32);
+          SI(I_PENDING, slot) = 1;
+          SI(I_STATE, slot) = ST_ADVANCE;
+        }
+      }
+      got = __shfl_sync(FULL, got, 0);
+      if (got == -2) break;
+      __syncwarp();
+      continue;
+    }
+    const int nT = __popcll(mT), nL = min(__popcll(mL), 32), nA = min(__popcll(mA), 32);  // a pass serves at most 32 slots
     // Phase choice: a full expansion pass (16 slots x 2 lanes) whenever one is available; otherwise
     // first turn waiting slots back into traversable ones (the larger of the LEAF / ADVANCE groups),
     // and only run a partial expansion pass when nothing is waiting.
     int phase;
-    if (nT >= 16) phase = ST_TRAVERSE;
+    if (nL == 32) phase = ST_LEAF;  // cannot get fuller
+    else if (nT >= 16) phase = ST_TRAVERSE;
     else if (nL > 0 || nA > 0) phase = (nL >= nA) ? ST_LEAF : ST_ADVANCE;
     else phase = ST_TRAVERSE;
 
-    const bool steady = (mT | mL | mA) == FULL;  // statistics cover warps whose 32 slots are all live (not the tail)
+    const bool steady = (mT | mL | mA) == ((1ull << Q) - 1ull);  // statistics cover warps whose slots are all live (not the tail)
     if (args.stats && lane == 0 && steady)
     {
       const int k = phase == ST_TRAVERSE ? 0 : (phase == ST_LEAF ? 2 : 4);
@@ -189,7 +264,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
       const int grp = lane / G, t = lane - grp * G;
       if (grp < nT)
       {
-        const int slot = __fns(mT, 0, grp + 1);
+        const int slot = nth_slot(mT, (pass_no & 1) ? nT - 1 - grp : grp);  // alternate ends: no slot is starved
         const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << (grp * G));
         const int gbase = grp * G;
         double *stk = stack_base + (size_t)slot * stack_stride;
@@ -425,7 +500,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
       // C2A.cpp:1141-1183
       if (lane < nL)
       {
-        const int slot = __fns(mL, 0, lane + 1);
+        const int slot = nth_slot(mL, lane);
         const int b1 = SI(I_LEAFB1, slot), b2 = SI(I_LEAFB2, slot);
         double Rrel[9], Trel[3], p[3], qq[3];
 #pragma unroll
@@ -447,8 +522,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
           v_sub(S1, w2, w1);
           v_normalize(S1);  // S2 = S1 * -1 normalises to exactly -S1 (see c2a_motion.cuh)
           S2[0] = -S1[0]; S2[1] = -S1[1]; S2[2] = -S1[2];
+          if (args.out.p1p2)
+          {
+            const long long q = ((long long)SI(I_QHI, slot) << 32) | (unsigned)SI(I_QLO, slot);
 #pragma unroll
-          for (int i = 0; i < 3; i++) { SD(F_P1 + i, slot) = p[i]; SD(F_P2 + i, slot) = qq[i]; }
+            for (int i = 0; i < 3; i++) { args.out.p1p2[6 * q + i] = p[i]; args.out.p1p2[6 * q + 3 + i] = qq[i]; }
+          }
           Motion m;
 #pragma unroll
           for (int i = 0; i < 3; i++) { m.cv[i] = SD(F_CV1 + i, slot); m.axis[i] = SD(F_AX1 + i, slot); }
@@ -473,11 +552,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
       // CA-loop bookkeeping after a finished step / result write-out / claim / next step's set-up
       if (lane < nA)
       {
-        const int slot = __fns(mA, 0, lane + 1);
+        const int slot = nth_slot(mA, lane);
         long long q = ((long long)SI(I_QHI, slot) << 32) | (unsigned)SI(I_QLO, slot);
         bool pending = SI(I_PENDING, slot) != 0;
         int numCA = SI(I_NUMCA, slot);
         double lamda = SD(F_LAMDA, slot);
+        bool handed_over = false;
         if (q >= 0 && !pending && args.step_in)
         {
           // single-step mode: report this traversal and release the slot
@@ -488,13 +568,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
           if (o.distance) o.distance[q] = SD(F_DIST, slot);
           if (o.mint) o.mint[q] = SD(F_MINT, slot);
           if (o.last_tri) { o.last_tri[2 * q] = SI(I_LASTA, slot); o.last_tri[2 * q + 1] = SI(I_LASTB, slot); }
-          if (o.p1p2)
-          {
-#pragma unroll
-            for (int i = 0; i < 3; i++) { o.p1p2[6 * q + i] = SD(F_P1 + i, slot); o.p1p2[6 * q + 3 + i] = SD(F_P2 + i, slot); }
-          }
           q = -1;
         }
+        bool just_continued = false;
         if (q >= 0 && !pending)
         {
           // a step just ended: C2A_QueryTimeOfContact's loop, C2A.cpp:2053-2123
@@ -524,6 +600,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
                   numCA++;
                   SD(F_UPB, slot) = 1.0 - lamda;
                   pending = true;
+                  just_continued = true;
                 }
               }
             }
@@ -563,16 +640,35 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
             if (o.distance) o.distance[q] = dist;
             if (o.mint) o.mint[q] = mint;
             if (o.last_tri) { o.last_tri[2 * q] = SI(I_LASTA, slot); o.last_tri[2 * q + 1] = SI(I_LASTB, slot); }
-            if (o.p1p2)
-            {
-#pragma unroll
-              for (int i = 0; i < 3; i++) { o.p1p2[6 * q + i] = SD(F_P1 + i, slot); o.p1p2[6 * q + 3 + i] = SD(F_P2 + i, slot); }
-            }
+            if (args.ctl) atomicAdd(args.ctl + 2, 1ull);
             q = -1;
           }
         }
 
-        if (q < 0)
+        // tail hand-over: the queue is empty (this warp holds exited slots), the warp has other live
+        // queries, and some warp is waiting for work -> pass this query on at its step boundary
+        if (args.ctl && just_continued && lane == 0 && n_live > 1 && n_live < Q)
+        {
+          const unsigned long long waiting = *(volatile unsigned long long *)(args.ctl + 3);
+          const unsigned long long issued = *(volatile unsigned long long *)(args.ctl + 0), taken = *(volatile unsigned long long *)(args.ctl + 1);
+          if (waiting > issued - taken)
+          {
+            const unsigned long long idx = atomicAdd(args.ctl + 0, 1ull);
+            if (idx < (unsigned long long)args.mb_cap)
+            {
+              double *r = args.mb_recs + (size_t)idx * MB_DOUBLES;
+              r[0] = __longlong_as_double(q); r[1] = lamda; r[2] = SD(F_LASTL, slot); r[3] = SD(F_MINT, slot); r[4] = SD(F_UPB, slot);
+              r[5] = __hiloint2double(numCA, SI(I_NITRS, slot)); r[6] = __hiloint2double(SI(I_NBV, slot), SI(I_NTRI, slot));
+              r[7] = __hiloint2double(SI(I_LASTA, slot), SI(I_LASTB, slot));
+              __threadfence();
+              *(volatile int *)(args.mb_ready + idx) = 1;
+              SI(I_STATE, slot) = ST_EXIT;
+              q = -1; pending = false; handed_over = true;
+            }
+          }
+        }
+
+        if (q < 0 && !handed_over)
         {
           // claim the next query
           const long long nq = (long long)atomicAdd(args.counter, 1ull);
@@ -590,6 +686,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
             {
               // translation-only branch of the reference (C2A.cpp:2391-2395): not implemented
               if (args.out.status) args.out.status[q] = C2A_B200_QUERY_TRANSLATION_ONLY;
+              if (args.ctl) atomicAdd(args.ctl + 2, 1ull);
               q = -1;  // stay in ADVANCE: claim another one next round
             }
             else
@@ -612,8 +709,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
                 const double *si_ = args.step_in + (size_t)STEP_IN_DOUBLES * q;
                 numCA = (int)__ldg(si_ + 24); SD(F_MINT, slot) = __ldg(si_ + 25); SD(F_UPB, slot) = __ldg(si_ + 26);
               }
+              if (args.out.p1p2)
+              {
+                // res->p1/p2 stay zero unless a leaf improves the distance (the LEAF phase writes them in place)
 #pragma unroll
-              for (int i = 0; i < 3; i++) { SD(F_P1 + i, slot) = 0; SD(F_P2 + i, slot) = 0; }
+                for (int i = 0; i < 6; i++) args.out.p1p2[6 * q + i] = 0.0;
+              }
               pending = true;
             }
           }
@@ -674,6 +775,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
           pending = false;
           SI(I_STATE, slot) = ST_TRAVERSE;
         }
+        if (handed_over) { SI(I_QLO, slot) = -1; SI(I_QHI, slot) = -1; }
         SI(I_NUMCA, slot) = numCA;
         SD(F_LAMDA, slot) = lamda;
         SI(I_PENDING, slot) = pending ? 1 : 0;
@@ -681,6 +783,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
     }
     __syncwarp();
     if (args.stats && lane == 0 && steady) atomicAdd(args.stats + 11 + (phase == ST_TRAVERSE ? 0 : (phase == ST_LEAF ? 1 : 2)), (unsigned long long)(clock64() - pass_t0));
+    if (args.stats && lane == 0 && n_live == 1)
+    {
+      // a query alone on its warp (the tail of a launch, or a single-query call): passes and cycles per phase
+      const int k = 14 + 2 * (phase == ST_TRAVERSE ? 0 : (phase == ST_LEAF ? 1 : 2));
+      atomicAdd(args.stats + k, 1ull); atomicAdd(args.stats + k + 1, (unsigned long long)(clock64() - pass_t0));
+    }
   }
 #undef SD
 #undef SI

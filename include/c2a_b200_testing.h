@@ -30,7 +30,7 @@ int c2a_b200_test_sincos(const double *x, int64_t n, double *s, double *c);
 int c2a_b200_host_sincos(const double *x, int64_t n, double *s, double *c);
 
 /* Phase statistics of the solve kernel (development aid): see c2a_kernels.cu. */
-int c2a_b200_phase_stats(int32_t enable, uint64_t *out14);
+int c2a_b200_phase_stats(int32_t enable, uint64_t *out20);
 
 /* FP64 pipe peak of the current device in TFLOP/s: dependent-free DFMA chains, and the same with
  * separate DMUL + DADD (the product is built with -fmad=false, so that is its ceiling). */
