@@ -257,6 +257,22 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   static std::atomic<bool> attr_set{false};
   if (!attr_set.exchange(true))
     CUDA_TRY(cudaFuncSetAttribute(c2a_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BLOCK_SMEM_BYTES));
+  {
+    // keep the per-launch scratch (traversal stacks, staging arena) in the stream-ordered pool between launches
+    static std::mutex m;
+    static std::vector<int> done;
+    std::lock_guard<std::mutex> lk(m);
+    if (std::find(done.begin(), done.end(), a->device) == done.end())
+    {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, a->device) == cudaSuccess)
+      {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      done.push_back(a->device);
+    }
+  }
   int sms = 0, per_sm = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, a->device));
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c2a_solve_kernel, BLOCK_THREADS, BLOCK_SMEM_BYTES));
