@@ -178,6 +178,57 @@ def solve_batch(model_a, model_b, poses, seed_a=None, seed_b=None, tol_d=1e-4, t
     return out
 
 
+def solve_pairs(models, model_a, model_b, poses, seed_a=None, seed_b=None, tol_d=1e-4, tol_t=1e-4, fields=None):
+    """Heterogeneous batch (per-query model handles): ``models`` is a list of Model on one device,
+    ``model_a`` / ``model_b`` [n] index into it.  Returns the same dict as ``solve_batch``."""
+    poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 48)
+    n = poses.shape[0]
+    ma = np.ascontiguousarray(model_a, dtype=np.int32)
+    mb = np.ascontiguousarray(model_b, dtype=np.int32)
+    assert ma.shape == (n,) and mb.shape == (n,)
+    res = Results()
+    out = {}
+    for name, dt, shape in RESULT_FIELDS:
+        if fields is not None and name not in fields:
+            continue
+        a = np.zeros((n,) + shape, dtype=dt)
+        out[name] = a
+        setattr(res, name, a.ctypes.data)
+    if fields is None or "last_tri" in fields:
+        out["last_tri"] = np.full((n, 2), -1, dtype=np.int32)
+        res.last_tri = out["last_tri"].ctypes.data
+    sa = None if seed_a is None else np.ascontiguousarray(seed_a, dtype=np.int32)
+    sb = None if seed_b is None else np.ascontiguousarray(seed_b, dtype=np.int32)
+    handles = (C.c_void_p * len(models))(*[m.h for m in models])
+    _check(lib().c2a_b200_solve_pairs(handles, C.c_int32(len(models)), ma.ctypes.data_as(C.c_void_p), mb.ctypes.data_as(C.c_void_p),
+                                      poses.ctypes.data_as(C.c_void_p),
+                                      sa.ctypes.data_as(C.c_void_p) if sa is not None else None,
+                                      sb.ctypes.data_as(C.c_void_p) if sb is not None else None,
+                                      C.c_int64(n), C.c_double(tol_d), C.c_double(tol_t), C.byref(res)))
+    return out
+
+
+def broadphase(c0, c1, radius, margin=0.0, device=0, max_pairs=None):
+    """Swept-sphere candidate pairs of a scene: c0, c1 [n,3] (begin / end position of each instance's model
+    origin), radius [n] (max |vertex| of its model).  Returns int32 [m,2] with i < j, sorted."""
+    c0 = np.ascontiguousarray(c0, dtype=np.float64).reshape(-1, 3)
+    c1 = np.ascontiguousarray(c1, dtype=np.float64).reshape(-1, 3)
+    r = np.ascontiguousarray(radius, dtype=np.float64).reshape(-1)
+    n = c0.shape[0]
+    assert c1.shape == (n, 3) and r.shape == (n,)
+    cap = int(max_pairs) if max_pairs is not None else max(1024, 32 * n)
+    while True:
+        pairs = np.empty((cap, 2), dtype=np.int32)
+        found = C.c_int64(0)
+        _check(lib().c2a_b200_broadphase(c0.ctypes.data_as(C.c_void_p), c1.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p),
+                                         C.c_int32(n), C.c_double(margin), C.c_int32(device), pairs.ctypes.data_as(C.c_void_p),
+                                         C.c_int64(cap), C.byref(found)))
+        if found.value <= cap or max_pairs is not None:
+            pairs = pairs[:min(found.value, cap)]
+            return pairs[np.lexsort((pairs[:, 1], pairs[:, 0]))]
+        cap = int(found.value)
+
+
 def contacts_batch(model_a, model_b, poses24, threshold, max_contacts=64):
     """Batched C2A_QueryContact: poses24 [n,24] (pose of A, pose of B), threshold [n]."""
     poses24 = np.ascontiguousarray(poses24, dtype=np.float64).reshape(-1, 24)

@@ -278,7 +278,9 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c2a_solve_kernel, BLOCK_THREADS, BLOCK_SMEM_BYTES));
   if (per_sm < 1) per_sm = 1;
   long long blocks = (long long)sms * per_sm;  // persistent: one resident wave (a multiple of the SM count)
-  const long long need = (n + WARPS_PER_BLOCK * Q - 1) / (WARPS_PER_BLOCK * Q);
+  // small batches spread out, one query per warp before any warp takes a second one: a warp that holds few
+  // queries spends its idle lanes on look-ahead, so each query finishes sooner (the GPU is not full anyway)
+  const long long need = (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
   if (blocks > need) blocks = need;
   if (const char *cap = getenv("C2A_B200_MAX_BLOCKS"))  // development aid: profile a slice of the GPU
     if (atoll(cap) > 0 && blocks > atoll(cap)) blocks = atoll(cap);
@@ -585,6 +587,213 @@ int c2a_b200_host_timing(double *out8)
   if (!out8) return fail(C2A_B200_ERR_ARG, "NULL argument");
   memcpy(out8, g_host_timing, sizeof(g_host_timing));
   return C2A_B200_OK;
+}
+
+// ---- heterogeneous batches (per-query model handles) and the swept-sphere broadphase: SURVEY section 8, config 4 ----
+int c2a_b200_solve_pairs(const c2a_b200_model *const *models, int32_t n_models, const int32_t *model_a,
+                         const int32_t *model_b, const double *poses, const int32_t *seed_a, const int32_t *seed_b,
+                         int64_t n, double tol_d, double tol_t, const c2a_b200_results *out)
+{
+  if (!models || n_models <= 0 || !out || n < 0 || (n > 0 && (!poses || !model_a || !model_b)))
+    return fail(C2A_B200_ERR_ARG, "NULL argument");
+  if (n > 0x7fffffff) return fail(C2A_B200_ERR_ARG, "batch too large for 32-bit query indices");
+  if (out->num_contact || out->contacts) return fail(C2A_B200_ERR_ARG, "the contact pass is not available for heterogeneous batches");
+  for (int32_t m = 0; m < n_models; m++)
+  {
+    if (!models[m]) return fail(C2A_B200_ERR_ARG, "NULL model handle");
+    if (models[m]->device != models[0]->device) return fail(C2A_B200_ERR_DEVICE, "models live on different devices");
+  }
+  if (n == 0) return C2A_B200_OK;
+  // group the queries by (model_a, model_b): every group is one launch whose claim order lists its queries
+  const size_t N = (size_t)n;
+  std::vector<int64_t> start((size_t)n_models * n_models + 1, 0);
+  for (size_t i = 0; i < N; i++)
+  {
+    if (model_a[i] < 0 || model_a[i] >= n_models || model_b[i] < 0 || model_b[i] >= n_models)
+      return fail(C2A_B200_ERR_ARG, "model index out of range");
+    start[(size_t)model_a[i] * n_models + model_b[i] + 1]++;
+  }
+  for (size_t g = 0; g < (size_t)n_models * n_models; g++) start[g + 1] += start[g];
+  for (size_t g = 0; g < (size_t)n_models * n_models; g++)
+    if (start[g + 1] > start[g])
+    {
+      int rc = check_pair(models[g / n_models], models[g % n_models], n, poses, out);
+      if (rc) return rc;
+    }
+  CUDA_TRY(cudaSetDevice(models[0]->device));
+  cudaStream_t stream;
+  CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_pose = take(N * 48 * 8), o_order = take(N * 4);
+  const size_t o_sa = seed_a ? take(N * 4) : 0, o_sb = seed_b ? take(N * 4) : 0;
+  const size_t o_zero = off;  // outputs start zeroed from here
+  const size_t o_status = out->status ? take(N * 4) : 0, o_cf = out->collisionfree ? take(N * 4) : 0;
+  const size_t o_nca = out->num_ca ? take(N * 4) : 0, o_nbv = out->num_bv_tests ? take(N * 4) : 0;
+  const size_t o_ntri = out->num_tri_tests ? take(N * 4) : 0;
+  const size_t o_toc = out->toc ? take(N * 8) : 0, o_dist = out->distance ? take(N * 8) : 0;
+  const size_t o_mint = out->mint ? take(N * 8) : 0, o_pp = out->p1p2 ? take(N * 48) : 0;
+  const size_t o_pt = out->pose_toc ? take(N * 192) : 0, o_lt = out->last_tri ? take(N * 8) : 0;
+  const size_t o_cnt = take((size_t)n_models * n_models * 8);
+  char *arena = nullptr;
+  cudaError_t e = cudaMallocAsync(&arena, off, stream);
+  if (e != cudaSuccess)
+  {
+    cudaStreamDestroy(stream);
+    return fail(C2A_B200_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+  }
+  c2a_b200_results d;
+  memset(&d, 0, sizeof(d));
+  if (out->status) d.status = (int32_t *)(arena + o_status);
+  if (out->collisionfree) d.collisionfree = (int32_t *)(arena + o_cf);
+  if (out->num_ca) d.num_ca = (int32_t *)(arena + o_nca);
+  if (out->num_bv_tests) d.num_bv_tests = (int32_t *)(arena + o_nbv);
+  if (out->num_tri_tests) d.num_tri_tests = (int32_t *)(arena + o_ntri);
+  if (out->toc) d.toc = (double *)(arena + o_toc);
+  if (out->distance) d.distance = (double *)(arena + o_dist);
+  if (out->mint) d.mint = (double *)(arena + o_mint);
+  if (out->p1p2) d.p1p2 = (double *)(arena + o_pp);
+  if (out->pose_toc) d.pose_toc = (double *)(arena + o_pt);
+  if (out->last_tri) d.last_tri = (int32_t *)(arena + o_lt);
+
+  int rc = C2A_B200_OK;
+#define STEP(x) \
+  if (rc == C2A_B200_OK && (e = (x)) != cudaSuccess) rc = fail(C2A_B200_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e));
+  STEP(cudaMemsetAsync(arena + o_zero, 0, off - o_zero, stream));
+  PinnedLease pin;
+  STEP(pin.acquire(N * 48 * 8));
+  std::vector<int32_t> order(N);
+  if (rc == C2A_B200_OK)
+  {
+    motions_from_poses_mt(poses, n, (double *)pin.ptr, 0);
+    // claim order: the whole batch sorted by expected length (the root radii of the first group stand in for
+    // all -- it is only a hint), then split stably by group
+    std::vector<int32_t> by_cost(N);
+    schedule_order((const double *)pin.ptr, n, models[model_a[0]]->root_ang_radius, models[model_b[0]]->root_ang_radius, by_cost.data());
+    std::vector<int64_t> cur(start.begin(), start.end() - 1);
+    for (size_t k = 0; k < N; k++)
+    {
+      const int32_t i = by_cost[k];
+      order[(size_t)cur[(size_t)model_a[i] * n_models + model_b[i]]++] = i;
+    }
+  }
+  STEP(cudaMemcpyAsync(arena + o_pose, pin.ptr, N * 48 * 8, cudaMemcpyHostToDevice, stream));
+  STEP(cudaMemcpyAsync(arena + o_order, order.data(), N * 4, cudaMemcpyHostToDevice, stream));
+  if (seed_a) STEP(cudaMemcpyAsync(arena + o_sa, seed_a, N * 4, cudaMemcpyHostToDevice, stream));
+  if (seed_b) STEP(cudaMemcpyAsync(arena + o_sb, seed_b, N * 4, cudaMemcpyHostToDevice, stream));
+  // one launch per non-empty group, on side streams so that a group's tail overlaps the next group's start
+  constexpr int NSIDE = 4;
+  cudaStream_t side[NSIDE] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ready = nullptr, done[NSIDE] = {nullptr, nullptr, nullptr, nullptr};
+  STEP(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  STEP(cudaEventRecord(ready, stream));
+  for (int k = 0; k < NSIDE; k++)
+  {
+    STEP(cudaStreamCreateWithFlags(&side[k], cudaStreamNonBlocking));
+    STEP(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+    if (rc == C2A_B200_OK) STEP(cudaStreamWaitEvent(side[k], ready, 0));
+  }
+  int launched = 0;
+  for (size_t g = 0; g < (size_t)n_models * n_models && rc == C2A_B200_OK; g++)
+  {
+    const int64_t ng = start[g + 1] - start[g];
+    if (ng == 0) continue;
+    rc = launch_batch(models[g / n_models], models[g % n_models], (const double *)(arena + o_pose),
+                      seed_a ? (const int32_t *)(arena + o_sa) : nullptr, seed_b ? (const int32_t *)(arena + o_sb) : nullptr, ng,
+                      tol_d, tol_t, &d, (unsigned long long *)(arena + o_cnt) + g, side[launched % NSIDE], nullptr,
+                      (const int32_t *)(arena + o_order) + start[g]);
+    launched++;
+  }
+  for (int k = 0; k < NSIDE; k++)
+    if (side[k] && done[k])
+    {
+      STEP(cudaEventRecord(done[k], side[k]));
+      STEP(cudaStreamWaitEvent(stream, done[k], 0));
+    }
+#define BACK(field, ofs, bytes) \
+  if (out->field) STEP(cudaMemcpyAsync(out->field, arena + ofs, bytes, cudaMemcpyDeviceToHost, stream));
+  BACK(status, o_status, N * 4) BACK(collisionfree, o_cf, N * 4) BACK(num_ca, o_nca, N * 4)
+  BACK(num_bv_tests, o_nbv, N * 4) BACK(num_tri_tests, o_ntri, N * 4) BACK(toc, o_toc, N * 8)
+  BACK(distance, o_dist, N * 8) BACK(mint, o_mint, N * 8) BACK(p1p2, o_pp, N * 48) BACK(pose_toc, o_pt, N * 192)
+  BACK(last_tri, o_lt, N * 8)
+#undef BACK
+  STEP(cudaStreamSynchronize(stream));
+#undef STEP
+  for (int k = 0; k < NSIDE; k++)
+  {
+    if (side[k]) { cudaStreamSynchronize(side[k]); cudaStreamDestroy(side[k]); }
+    if (done[k]) cudaEventDestroy(done[k]);
+  }
+  if (ready) cudaEventDestroy(ready);
+  cudaFreeAsync(arena, stream);
+  cudaStreamSynchronize(stream);
+  cudaStreamDestroy(stream);
+  return rc;
+}
+
+// Swept-sphere broadphase: one block per instance i, its threads scan j > i.
+__global__ void c2a_broadphase_kernel(const double *c0, const double *c1, const double *radius, int n, double margin,
+                                      int *pairs, unsigned long long max_pairs, unsigned long long *count)
+{
+  const int i = blockIdx.x;
+  const double ax = c0[3 * i], ay = c0[3 * i + 1], az = c0[3 * i + 2];
+  const double avx = c1[3 * i] - ax, avy = c1[3 * i + 1] - ay, avz = c1[3 * i + 2] - az;
+  const double ri = radius[i];
+  for (int j = i + 1 + threadIdx.x; j < n; j += blockDim.x)
+  {
+    const double px = ax - c0[3 * j], py = ay - c0[3 * j + 1], pz = az - c0[3 * j + 2];
+    const double vx = avx - (c1[3 * j] - c0[3 * j]), vy = avy - (c1[3 * j + 1] - c0[3 * j + 1]), vz = avz - (c1[3 * j + 2] - c0[3 * j + 2]);
+    const double vv = vx * vx + vy * vy + vz * vz;
+    double t = (vv > 0.0) ? -(px * vx + py * vy + pz * vz) / vv : 0.0;
+    t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+    const double qx = px + t * vx, qy = py + t * vy, qz = pz + t * vz;
+    const double reach = ri + radius[j] + margin;
+    if (qx * qx + qy * qy + qz * qz <= reach * reach)
+    {
+      const unsigned long long k = atomicAdd(count, 1ull);
+      if (k < max_pairs) { pairs[2 * k] = i; pairs[2 * k + 1] = j; }
+    }
+  }
+}
+
+int c2a_b200_broadphase(const double *c0, const double *c1, const double *radius, int32_t n, double margin, int32_t device,
+                        int32_t *pairs, int64_t max_pairs, int64_t *n_pairs)
+{
+  if (n < 0 || max_pairs < 0 || !n_pairs || (n > 0 && (!c0 || !c1 || !radius)) || (max_pairs > 0 && !pairs))
+    return fail(C2A_B200_ERR_ARG, "NULL argument");
+  *n_pairs = 0;
+  if (n < 2) return C2A_B200_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  const size_t N = (size_t)n, o_c1 = N * 24, o_r = 2 * N * 24, o_cnt = o_r + N * 8, o_pairs = o_cnt + 8;
+  char *arena = nullptr;
+  CUDA_TRY(cudaMalloc(&arena, o_pairs + (size_t)max_pairs * 8));
+  int rc = C2A_B200_OK;
+  cudaError_t e;
+  if ((e = cudaMemcpy(arena, c0, N * 24, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(arena + o_c1, c1, N * 24, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(arena + o_r, radius, N * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemset(arena + o_cnt, 0, 8)) != cudaSuccess)
+    rc = fail(C2A_B200_ERR_CUDA, cudaGetErrorString(e));
+  if (rc == C2A_B200_OK)
+  {
+    c2a_broadphase_kernel<<<(unsigned)(n - 1), 128>>>((const double *)arena, (const double *)(arena + o_c1), (const double *)(arena + o_r), n,
+                                                      margin, (int *)(arena + o_pairs), (unsigned long long)max_pairs,
+                                                      (unsigned long long *)(arena + o_cnt));
+    g_launches.fetch_add(1);
+    unsigned long long cnt = 0;
+    if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaMemcpy(&cnt, arena + o_cnt, 8, cudaMemcpyDeviceToHost)) != cudaSuccess)
+      rc = fail(C2A_B200_ERR_CUDA, cudaGetErrorString(e));
+    else
+    {
+      *n_pairs = (int64_t)cnt;
+      const size_t w = (size_t)std::min<unsigned long long>(cnt, (unsigned long long)max_pairs);
+      if (w > 0 && (e = cudaMemcpy(pairs, arena + o_pairs, w * 8, cudaMemcpyDeviceToHost)) != cudaSuccess)
+        rc = fail(C2A_B200_ERR_CUDA, cudaGetErrorString(e));
+    }
+  }
+  cudaFree(arena);
+  return rc;
 }
 
 int c2a_b200_solve_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses,

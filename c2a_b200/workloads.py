@@ -83,3 +83,52 @@ def grazing_batch(poses, toc, pose_toc, p1p2, push, seed=0):
     out[:, 12:21] = pose_toc[:, 0:9]
     out[:, 21:24] = pose_toc[:, 9:12] + np.asarray(push, dtype=np.float64).reshape(n, 1) * d
     return np.ascontiguousarray(out)
+
+
+def scene(n_instances, seed, radii, side=None, speed=0.35, max_turn=1.0):
+    """Config 4: ``n_instances`` objects, model k = i % len(radii), at random poses in a cube
+    of edge ``side`` moving with random velocities (|displacement| ~ U(0, speed*side)) and turning by up to
+    ``max_turn`` rad.  ``radii``: max |vertex| per model.  side=None sizes the cube for about 8 swept-sphere
+    neighbours per instance.  Returns dict(model [n], begin [n,12], end [n,12]) with R(9)+T(3) poses."""
+    rng = np.random.default_rng(seed)
+    radii = np.asarray(radii, dtype=np.float64)
+    model = (np.arange(n_instances) % len(radii)).astype(np.int32)
+    if side is None:
+        # expected neighbours ~ n * (4/3) pi (2 r_eff)^3 / side^3 with r_eff inflated by the sweep; solved for 8
+        r_eff = float(np.mean(radii)) * 1.08
+        side = (n_instances * (4.0 / 3.0) * np.pi * (2 * r_eff) ** 3 / 8.0) ** (1.0 / 3.0)
+    T0 = rng.uniform(0.0, side, size=(n_instances, 3))
+    d = rng.normal(size=(n_instances, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    T1 = T0 + d * rng.uniform(0.0, speed * side / n_instances ** (1.0 / 3.0) * 2.0, size=(n_instances, 1))
+    R0 = quat_to_matrix(rng.normal(size=(n_instances, 4)))
+    R1 = _matmul9(R0, axis_angle_to_matrix(rng.normal(size=(n_instances, 3)), rng.uniform(0.05, max_turn, size=n_instances)))
+    return {"model": model, "begin": np.ascontiguousarray(np.concatenate([R0, T0], 1)),
+            "end": np.ascontiguousarray(np.concatenate([R1, T1], 1)), "side": side}
+
+
+def scene_queries(sc, pairs):
+    """Assemble the heterogeneous CCD batch of a scene's candidate pairs: poses [m,48] = trans00, trans01 of
+    instance i and trans10, trans11 of instance j, plus the two model-index arrays."""
+    i, j = pairs[:, 0], pairs[:, 1]
+    poses = np.concatenate([sc["begin"][i], sc["end"][i], sc["begin"][j], sc["end"][j]], 1)
+    return np.ascontiguousarray(poses), sc["model"][i].copy(), sc["model"][j].copy()
+
+
+def broadphase_reference(c0, c1, radius, margin=0.0):
+    """numpy statement of c2a_b200_broadphase (same formula, FP64); returns (pairs sorted, |gap| per pair) where gap
+    is how far inside the reach the pair is -- tests skip pairs whose gap is within rounding of zero."""
+    n = len(radius)
+    out, gaps = [], []
+    v = c1 - c0
+    for i in range(n - 1):
+        p = c0[i] - c0[i + 1:]
+        w = v[i] - v[i + 1:]
+        vv = (w * w).sum(1)
+        t = np.where(vv > 0, -(p * w).sum(1) / np.where(vv > 0, vv, 1.0), 0.0)
+        t = np.clip(t, 0.0, 1.0)
+        qv = p + t[:, None] * w
+        reach = radius[i] + radius[i + 1:] + margin
+        gap = reach - np.sqrt((qv * qv).sum(1))
+        for k in np.nonzero(gap >= -1e-9)[0]:
+            out.append((i, i + 1 + int(k))); gaps.append(float(gap[k]))
+    return np.array(out, dtype=np.int32).reshape(-1, 2), np.array(gaps)

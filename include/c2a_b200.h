@@ -179,6 +179,25 @@ int c2a_b200_solve_batch_device(const c2a_b200_model *a, const c2a_b200_model *b
 int c2a_b200_schedule_order(const c2a_b200_model *a, const c2a_b200_model *b, const double *motions, int64_t n,
                             int32_t *order);
 
+/* Heterogeneous batch: per-query model handles (the reference has no batch API, its
+ * C2A_Solve takes the two C2A_Model* per call, C2A/C2A.h:23-35).  models: [n_models] handles on ONE device;
+ * model_a / model_b: [n] indices into it.  Queries are grouped by (model_a, model_b); each group is one launch of
+ * the batched kernel over its own queries, results land at the query's index.  Otherwise as c2a_b200_solve_batch
+ * (host buffers; the contact pass is not available here). */
+int c2a_b200_solve_pairs(const c2a_b200_model *const *models, int32_t n_models, const int32_t *model_a,
+                         const int32_t *model_b, const double *poses, const int32_t *seed_a, const int32_t *seed_b,
+                         int64_t n, double tol_d, double tol_t, const c2a_b200_results *out);
+
+/* Swept-sphere broadphase for a scene of moving instances (NOT in the reference: config 4 needs a candidate pair
+ * list).  Instance i's model-frame origin moves on a straight line from c0[i] to c1[i] -- which is what
+ * CInterpMotion_Linear does to it (C2A/src/InterpMotion.cpp:516-568) -- and all its vertices stay within
+ * radius[i] of that origin (use max |vertex|, not C2A_Model::radius).  Reports every pair
+ * i < j whose spheres come within `margin` of each other for some t in [0, 1]: conservative for the CCD query.
+ * c0, c1: [n][3]; pairs: [max_pairs][2], unordered; *n_pairs = pairs found (if > max_pairs only max_pairs were
+ * written).  Host buffers, brute force on `device` (n^2/2 sphere tests). */
+int c2a_b200_broadphase(const double *c0, const double *c1, const double *radius, int32_t n, double margin, int32_t device,
+                        int32_t *pairs, int64_t max_pairs, int64_t *n_pairs);
+
 /* Number of kernel launches issued by this library on the calling process so far. */
 int64_t c2a_b200_launch_count(void);
 

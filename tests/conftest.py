@@ -58,6 +58,19 @@ def bvhs(bunny_tris):
 
 
 @pytest.fixture(scope="session")
+def models(bvhs):
+    """Models resident on cuda:0 (GPU tests only), cached per session."""
+    from c2a_b200 import api
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = api.Model(bvhs(name), 0)
+        return cache[name]
+    return get
+
+
+@pytest.fixture(scope="session")
 def bvh_digest():
     with open(os.path.join(GOLDEN, "bvh_digest.json")) as f:
         return json.load(f)

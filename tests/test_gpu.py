@@ -26,17 +26,6 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-@pytest.fixture(scope="module")
-def models(bvhs):
-    cache = {}
-
-    def get(name):
-        if name not in cache:
-            cache[name] = api.Model(bvhs(name), 0)
-        return cache[name]
-    return get
-
-
 def assert_contract(got, ref, tol_t):
     """BASELINE.json's contract, checked explicitly besides the bit-exact comparison."""
     assert (got["status"] == 0).all()

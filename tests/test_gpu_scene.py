@@ -1,0 +1,78 @@
+"""GPU parity of the scene path: swept-sphere broadphase -> heterogeneous batch with
+per-query model handles -> c2a_b200_solve_pairs, against the numpy statement of the broadphase and the oracle port."""
+import numpy as np
+import pytest
+
+import oracle
+from c2a_b200 import api, workloads
+
+pytestmark = pytest.mark.gpu
+FIELDS = (("collisionfree", "collisionfree"), ("num_ca", "numCA"), ("num_bv_tests", "num_bv_tests"),
+          ("num_tri_tests", "num_tri_tests"), ("toc", "toc"), ("distance", "distance"), ("mint", "mint"), ("pose_toc", "pose_toc"))
+
+
+def radii_of(bvhs, names):
+    return np.array([np.linalg.norm(bvhs(n)["tris"].reshape(-1, 3), axis=1).max() for n in names])
+
+
+def test_broadphase_matches_numpy_statement():
+    for n, seed in ((2, 1), (97, 2), (700, 3)):
+        sc = workloads.scene(n, seed, [131.4, 198.0])
+        c0, c1 = sc["begin"][:, 9:], sc["end"][:, 9:]
+        r = np.array([131.4, 198.0])[sc["model"]]
+        ref, gap = workloads.broadphase_reference(c0, c1, r, margin=1.0)
+        got = api.broadphase(c0, c1, r, margin=1.0)
+        sure = {tuple(p) for p, g in zip(ref.tolist(), gap) if g > 1e-9}       # clearly inside the reach
+        maybe = {tuple(p) for p in ref.tolist()}                                # including the rounding band
+        got_s = {tuple(p) for p in got.tolist()}
+        assert sure <= got_s <= maybe
+        assert (got[:, 0] < got[:, 1]).all()
+    # capacity handling: the count is reported even when the buffer is too small
+    few = api.broadphase(c0, c1, r, margin=1.0, max_pairs=5)
+    assert len(few) == 5 and {tuple(p) for p in few.tolist()} <= maybe
+
+
+def test_scene_pairs_match_oracle(models, bvhs):
+    names = ["bunny", "knot_128x16"]
+    radii = radii_of(bvhs, names)
+    sc = workloads.scene(160, 11, radii)
+    pairs = api.broadphase(sc["begin"][:, 9:], sc["end"][:, 9:], radii[sc["model"]])
+    assert len(pairs) > 200
+    poses, ma, mb = workloads.scene_queries(sc, pairs)
+    rng = np.random.default_rng(3)
+    ntri = np.array([bvhs(n)["tris"].shape[0] for n in names])
+    sa = rng.integers(0, ntri[ma]).astype(np.int32)
+    sb = rng.integers(0, ntri[mb]).astype(np.int32)
+    got = api.solve_pairs([models(n) for n in names], ma, mb, poses, sa, sb)
+    assert (got["status"] == 0).all()
+    seen = 0
+    for a in range(2):
+        for b in range(2):
+            g = np.nonzero((ma == a) & (mb == b))[0]
+            if len(g) == 0:
+                continue
+            ref = oracle.port().solve_batch(bvhs(names[a]), bvhs(names[b]), poses[g], sa[g], sb[g], threads=8)
+            for x, y in FIELDS:
+                assert np.array_equal(got[x][g], ref[y]), (names[a], names[b], x)
+            assert np.array_equal(got["last_tri"][g, 0], ref["last_tri_a"]) and np.array_equal(got["last_tri"][g, 1], ref["last_tri_b"])
+            seen += 1
+    assert seen == 4
+    hits = (got["collisionfree"] == 0).sum()
+    assert 0 < hits < len(pairs)  # the broadphase is conservative: some candidates are free, some collide
+
+
+def test_solve_pairs_single_group_equals_solve_batch(models, golden):
+    g = golden("ref_knot_128x16")
+    n = 300
+    m = models("knot_128x16")
+    zeros = np.zeros(n, dtype=np.int32)
+    a = api.solve_pairs([m], zeros, zeros, g["poses"][:n])
+    for x, y in FIELDS:
+        assert np.array_equal(a[x], g[y][:n]), x
+
+
+def test_solve_pairs_argument_errors(models):
+    m = models("knot_128x16")
+    poses = np.zeros((2, 48))
+    with pytest.raises(api.C2AError):
+        api.solve_pairs([m], [0, 1], [0, 0], poses)  # model index out of range

@@ -177,3 +177,25 @@ def test_dropin_header_compiles_standalone(tmp_path):
     out = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-Wall", "-I" + os.path.join(ROOT, "include"), str(src)],
                          capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
+
+
+def test_scene_workload_and_broadphase_statement():
+    """Config 4 plumbing on the CPU: scene generator, query assembly and the numpy broadphase statement."""
+    from c2a_b200 import workloads
+    # two unit spheres passing each other: closest approach 1.0 at t = 0.5
+    c0 = np.array([[-5.0, 0.5, 0.0], [5.0, -0.5, 0.0]]); c1 = np.array([[5.0, 0.5, 0.0], [-5.0, -0.5, 0.0]])
+    p, gap = workloads.broadphase_reference(c0, c1, np.array([0.4, 0.4]))
+    assert len(p) == 0
+    p, gap = workloads.broadphase_reference(c0, c1, np.array([0.5, 0.6]))
+    assert p.tolist() == [[0, 1]] and abs(gap[0] - 0.1) < 1e-12
+    p, _ = workloads.broadphase_reference(c0, c0, np.array([0.5, 0.6]))   # static and 10.05 apart
+    assert len(p) == 0
+    sc = workloads.scene(300, 4, [131.4, 198.0])
+    r = np.array([131.4, 198.0])[sc["model"]]
+    pairs, _ = workloads.broadphase_reference(sc["begin"][:, 9:], sc["end"][:, 9:], r)
+    assert 3.0 < 2.0 * len(pairs) / 300 < 14.0            # "about 8 neighbours"
+    poses, ma, mb = workloads.scene_queries(sc, pairs)
+    assert poses.shape == (len(pairs), 48) and np.array_equal(ma, sc["model"][pairs[:, 0]])
+    assert np.array_equal(poses[:, 24:36], sc["begin"][pairs[:, 1]])
+    R = poses[:, :9].reshape(-1, 3, 3)
+    assert np.allclose(np.einsum("nij,nkj->nik", R, R), np.eye(3), atol=1e-12)
