@@ -294,7 +294,7 @@ void record_from_motion(CInterpMotion *m, double *rec)
   rec[18] = m->m_angVel;
   const Quaternion qs = m->transform_s.Quaternion_();
   for (int i = 0; i < 4; i++) rec[19 + i] = qs[i];
-  rec[23] = 0.0;
+  rec[23] = m->m_toc_delta;  // read by the translation-only branch (ConservD, InterpMotion.cpp:291-298); 0 = tolerance_d
 }
 int seed_index(C2A_Model *o, Tri *t)
 {
@@ -336,7 +336,7 @@ PQP_REAL C2A_QueryTimeOfContact(CInterpMotion *objmotion1, CInterpMotion *objmot
   if (rc != 0 || status != C2A_B200_QUERY_OK)
   {
     if (rc) fprintf(stderr, "c2a_b200: %s\n", c2a_b200_last_error());
-    else fprintf(stderr, "c2a_b200: translation-only query (both angular speeds < 1e-8) is not implemented\n");
+    else fprintf(stderr, "c2a_b200: translation-only query on hierarchies deeper than its traversal stack\n");
     res->numCA = -1;
     return 0;
   }
@@ -344,6 +344,17 @@ PQP_REAL C2A_QueryTimeOfContact(CInterpMotion *objmotion1, CInterpMotion *objmot
   res->toc = toc; res->distance = dist; res->mint = mint; res->numCA = nca;
   res->num_bv_tests = nbv; res->num_tri_tests = ntri;
   for (int i = 0; i < 3; i++) { res->p1[i] = p1p2[i]; res->p2[i] = p1p2[3 + i]; }
+  if (objmotion1->m_angVel < 1e-8 && objmotion2->m_angVel < 1e-8)
+  {
+    // translation-only branch (C2A.cpp:2032-2049): the traversal updates res->last_triA/B instead of the models'
+    // last_tri (:1413-1414) and leaves both motions at the pose of the step bound (:1907-1908); numCA stays 0
+    if (last[0] >= 0) res->last_triA = &o1->tris[last[0]];
+    if (last[1] >= 0) res->last_triB = &o2->tris[last[1]];
+    PQP_REAL Rt[3][3], Tt[3];
+    objmotion1->integrate(mint, Rt, Tt);
+    objmotion2->integrate(mint, Rt, Tt);
+    return toc;
+  }
   // the traversal's side effect on the models (C2A.cpp:1175-1176); the demo feeds it back as the next seeds
   if (last[0] >= 0) o1->last_tri = &o1->tris[last[0]];
   if (last[1] >= 0) o2->last_tri = &o2->tris[last[1]];

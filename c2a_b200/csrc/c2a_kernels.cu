@@ -18,6 +18,7 @@
 #include "../../include/c2a_b200.h"
 #include "c2a_solve.cuh"
 #include "c2a_contact.cuh"
+#include "c2a_translation.cuh"
 
 namespace c2a {
 
@@ -78,7 +79,7 @@ static void motion_record_from_pose(const double *pose, double *rec)
     rec[15] = tangent[0] * inv; rec[16] = tangent[1] * inv; rec[17] = tangent[2] * inv;
   }
   rec[19] = qs[0]; rec[20] = qs[1]; rec[21] = qs[2]; rec[22] = qs[3];
-  rec[23] = 0.0;
+  rec[23] = 0.0;  // CInterpMotion::m_toc_delta; 0 = the batch's tol_d (what C2A_Solve sets, C2A.cpp:2384-2388)
 }
 
 // Claim order for the persistent kernel: queries expected to run long first, so that their sequential
@@ -312,6 +313,23 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   cudaError_t le = cudaGetLastError();
   cudaFreeAsync(stacks, stream);
   if (le != cudaSuccess) return fail(C2A_B200_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(le));
+  if (!step_in)
+  {
+    // translation-only queries (both angular speeds < 1e-8) were skipped by the kernel above: the reference
+    // switches to a different traversal for them (C2A.cpp:2391-2395).  A thread per query; threads whose
+    // query has rotation return at once, so a batch without such queries pays one near-empty launch.
+    TransArgs t;
+    t.A = args.A; t.B = args.B; t.motions = poses; t.seedA = sa; t.seedB = sb; t.n = n; t.tol_d = tol_d;
+    t.out = *out; t.order = order;
+    t.too_deep = (a->depth + b->depth + 2 > TRANS_STACK) ? 1 : 0;
+    long long tb = (long long)sms * 8;
+    const long long tneed = (n + 127) / 128;
+    if (tb > tneed) tb = tneed;
+    c2a_translation_kernel<<<(unsigned)tb, 128, 0, stream>>>(t);
+    g_launches.fetch_add(1);
+    le = cudaGetLastError();
+    if (le != cudaSuccess) return fail(C2A_B200_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(le));
+  }
   return C2A_B200_OK;
 }
 

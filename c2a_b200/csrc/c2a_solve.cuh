@@ -684,8 +684,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
             const double w1 = __ldg(rec + 18), w2 = __ldg(rec + MOTION_DOUBLES + 18);
             if (!args.step_in && w1 < 1e-8 && w2 < 1e-8)
             {
-              // translation-only branch of the reference (C2A.cpp:2391-2395): not implemented
-              if (args.out.status) args.out.status[q] = C2A_B200_QUERY_TRANSLATION_ONLY;
+              // translation-only branch of the reference (C2A.cpp:2391-2395): solved by c2a_translation_kernel,
+              // which the host launches over the same batch right after this kernel
               if (args.ctl) atomicAdd(args.ctl + 2, 1ull);
               q = -1;  // stay in ADVANCE: claim another one next round
             }

@@ -49,6 +49,26 @@ def approach_batch(n, seed, radius=BUNNY_RADIUS, max_turn=2.0):
     return np.ascontiguousarray(np.concatenate([R0, T0, R1, T1, R2, Z, R2, Z], 1))
 
 
+def translation_batch(n, seed, radius=BUNNY_RADIUS, move_b=False):
+    """Pure translations (both angular speeds exactly 0): the reference's translation-only branch
+    (/root/reference/C2A/src/C2A.cpp:2391-2395, :1362-1521).  Object 1 keeps a random rotation and moves
+    from 300 units out (scaled) along u to s*u + a lateral offset, so hits, grazes and misses all occur;
+    object 2 keeps a random rotation and is static, or (``move_b``) drifts by up to 40 units."""
+    rng = np.random.default_rng(seed)
+    k = radius / BUNNY_RADIUS
+    u = rng.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    T0 = 300.0 * k * u
+    lat = rng.normal(size=(n, 3)); lat -= (lat * u).sum(1, keepdims=True) * u
+    lat /= np.linalg.norm(lat, axis=1, keepdims=True)
+    s = rng.uniform(-300.0, 200.0, size=n) * k
+    T1 = s[:, None] * u + lat * rng.uniform(0.0, 220.0, size=(n, 1)) * k
+    R1 = quat_to_matrix(rng.normal(size=(n, 4)))
+    R2 = quat_to_matrix(rng.normal(size=(n, 4)))
+    Z = np.zeros((n, 3))
+    Z1 = rng.normal(size=(n, 3)) * (40.0 * k / 3.0) if move_b else Z
+    return np.ascontiguousarray(np.concatenate([R1, T0, R1, T1, R2, Z, R2, Z1], 1))
+
+
 def demo_batch(R1f, T1f, R2f, T2f):
     """Config 1: the 303 queries ``cb_display`` builds from torusknot1.ani / torusknot2.ani
     (/root/reference/CCDDemo/mainTorusknot.cpp:216-266): object 1 moves from frame step1 to step2 of

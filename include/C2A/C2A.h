@@ -14,8 +14,10 @@
 // Deliberate differences (each documented in DESIGN.md):
 //   * nothing prints to stdout (the reference prints from EndModel and from every C2A_Solve call);
 //   * contact features: FeatureID entries the reference leaves uninitialised are -1 here;
-//   * the translation-only branch (both angular speeds < 1e-8, C2A/src/C2A.cpp:2391-2395) is not
-//     implemented yet: such a query returns CollisionNotFound with dres.numCA = -1 instead of a result;
+//   * the translation-only branch (both angular speeds < 1e-8, C2A/src/C2A.cpp:2391-2395) is chosen per
+//     query from the two motions' m_angVel (the reference reads a global that C2A_Solve sets); where the
+//     reference reads uninitialised memory in that branch (see c2a_b200/csrc/c2a_translation.cuh) the
+//     behaviour of its object code under any finite non-zero garbage is reproduced; res->p1/p2 stay zero;
 //   * degenerate rotations do not exit(0) (C2A/LinearMath.h:768).
 #ifndef C2A_B200_DROPIN_C2A_H
 #define C2A_B200_DROPIN_C2A_H

@@ -29,9 +29,11 @@ extern "C" {
 
 /* per-query status written to c2a_b200_results.status */
 #define C2A_B200_QUERY_OK 0
-#define C2A_B200_QUERY_TRANSLATION_ONLY 1 /* both angular speeds < 1e-8: the reference switches to its
-                                             translation-only branch (C2A/src/C2A.cpp:2391-2395), which
-                                             this build does not implement yet; outputs are not written */
+#define C2A_B200_QUERY_TRANSLATION_ONLY 1 /* a translation-only query (both angular speeds < 1e-8, the reference's
+                                             branch at C2A/src/C2A.cpp:2391-2395) on hierarchies with
+                                             depth(A)+depth(B)+2 > 96, deeper than that branch's traversal stack:
+                                             reported, outputs not written.  Otherwise such queries are solved
+                                             like any other (status 0; they are the ones with num_ca == 0) */
 
 /* Flattened RSS bounding-volume hierarchy of one C2A_Model after EndModel(): the hot fields of
  * C2A_BV (C2A/C2A_BV.h:33-77 on top of PQP's BV) and the triangles (PQP Tri p1,p2,p3) in the
@@ -120,12 +122,15 @@ int c2a_b200_model_free(c2a_b200_model *m);
 int c2a_b200_model_info(const c2a_b200_model *m, int32_t *device, int32_t *n_nodes, int32_t *n_tris,
                         int32_t *depth);
 
-/* Batched C2A_Solve (C2A/src/C2A.cpp:2315-2444, without its contact pass) over n independent
+/* Batched C2A_Solve (C2A/src/C2A.cpp:2315-2444; its contact pass runs when num_contact / contacts is set) over n independent
  * queries on the models' device.  poses: [n][48] = trans00, trans01, trans10, trans11, each R (9,
  * row-major) + T (3) (the four Transform* of C2A_Solve).  seed_a / seed_b: [n] triangle indices
  * standing in for res->last_triA / last_triB (C2A/src/C2A.cpp:1816-1817; NULL = triangle 0, the
  * state after EndModel, C2A/src/C2A_PQP.cpp:401).  tol_d / tol_t: C2A_Solve hard-codes 1e-4 for
  * both (C2A/src/C2A.cpp:2384-2385); C2A_QueryTimeOfContact takes them as arguments.
+ * Queries whose two angular speeds are both < 1e-8 take the reference's translation-only branch
+ * (C2A/src/C2A.cpp:2391-2395, :1362-1521; CInterpMotion::m_toc_delta = tol_d as C2A_Solve sets it): toc = the
+ * step bound of its single traversal, collisionfree = (toc >= 1), num_ca = 0, last_tri = res->last_triA/B.
  * Host buffers; host<->device copies are inside the call. */
 int c2a_b200_solve_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses,
                          const int32_t *seed_a, const int32_t *seed_b, int64_t n, double tol_d, double tol_t,
@@ -140,7 +145,7 @@ int c2a_b200_contacts_batch(const c2a_b200_model *a, const c2a_b200_model *b, co
 /* Host half of the motion model: what constructing the two CInterpMotion_Linear objects does in
  * C2A_Solve (C2A/src/C2A.cpp:2378-2379 -> C2A/src/InterpMotion.cpp:148-168, 486-491, 228-270).
  * poses [n][48] -> motions [n][C2A_B200_MOTION_DOUBLES]: per object R0(9) T0(3) cv(3) axis(3) angVel
- * qs(4) pad.  It stays on the host because LinearAngularVelocity calls acos(): the reference's
+ * qs(4) m_toc_delta (0 = the batch's tol_d; only object 1's is read, by the translation-only branch).  It stays on the host because LinearAngularVelocity calls acos(): the reference's
  * constants are whatever the host libm returns, and the device consumes exactly those.
  * n_threads <= 0: all host cores. */
 #define C2A_B200_MOTION_DOUBLES 48

@@ -739,6 +739,206 @@ void toc_step(Step &st, int numCA, int seedA, int seedB)
   st.mint = 1;
   toc_recurse(st, R, T, 0, 0);
 }
+// ---- translation-only branch (both angular speeds < 1e-8, C2A.cpp:2391-2395) -------------------
+// Only objmotion1's velocity enters the inner advancement (the reference calls objmotion1->CAonRSS /
+// CAonNonAdjacentTriangles and never reads objmotion2's cv there): reproduced, not fixed.
+//
+// Undefined behaviour in the reference, and what this restatement does about it: C2ARectDist leaves S
+// untouched when no edge pair is accepted and both face separations are negative (the rectangles cross,
+// C2A_RectDist.h:887-928), and CAonRSS then reads its uninitialised local S (InterpMotion.cpp:579-592).
+// With any finite non-zero garbage the outcome is the same -- d = 0, tocf = -0.1*delta/path_max < 0, the
+// call returns true with a negative step, and the caller descends iff 0 < res->distance -- so S is
+// preset to (1,0,0) here.  (Garbage that normalises to NaN would make the reference skip that subtree.)
+constexpr double SECURITY_RATIO = 0.1;  // GMP_CCD_SECURITY_DISTANCE_RATIO, InterpMotion.cpp:289
+
+// CInterpMotion_Linear::CAonRSS, C2A/src/InterpMotion.cpp:570-655 (bValid_C_clo is always true,
+// C2A_RectDist.h:931, so the centre-of-mass branch :607-621 is dead).
+bool ca_on_rss(const orc_motion *m1, double delta, const double r1[9], const double R[9], const double T[3],
+               const orc_bvh *A, int a, const orc_bvh *B, int b, double *mint, double *distance)
+{
+  double S[3] = {1, 0, 0}, temp1[3], temp2[3], Vel[3];
+  double d = bv_distance(R, T, A, a, B, b, S);
+  m_v(temp1, &A->R_loc[9 * a], S);
+  m_v(S, r1, temp1);
+  const double *cvc = m1->cv;
+  mt_v(temp1, r1, cvc);
+  mt_v(Vel, &A->R_loc[9 * a], temp1);
+  double tocf = (d - SECURITY_RATIO * delta) / orc_motion_bound_leaf(m1, A->ang_radius[a], S);
+  double total_toc = tocf;
+  int nIters = 1;
+  while ((d >= delta) && (total_toc <= mint[0]) && (nIters < 50))
+  {
+    v_madd(temp2, T, Vel, -total_toc);
+    d = bv_distance(R, temp2, A, a, B, b, S);
+    if (d == 0) break;
+    m_v(temp1, &A->R_loc[9 * a], S);
+    m_v(S, r1, temp1);
+    tocf = (d - SECURITY_RATIO * delta) / orc_motion_bound_leaf(m1, A->ang_radius[a], S);
+    nIters++;
+    if (tocf < delta) break;
+    total_toc += tocf;
+  }
+  if (total_toc < 1.0)
+  {
+    mint[0] = total_toc;
+    distance[0] = (total_toc - delta) * v_len(cvc);
+    if (distance[0] < 0) distance[0] = 0;
+    return true;
+  }
+  return false;
+}
+
+// CInterpMotion_Linear::CAonNonAdjacentTriangles, C2A/src/InterpMotion.cpp:657-743
+bool ca_on_triangles(const orc_motion *m1, double delta, const double r1[9], const double triA[9],
+                     const double triB[9], double *mint, double *distance)
+{
+  double p[3], q[3], triA_t[9], Vel[3], n[3];
+  const double *cvc = m1->cv;
+  mt_v(Vel, r1, cvc);
+  double d = orc_tri_dist(p, q, triA, triB);
+  v_sub(n, q, p);
+  v_normalize(n);
+  double u = v_dot(Vel, n);
+  if (u <= 0) u = 1e-30;
+  if (d == 0) { mint[0] = 0.0; distance[0] = 0.0; return true; }
+  double dt = (d - SECURITY_RATIO * delta) / u;
+  int nIters = 1;
+  if (dt >= mint[0]) return false;
+  double total_toc = dt;
+  while ((d > delta) && (total_toc <= mint[0]) && (nIters < 50))
+  {
+    for (int i = 0; i < 3; i++) v_madd(&triA_t[3 * i], &triA[3 * i], Vel, total_toc);
+    d = orc_tri_dist(p, q, triA_t, triB);
+    if (d == 0.0) break;
+    v_sub(n, q, p);
+    v_normalize(n);
+    u = v_dot(Vel, n);
+    if (u <= 0) u = 1e-30;
+    double tofc = (d - SECURITY_RATIO * delta) / u;
+    nIters++;
+    if (tofc < delta) break;
+    total_toc += tofc;
+  }
+  if (total_toc <= mint[0] && total_toc >= 0.0)
+  {
+    mint[0] = total_toc;
+    distance[0] = (total_toc)*v_len(cvc) + delta;
+    return true;
+  }
+  return false;
+}
+
+struct TStep
+{
+  const orc_bvh *A, *B;
+  const orc_motion *m1;
+  double delta;
+  double Rrel[9], Trel[3];
+  double distance, mint;
+  int num_bv_tests, num_tri_tests;
+  int last_a, last_b;  // res->last_triA / last_triB
+};
+
+// TOCStepRecurse_Dis_Translation, C2A/src/C2A.cpp:1362-1521 (abs_err = rel_err = 0, :1902-1903)
+void toc_recurse_translation(TStep &st, const double R[9], const double T[3], int b1, int b2)
+{
+  const orc_bvh *A = st.A, *B = st.B;
+  const int l1 = A->first_child[b1] < 0, l2 = B->first_child[b2] < 0;
+  const double *r1 = st.m1->Rc;
+  if (l1 && l2)
+  {
+    const int ta = -A->first_child[b1] - 1, tb = -B->first_child[b2] - 1;
+    const double *t1 = &A->tris[9 * ta], *t2 = &B->tris[9 * tb];
+    double tri2[9];
+    m_v_p(&tri2[0], st.Rrel, &t2[0], st.Trel); m_v_p(&tri2[3], st.Rrel, &t2[3], st.Trel); m_v_p(&tri2[6], st.Rrel, &t2[6], st.Trel);
+    if (ca_on_triangles(st.m1, st.delta, r1, t1, tri2, &st.mint, &st.distance)) { st.last_a = ta; st.last_b = tb; }
+    st.num_tri_tests++;
+    return;
+  }
+  int a1, a2, c1, c2;
+  double R1[9], T1[3], R2[9], T2[3], Tt[3];
+  double sz1 = bv_size(A, b1), sz2 = bv_size(B, b2);
+  if (l2 || (!l1 && (sz1 > sz2)))
+  {
+    a1 = A->first_child[b1]; a2 = b2; c1 = a1 + 1; c2 = b2;
+    mt_m(R1, &A->R[9 * a1], R); v_sub(Tt, T, &A->Tr[3 * a1]); mt_v(T1, &A->R[9 * a1], Tt);
+    mt_m(R2, &A->R[9 * c1], R); v_sub(Tt, T, &A->Tr[3 * c1]); mt_v(T2, &A->R[9 * c1], Tt);
+  }
+  else
+  {
+    a1 = b1; a2 = B->first_child[b2]; c1 = b1; c2 = a2 + 1;
+    m_m(R1, R, &B->R[9 * a2]); m_v_p(T1, R, &B->Tr[3 * a2], T);
+    m_m(R2, R, &B->R[9 * c2]); m_v_p(T2, R, &B->Tr[3 * c2], T);
+  }
+  double d1 = 1e+30, d2 = 1e+30, minta = st.mint, mintc = st.mint;
+  ca_on_rss(st.m1, st.delta, r1, R1, T1, A, a1, B, a2, &minta, &d1);
+  ca_on_rss(st.m1, st.delta, r1, R2, T2, A, c1, B, c2, &mintc, &d2);
+  st.num_bv_tests += 2;
+#define DESCEND_T(mt, d) ((mt) < st.mint && (((d) < (st.distance - 0.0)) || ((d) * (1 + 0.0) < st.distance)))
+  if (d2 < d1)
+  {
+    if (DESCEND_T(mintc, d2)) toc_recurse_translation(st, R2, T2, c1, c2);
+    if (DESCEND_T(minta, d1)) toc_recurse_translation(st, R1, T1, a1, a2);
+  }
+  else
+  {
+    if (DESCEND_T(minta, d1)) toc_recurse_translation(st, R1, T1, a1, a2);
+    if (DESCEND_T(mintc, d2)) toc_recurse_translation(st, R2, T2, c1, c2);
+  }
+#undef DESCEND_T
+}
+
+// The translation-only path of C2A_TimeOfContactStep (C2A.cpp:1818-1852, :1900-1917) and of
+// C2A_QueryTimeOfContact (:2032-2049), with the pose outputs of C2A_Solve (:2411-2429).
+void solve_translation(const orc_bvh *A, const orc_bvh *B, orc_motion &m1, orc_motion &m2, int seedA, int seedB,
+                       double delta, orc_result *out)
+{
+  TStep st;
+  st.A = A; st.B = B; st.m1 = &m1; st.delta = delta;
+  st.num_bv_tests = 0; st.num_tri_tests = 0; st.last_a = seedA; st.last_b = seedB;
+  double Tt[3], Rt[9], R[9], T[3];
+  mt_m(st.Rrel, m1.Rc, m2.Rc);
+  v_sub(Tt, m2.Tc, m1.Tc);
+  mt_v(st.Trel, m1.Rc, Tt);
+  m_m(Rt, st.Rrel, &B->R[0]);
+  mt_m(R, &A->R[0], Rt);
+  m_v_p(Tt, st.Rrel, &B->Tr[0], st.Trel);
+  v_sub(Tt, Tt, &A->Tr[0]);
+  mt_v(T, &A->R[0], Tt);
+
+  const double *t1 = &A->tris[9 * seedA], *t2 = &B->tris[9 * seedB];
+  double tri2[9], mint = 1.0, dTri = 0;
+  m_v_p(&tri2[0], st.Rrel, &t2[0], st.Trel); m_v_p(&tri2[3], st.Rrel, &t2[3], st.Trel); m_v_p(&tri2[6], st.Rrel, &t2[6], st.Trel);
+  if (ca_on_triangles(&m1, delta, m1.Rc, t1, tri2, &mint, &dTri)) { st.mint = mint; st.distance = dTri; }
+  else { st.mint = 1.0; st.distance = 1e+30; }
+  toc_recurse_translation(st, R, T, 0, 0);
+
+  // :1907-1916: distance of the last improving triangle pair at the pose of the step bound
+  orc_motion_integrate(&m1, st.mint, 0);
+  orc_motion_integrate(&m2, st.mint, 0);
+  double Rrel[9], Trel[3], p[3], q[3];
+  mt_m(Rrel, m1.Rc, m2.Rc);
+  v_sub(Tt, m2.Tc, m1.Tc);
+  mt_v(Trel, m1.Rc, Tt);
+  st.distance = orc_tri_distance(Rrel, Trel, &A->tris[9 * st.last_a], &B->tris[9 * st.last_b], p, q);
+
+  out->toc = st.mint;
+  out->collisionfree = (st.mint >= 1.0) ? 1 : 0;
+  out->numCA = 0;
+  out->num_bv_tests = st.num_bv_tests;
+  out->num_tri_tests = st.num_tri_tests;
+  out->distance = st.distance;
+  out->mint = st.mint;
+  out->last_tri_a = st.last_a; out->last_tri_b = st.last_b;
+  // res->p1 / p2 are copied from never-written locals in the reference (C2A.cpp:1392,1411-1412): left zero
+  if (!out->collisionfree)
+  {
+    orc_motion_integrate(&m1, out->toc, 0);
+    orc_motion_integrate(&m2, out->toc, 0);
+    memcpy(&out->pose_toc[0], m1.Rc, sizeof(double) * 9); memcpy(&out->pose_toc[9], m1.Tc, sizeof(double) * 3);
+    memcpy(&out->pose_toc[12], m2.Rc, sizeof(double) * 9); memcpy(&out->pose_toc[21], m2.Tc, sizeof(double) * 3);
+  }
+}
 }  // namespace
 
 // C2A_Solve (C2A/src/C2A.cpp:2315-2444) up to and including the pose outputs,
@@ -753,9 +953,8 @@ extern "C" void orc_solve(const orc_bvh *A, const orc_bvh *B, const double poses
   memset(out, 0, sizeof(*out));
   if (m1.ang_vel < 1e-8 && m2.ang_vel < 1e-8)
   {
-    // translation-only branch (C2A.cpp:2391-2395, :1362-1521) -- SURVEY.md section 8f rank 2, not restated yet
-    out->collisionfree = -1;
-    out->last_tri_a = out->last_tri_b = -1;
+    // translation-only branch (C2A.cpp:2391-2395, :1362-1521); m_toc_delta = d_delta (:2387-2388)
+    solve_translation(A, B, m1, m2, seedA, seedB, tol_d, out);
     return;
   }
 

@@ -107,6 +107,12 @@ void query_toc(C2A_Model *A, C2A_Model *B, const double *poses, int seedA, int s
   C2A_QueryTimeOfContact(&motion1, &motion2, &dres, A, B, tol_d, tol_t, 0);
   fill_common(o, dres);
   if (allow_translation) fill_last_tri(o, A, B);
+  if (translation)
+  {
+    // the translation-only traversal updates res->last_triA/B instead of o->last_tri (C2A.cpp:1413-1414)
+    o->last_tri_a = (int)((C2A_Tri *)dres.last_triA - (C2A_Tri *)A->tris);
+    o->last_tri_b = (int)((C2A_Tri *)dres.last_triB - (C2A_Tri *)B->tris);
+  }
   if (!dres.collisionfree)
   {
     PQP_REAL qua[7];

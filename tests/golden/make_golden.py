@@ -6,6 +6,7 @@ Run in the container that has /root/reference:   python tests/golden/make_golden
 Outputs (all consumed by tests/ and bench.py; nothing under /root/reference is read at test time):
   bunny_mesh.npz        verts float64 [34834,3], vidx int32 [69664,3] parsed from tri_models/bunny_noholes.tri
   demo_poses.npy        the 303 queries of the CCDDemo (config 1), from models/torusknot{1,2}.ani
+  ref_translation_*.npz the same for pure translations (the reference's translation-only branch)
   ref_<case>.npz        per-query results of the reference (collisionfree, toc, distance, numCA, counters,
                         p1p2, pose_toc) + the poses / tolerances that produced them
   bvh_digest.json       sha256 of every flattened BVH array built by the reference's builder
@@ -64,9 +65,41 @@ def carry_fixture(R, name, mA, mB, poses):
                   "last_tri": np.stack([rows["last_tri_a"], rows["last_tri_b"]], 1)})
 
 
+def translation_fixtures(R, bunny):
+    """Translation-only branch (both angular speeds < 1e-8, C2A.cpp:2391-2395, :1362-1521): pure translations,
+    object 2 static or drifting, run one at a time (the reference keeps the branch flag in a global)."""
+    tris, vi = meshes.torus_knot(128, 16)
+    knot = R.model(tris, vi)
+    poses = np.concatenate([workloads.translation_batch(300, 20260011, radius=workloads.KNOT_RADIUS),
+                            workloads.translation_batch(300, 20260012, radius=workloads.KNOT_RADIUS, move_b=True)])
+    res = R.solve_batch(knot, knot, poses, threads=1)
+    assert (res["numCA"] == 0).all()
+    # the full, unmodified C2A_Solve agrees with the TOC-only wrapper and gives the contact counts
+    full, ncont = R.solve_batch(knot, knot, poses[:120], mode=1)
+    for k in ("collisionfree", "numCA", "num_bv_tests", "num_tri_tests", "toc", "distance", "pose_toc"):
+        assert np.array_equal(full[k], res[k][:120]), k
+    save_results("ref_translation_knot_128x16.npz", res, poses, 1e-4, 1e-4,
+                 {"last_tri": np.stack([res["last_tri_a"], res["last_tri_b"]], 1), "num_contact": ncont})
+    # heterogeneous pair, explicit seeds, non-default tolerances (m_toc_delta = tolerance_d)
+    tris, vi = meshes.torus_knot(512, 32)
+    knot512 = R.model(tris, vi)
+    rng = np.random.default_rng(8)
+    n = 160
+    sa = rng.integers(0, bunny.n_tris, n).astype(np.int32)
+    sb = rng.integers(0, knot512.n_tris, n).astype(np.int32)
+    poses = workloads.translation_batch(n, 20260013, radius=workloads.KNOT_RADIUS, move_b=True)
+    res = R.solve_batch(bunny, knot512, poses, seedA=sa, seedB=sb, tol_d=1e-3, tol_t=1e-5, threads=1)
+    save_results("ref_translation_bunny_vs_knot_seeded.npz", res, poses, 1e-3, 1e-5,
+                 {"seed_a": sa, "seed_b": sb, "last_tri": np.stack([res["last_tri_a"], res["last_tri_b"]], 1)})
+
+
 def main():
     oracle.build_oracle()
     R = oracle.ref()
+    if "--only-translation" in sys.argv:
+        m = np.load(os.path.join(HERE, "bunny_mesh.npz"))
+        translation_fixtures(R, R.model(m["verts"][m["vidx"]].reshape(-1, 9).copy(), m["vidx"]))
+        return
 
     # --- meshes
     with open(os.path.join(REF, "tri_models/bunny_noholes.tri")) as f:
@@ -151,6 +184,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ref_contacts_knot_128x16.npz"), num_contact=np.array(counts, np.int32),
                         **{k: allr[k] for k in allr.dtype.names})
     print(f"ref_contacts_knot_128x16.npz: {nq} queries, {int(np.sum(counts))} contacts, max {int(np.max(counts))}")
+
+    translation_fixtures(R, bunny)
 
     with open(os.path.join(HERE, "bvh_digest.json"), "w") as f:
         json.dump(digests, f, indent=1, sort_keys=True)

@@ -13,7 +13,7 @@ import pytest
 import oracle
 from c2a_b200 import api, meshes, workloads
 from conftest import GOLDEN_CASES
-from test_oracle import rect_cases, tri_cases
+from test_oracle import rect_cases, tri_cases, TRANSLATION_CASES
 
 pytestmark = pytest.mark.gpu
 
@@ -120,6 +120,52 @@ def test_golden_bit_exact(case, ma, mb, golden, models):
         assert np.array_equal(got["last_tri"], g["last_tri"])
 
 
+@pytest.mark.parametrize("case,ma,mb", TRANSLATION_CASES)
+def test_translation_golden_bit_exact(case, ma, mb, golden, models):
+    """The translation-only branch (C2A.cpp:2391-2395, :1362-1521; c2a_translation_kernel) against the reference's
+    object code on pure translations: every field bit-exact, incl. the res->last_triA/B the traversal leaves."""
+    g = golden(case)
+    tol_d, tol_t = float(g["tol_d"]), float(g["tol_t"])
+    got = api.solve_batch(models(ma), models(mb), g["poses"], g.get("seed_a"), g.get("seed_b"), tol_d, tol_t,
+                          max_contacts=8 if "num_contact" in g else 0)
+    assert_contract(got, g, tol_t)
+    for a, b in FIELDS:
+        assert np.array_equal(got[a], g[b]), (case, a, int((got[a] != g[b]).sum()))
+    assert np.array_equal(got["last_tri"], g["last_tri"])
+    assert (got["p1p2"] == 0).all()
+    if "num_contact" in g:  # the full, unmodified C2A_Solve's number_of_contact on the first queries
+        k = len(g["num_contact"])
+        assert np.array_equal(got["num_contact"][:k], g["num_contact"])
+
+
+def test_translation_mixed_batch_and_device_entry(models, bvhs):
+    """Rotational and translation-only queries interleaved in one batch, through the host entry and the
+    device-resident entry (claim order given), vs the oracle port."""
+    import torch
+    poses = np.concatenate([workloads.translation_batch(150, 41, radius=workloads.KNOT_RADIUS, move_b=True),
+                            workloads.approach_batch(150, 42, radius=workloads.KNOT_RADIUS)])
+    poses = np.ascontiguousarray(poses[np.random.default_rng(1).permutation(len(poses))])
+    n = len(poses)
+    ref = oracle.port().solve_batch(bvhs("knot_128x16"), bvhs("knot_128x16"), poses, threads=8)
+    m = models("knot_128x16")
+    got = api.solve_batch(m, m, poses)
+    assert_contract(got, ref, 1e-4)
+    for a, b in FIELDS:
+        assert np.array_equal(got[a], ref[b]), a
+    assert (ref["numCA"] == 0).sum() == 150
+    mot = torch.from_numpy(api.motions_from_poses(poses)).cuda()
+    out = {"status": torch.full((n,), -7, dtype=torch.int32, device="cuda"),
+           "collisionfree": torch.zeros(n, dtype=torch.int32, device="cuda"),
+           "num_ca": torch.full((n,), -1, dtype=torch.int32, device="cuda"),
+           "toc": torch.zeros(n, dtype=torch.float64, device="cuda"),
+           "distance": torch.zeros(n, dtype=torch.float64, device="cuda")}
+    api.solve_batch_device(m, m, mot.data_ptr(), n, {k: v.data_ptr() for k, v in out.items()},
+                           stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for k, v in out.items():
+        assert np.array_equal(v.cpu().numpy(), got[k]), k
+
+
 def test_fresh_batch_against_oracle_port(models, bvhs):
     """Inputs that are in no fixture: GPU vs the oracle port run here, bit-exact."""
     poses = workloads.approach_batch(300, 777, radius=workloads.KNOT_RADIUS, max_turn=3.1)
@@ -196,11 +242,11 @@ def test_edge_cases(models):
         a = api.solve_batch(m, m, p)
         b = api.solve_batch(m, m, p[::-1].copy())
         assert np.array_equal(a["toc"], b["toc"][::-1]) and np.array_equal(a["num_bv_tests"], b["num_bv_tests"][::-1])
-    # pure translation: the reference switches branch (C2A.cpp:2391-2395); reported, not silently mis-solved
+    # pure translation inside a rotational batch: the reference switches branch (C2A.cpp:2391-2395); solved (num_ca == 0)
     p = workloads.approach_batch(4, 2, radius=workloads.KNOT_RADIUS)
     p[1, 12:21] = p[1, 0:9]
     got = api.solve_batch(m, m, p)
-    assert list(got["status"]) == [0, 1, 0, 0]
+    assert list(got["status"]) == [0, 0, 0, 0] and list(got["num_ca"] == 0) == [False, True, False, False]
     # bad seeds / mismatched devices are argument errors, not crashes
     with pytest.raises(api.C2AError):
         api._check(api.lib().c2a_b200_solve_batch(m.h, None, None, None, None, C.c_int64(1), C.c_double(1e-4), C.c_double(1e-4), None))

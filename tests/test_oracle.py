@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import oracle
+from c2a_b200 import workloads
 from conftest import GOLDEN_CASES
 
 needs_ref = pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
@@ -131,6 +132,44 @@ def test_port_matches_golden(case, ma, mb, golden, bvhs):
         nxt_a = np.where(lt[:-1, 0] >= 0, lt[:-1, 0], g["seed_a"][sl][:-1])
         nxt_b = np.where(lt[:-1, 1] >= 0, lt[:-1, 1], g["seed_b"][sl][:-1])
         assert np.array_equal(nxt_a, g["seed_a"][sl][1:]) and np.array_equal(nxt_b, g["seed_b"][sl][1:])
+
+
+TRANSLATION_CASES = [("ref_translation_knot_128x16", "knot_128x16", "knot_128x16"),
+                     ("ref_translation_bunny_vs_knot_seeded", "bunny", "knot_512x32")]
+
+
+@pytest.mark.parametrize("case,ma,mb", TRANSLATION_CASES)
+def test_port_translation_matches_golden(case, ma, mb, golden, bvhs):
+    """Translation-only branch (C2A.cpp:2391-2395, :1362-1521): the port reproduces the reference's object code
+    bit for bit on pure translations -- including where that code reads an uninitialised direction (see
+    oracle/c2a_oracle.cpp: any finite non-zero garbage gives the same outcome)."""
+    g = golden(case)
+    out = oracle.port().solve_batch(bvhs(ma), bvhs(mb), g["poses"], g["seed_a"] if "seed_a" in g else None,
+                                    g["seed_b"] if "seed_b" in g else None, float(g["tol_d"]), float(g["tol_t"]), threads=8)
+    for k in ("collisionfree", "numCA", "num_bv_tests", "num_tri_tests", "toc", "distance", "mint", "pose_toc"):
+        assert np.array_equal(out[k], g[k]), (case, k)
+    assert np.array_equal(np.stack([out["last_tri_a"], out["last_tri_b"]], 1), g["last_tri"])
+    # the branch's semantics: one traversal, no outer CA loop; the verdict is toc < 1; free queries keep toc = mint >= 1
+    assert (g["numCA"] == 0).all() and np.array_equal(g["collisionfree"] == 1, g["toc"] >= 1.0)
+    assert (g["collisionfree"] == 1).sum() > 20 and (g["collisionfree"] == 0).sum() > 20
+
+
+@needs_ref
+def test_port_translation_matches_ref_fresh_and_mixed(bvhs):
+    """Inputs in no fixture, and a batch mixing rotational and translation-only queries (the reference's threaded
+    wrapper defers the latter to a serial phase because the branch flag is a global, C2A.cpp:33)."""
+    from c2a_b200 import meshes
+    tris, vi = meshes.torus_knot(128, 16)
+    R = oracle.ref()
+    m = R.model(tris, vi)
+    poses = np.concatenate([workloads.translation_batch(60, 5, radius=workloads.KNOT_RADIUS, move_b=True),
+                            workloads.approach_batch(60, 6, radius=workloads.KNOT_RADIUS)])
+    poses = np.ascontiguousarray(poses[np.random.default_rng(0).permutation(len(poses))])
+    ref = R.solve_batch(m, m, poses, threads=4)
+    out = oracle.port().solve_batch(bvhs("knot_128x16"), bvhs("knot_128x16"), poses, threads=4)
+    for k in ("collisionfree", "numCA", "num_bv_tests", "num_tri_tests", "toc", "distance", "mint", "pose_toc"):
+        assert np.array_equal(out[k], ref[k]), k
+    assert (ref["numCA"] == 0).sum() == 60
 
 
 def test_golden_fixtures_are_sane(golden):
