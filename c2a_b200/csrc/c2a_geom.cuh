@@ -394,43 +394,63 @@ C2A_DEV bool face_vertex_case(const double F[9], const double Fv[9], const doubl
   return true;
 }
 
-// PQP TriDist (in-tree copy C2A/src/C2A.cpp:165-405 without the contact-feature writes).
-C2A_DEV double tri_dist(double P[3], double Q[3], const double S[9], const double T[9])
+// rotate three 3-vectors stored back to back: (v0, v1, v2) <- (v1, v2, v0)
+C2A_DEV void rot3(double v[9])
 {
-  double Sv[9], Tv[9], VEC[3], V[3], Z[3];
-  v_sub(&Sv[0], &S[3], &S[0]); v_sub(&Sv[3], &S[6], &S[3]); v_sub(&Sv[6], &S[0], &S[6]);
-  v_sub(&Tv[0], &T[3], &T[0]); v_sub(&Tv[3], &T[6], &T[3]); v_sub(&Tv[6], &T[0], &T[6]);
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+  {
+    const double t = v[k];
+    v[k] = v[3 + k]; v[3 + k] = v[6 + k]; v[6 + k] = t;
+  }
+}
+
+// PQP TriDist (in-tree copy C2A/src/C2A.cpp:165-405 without the contact-feature writes).
+// The 3x3 edge-pair loop stays rolled (one SegPoints body), but the vertex / edge arrays are never indexed by
+// the loop counters: after each trip the vertices are rotated by one, so edge i / j always starts at position 0
+// and the opposite vertex (i+2)%3 / (j+2)%3 is at position 2 -- the arrays stay in registers instead of local
+// memory (whose lines the small L1 left beside the slot pool keeps losing to L2).  Three rotations restore the
+// order.  Edge vectors are re-formed per trip (same subtraction, same bits) rather than kept live.
+C2A_DEV double tri_dist(double P[3], double Q[3], const double S_in[9], const double T_in[9])
+{
+  double S[9], T[9], VEC[3], V[3], Z[3];
+#pragma unroll
+  for (int k = 0; k < 9; k++) { S[k] = S_in[k]; T[k] = T_in[k]; }
 
   double minP[3], minQ[3], mindd;
   int shown_disjoint = 0;
   mindd = v_dist2(&S[0], &T[0]) + 1;
 
 #pragma unroll 1
-  for (int i = 0; i < 3; i++)
+  for (int ij = 0; ij < 9; ij++)
   {
-    const int i2 = (i + 2) % 3;
-#pragma unroll 1
-    for (int j = 0; j < 3; j++)
+    // edge i of S: S[0..2] + Sv[0..2], opposite vertex S[6..8]; edge j of T likewise
+    double A[3], B[3];  // edge vectors Sv[i] = S[i+1] - S[i], Tv[j] = T[j+1] - T[j]: the same subtraction every time
+    v_sub(A, &S[3], &S[0]);
+    v_sub(B, &T[3], &T[0]);
+    seg_points(VEC, P, Q, &S[0], A, &T[0], B);
+    v_sub(V, Q, P);
+    const double dd = v_dot(V, V);
+    if (dd <= mindd)
     {
-      seg_points(VEC, P, Q, &S[3 * i], &Sv[3 * i], &T[3 * j], &Tv[3 * j]);
-      v_sub(V, Q, P);
-      const double dd = v_dot(V, V);
-      if (dd <= mindd)
-      {
-        v_cpy(minP, P); v_cpy(minQ, Q); mindd = dd;
-        v_sub(Z, &S[3 * i2], P);
-        double a = v_dot(Z, VEC);
-        v_sub(Z, &T[3 * ((j + 2) % 3)], Q);
-        double b = v_dot(Z, VEC);
-        if ((a <= 0) && (b >= 0)) return sqrt(dd);
-        const double p = v_dot(V, VEC);
-        if (a < 0) a = 0;
-        if (b > 0) b = 0;
-        if ((p - a + b) > 0) shown_disjoint = 1;
-      }
+      v_cpy(minP, P); v_cpy(minQ, Q); mindd = dd;
+      v_sub(Z, &S[6], P);
+      double a = v_dot(Z, VEC);
+      v_sub(Z, &T[6], Q);
+      double b = v_dot(Z, VEC);
+      if ((a <= 0) && (b >= 0)) return sqrt(dd);
+      const double p = v_dot(V, VEC);
+      if (a < 0) a = 0;
+      if (b > 0) b = 0;
+      if ((p - a + b) > 0) shown_disjoint = 1;
     }
+    rot3(T);                                     // next j
+    if (ij == 2 || ij == 5 || ij == 8) rot3(S);  // j wrapped: next i (T is back in order)
   }
 
+  double Sv[9], Tv[9];
+  v_sub(&Sv[0], &S[3], &S[0]); v_sub(&Sv[3], &S[6], &S[3]); v_sub(&Sv[6], &S[0], &S[6]);
+  v_sub(&Tv[0], &T[3], &T[0]); v_sub(&Tv[3], &T[6], &T[3]); v_sub(&Tv[6], &T[0], &T[6]);
   double onFace[3], vert[3];
   if (face_vertex_case(S, Sv, T, shown_disjoint, onFace, vert))
   {

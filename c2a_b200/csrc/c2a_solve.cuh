@@ -415,14 +415,47 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
             const bool v = mt < upbound && ((d < (dist - abs_err)) || (d * (1 + rel_err) < dist));
             const int flags = (valid ? 1 : 0) | (my_leafpair ? 2 : 0) | (v ? 4 : 0);
 
-            // ---- replay the reference's decisions level by level (C2A.cpp:1281-1351): every lane of
-            // the group computes the same walk from the shuffled (d, mint, flags)
-            int P = 0;             // index (within its level) of the node pair being expanded
+            // ---- replay the reference's depth-first walk (C2A.cpp:1281-1351) over the evaluated tree: every lane
+            // of the group computes the same walk from the shuffled (d, mint, flags).  When a node pair's two
+            // children are both pruned the walk returns to the most recent pending far child; if that one was
+            // pushed during THIS pass its own child tests are in the tree as well (the distance has not changed,
+            // so it still passes the descend test it passed when pushed) and the walk carries on through it.
+            // The pass ends at a leaf pair, at a pair whose children lie below the tree, or when nothing
+            // pushed in this pass is pending.
+            int P = 0, l = 0;      // expanding the pair reached by test (l - 1, P); the slot's node pair for l = 0
             int levels = 0;        // expansions committed
             int write_cur = -1;    // group lane whose child becomes the current entry
             int write_leaf = -1;   // group lane whose child is a leaf pair to hand to the LEAF phase
             bool me_push = false; int my_push_sp = 0;
-            for (int l = 0; l < D; l++)
+            unsigned pend = 0; int npend = 0;  // far children pushed in this pass and still pending (lane ids, 8 bits each)
+            if (D == 1)
+            {
+              // the steady state (a lane pair per slot): one expansion, no walk
+              const double d_o = __shfl_xor_sync(gmask, d, 1), m_o = __shfl_xor_sync(gmask, mt, 1);
+              const int f_o = __shfl_xor_sync(gmask, flags, 1);
+              const double d_a = t ? d_o : d, d_c = t ? d : d_o, m_a = t ? m_o : mt, m_c = t ? mt : m_o;
+              const int f_a = t ? f_o : flags, f_c = t ? flags : f_o;
+              levels = 1;
+              const bool v_a = f_a & 4, v_c = f_c & 4;
+              const bool c_first = d_c < d_a;  // ties visit 'a' first (the test is d2 < d1)
+              const bool v_near = c_first ? v_c : v_a, v_far = c_first ? v_a : v_c;
+              const int near_lane = c_first ? 1 : 0, far_lane = c_first ? 0 : 1;
+              if (!v_a && m_a < mint) mint = m_a;
+              if (!v_c && m_c < mint) mint = m_c;
+              if (v_near || v_far)
+              {
+                const int next_lane = v_near ? near_lane : far_lane;
+                if (v_near && v_far)
+                {
+                  if (t == far_lane) { me_push = true; my_push_sp = sp; }
+                  sp++;
+                }
+                if ((next_lane ? f_c : f_a) & 2) write_leaf = next_lane;
+                else write_cur = next_lane;
+              }
+            }
+            else
+            while (true)
             {
               const int la = (2 << l) - 2 + 2 * P, lc = la + 1;  // group lanes of children 'a' and 'c'
               const double d_a = __shfl_sync(gmask, d, gbase + la), d_c = __shfl_sync(gmask, d, gbase + lc);
@@ -436,8 +469,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
               const int near_lane = c_first ? lc : la, far_lane = c_first ? la : lc;
               if (!v_a && m_a < mint) mint = m_a;
               if (!v_c && m_c < mint) mint = m_c;
-              if (!v_near && !v_far) { write_cur = -1; break; }
-              int next_lane;
+              int next_lane, f_next;
               if (v_near)
               {
                 next_lane = near_lane;
@@ -445,13 +477,27 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
                 {
                   if (t == far_lane) { me_push = true; my_push_sp = sp; }
                   sp++;
+                  pend |= (unsigned)far_lane << (8 * npend);
+                  npend++;
                 }
+                f_next = (next_lane == la) ? f_a : f_c;
               }
-              else next_lane = far_lane;
-              const int f_next = (next_lane == la) ? f_a : f_c;
+              else if (v_far) { next_lane = far_lane; f_next = (next_lane == la) ? f_a : f_c; }
+              else
+              {
+                if (npend == 0) { write_cur = -1; break; }
+                npend--;
+                next_lane = (int)((pend >> (8 * npend)) & 0xffu);
+                pend &= ~(0xffu << (8 * npend));
+                sp--;
+                if (t == next_lane) me_push = false;
+                f_next = __shfl_sync(gmask, flags, gbase + next_lane);
+              }
               if (f_next & 2) { write_leaf = next_lane; write_cur = -1; break; }
-              write_cur = next_lane;
-              P = 2 * P + (next_lane == lc ? 1 : 0);
+              const int Ln = 30 - __clz(next_lane + 2);  // level of that test
+              if (Ln + 1 >= D) { write_cur = next_lane; break; }
+              l = Ln + 1;
+              P = next_lane + 2 - (2 << Ln);
             }
 
             if (me_push)
