@@ -240,6 +240,8 @@ int c2a_b200_model_info(const c2a_b200_model *m, int32_t *device, int32_t *n_nod
 }
 
 static unsigned long long *g_stats_dev = nullptr;  // phase statistics (c2a_b200_phase_stats), off by default
+static unsigned long long *g_trace_dev = nullptr;  // per-query claim / finish times (c2a_b200_query_trace), off by default
+static int64_t g_trace_n = 0;
 
 // per-device scratch: the claim counter
 static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses, const int32_t *sa,
@@ -307,6 +309,7 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
     CUDA_TRY(cudaMemsetAsync(extra, 0, ctl_bytes + ready_bytes, stream));
   }
   args.stats = g_stats_dev;
+  args.trace = (g_trace_dev && n <= g_trace_n && !step_in) ? g_trace_dev : nullptr;
   CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
   c2a_solve_kernel<<<(unsigned)blocks, BLOCK_THREADS, BLOCK_SMEM_BYTES, stream>>>(args);
   g_launches.fetch_add(1);
@@ -962,6 +965,27 @@ int c2a_b200_test_sincos(const double *x, int64_t n, double *s, double *c)
 // out[9..10] = 32-lane look-ahead passes and the expansion levels they committed;
 // out[11..13] = warp cycles spent in EXPAND / LEAF / ADVANCE passes; out[14..19] = {passes, cycles} of the
 // three phases for a query alone on its warp (out must hold 20).
+// Per-query timeline of the next batches of up to n queries (development aid): out [n][2] = globaltimer ns at
+// claim and at result write-out.  n > 0 arms (allocates), n == 0 with out reads back the last launch, n < 0 frees.
+int c2a_b200_query_trace(int64_t n, uint64_t *out)
+{
+  if (n > 0)
+  {
+    if (g_trace_dev) cudaFree(g_trace_dev);
+    g_trace_dev = nullptr; g_trace_n = 0;
+    CUDA_TRY(cudaMalloc(&g_trace_dev, (size_t)n * 16));
+    CUDA_TRY(cudaMemset(g_trace_dev, 0, (size_t)n * 16));
+    g_trace_n = n;
+  }
+  else if (n == 0 && out && g_trace_dev)
+  {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out, g_trace_dev, (size_t)g_trace_n * 16, cudaMemcpyDeviceToHost));
+  }
+  else if (n < 0 && g_trace_dev) { cudaFree(g_trace_dev); g_trace_dev = nullptr; g_trace_n = 0; }
+  return C2A_B200_OK;
+}
+
 int c2a_b200_phase_stats(int32_t enable, uint64_t *out20)
 {
   uint64_t *out9 = out20;

@@ -69,6 +69,7 @@ struct BatchArgs
   const int *order;       // optional [n]: the k-th claim takes query order[k] (longest-expected first); NULL = identity
   const double *step_in;  // optional [n][STEP_IN_DOUBLES]: single-step mode (C2A_TimeOfContactStep), see below
   unsigned long long *stats;  // optional [14], see c2a_b200_phase_stats; NULL = off
+  unsigned long long *trace;  // optional [n][2]: globaltimer at claim / at result write-out (development aid)
   // Tail hand-over (NULL = off): once the claim queue is empty, a warp that still holds several queries
   // passes one on, at a CA-step boundary (where a query's state is ~64 bytes: no stack), to a warp that
   // has run out of work; alone on a warp, a query gets all 32 lanes for look-ahead.
@@ -687,6 +688,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
             if (o.mint) o.mint[q] = mint;
             if (o.last_tri) { o.last_tri[2 * q] = SI(I_LASTA, slot); o.last_tri[2 * q + 1] = SI(I_LASTB, slot); }
             if (args.ctl) atomicAdd(args.ctl + 2, 1ull);
+            if (args.trace) args.trace[2 * q + 1] = global_ns();
             q = -1;
           }
         }
@@ -726,6 +728,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const Batch
           else
           {
             q = args.order ? (long long)__ldg(args.order + nq) : nq;
+            if (args.trace) args.trace[2 * q] = global_ns();
             const double *rec = args.motions + (size_t)(2 * MOTION_DOUBLES) * q;
             const double w1 = __ldg(rec + 18), w2 = __ldg(rec + MOTION_DOUBLES + 18);
             if (!args.step_in && w1 < 1e-8 && w2 < 1e-8)

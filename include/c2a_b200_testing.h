@@ -32,6 +32,10 @@ int c2a_b200_host_sincos(const double *x, int64_t n, double *s, double *c);
 /* Phase statistics of the solve kernel (development aid): see c2a_kernels.cu. */
 int c2a_b200_phase_stats(int32_t enable, uint64_t *out20);
 
+/* Per-query timeline (development aid): n > 0 arms a [n][2] device buffer that the next batches of <= n queries fill
+ * with the globaltimer (ns) at claim and at result write-out; n == 0 copies it to out; n < 0 frees it. */
+int c2a_b200_query_trace(int64_t n, uint64_t *out);
+
 /* FP64 pipe peak of the current device in TFLOP/s: dependent-free DFMA chains, and the same with
  * separate DMUL + DADD (the product is built with -fmad=false, so that is its ceiling). */
 int c2a_b200_fp64_peak(double *tflops_fma, double *tflops_mul_add);
