@@ -52,7 +52,10 @@ struct DevModel
 constexpr int ENTRY_DOUBLES = 16;  // R(9) T(3) d mint {b1,b2} pad  -> 128 B
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr int BLOCK_THREADS = 32 * WARPS_PER_BLOCK;
-constexpr int Q = 48;              // query slots per warp: more than one EXPAND pass (16) plus one LEAF pass can use,
+#ifndef C2A_Q
+#define C2A_Q 48
+#endif
+constexpr int Q = C2A_Q;              // query slots per warp: more than one EXPAND pass (16) plus one LEAF pass can use,
                                    // so that leaves pile up to a full 32-lane LEAF pass while expansion stays fed
 
 struct BatchArgs
@@ -120,12 +123,29 @@ C2A_DEV void load3(double d[3], const double *s) { d[0] = __ldg(s); d[1] = __ldg
 C2A_DEV unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 C2A_DEV void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
+// index of the (n+1)-th set bit of a 32-bit word (n < popc(m)): five branch-free halving steps on popc
+// (the __fns intrinsic is a software loop and showed up with 4.5 % of the stall samples)
+C2A_DEV int nth_bit32(unsigned m, int n)
+{
+  int pos = 0;
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1)
+  {
+    const int c = __popc(m & ((1u << w) - 1u));
+    const bool up = n >= c;
+    n -= up ? c : 0;
+    m = up ? (m >> w) : m;
+    pos += up ? w : 0;
+  }
+  return pos;
+}
 // index of the (n+1)-th set bit of a 64-bit slot mask
 C2A_DEV int nth_slot(unsigned long long m, int n)
 {
   const unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
   const int nlo = __popc(lo);
-  return n < nlo ? (int)__fns(lo, 0, n + 1) : 32 + (int)__fns(hi, 0, n - nlo + 1);
+  const bool in_lo = n < nlo;
+  return (in_lo ? 0 : 32) + nth_bit32(in_lo ? lo : hi, in_lo ? n : n - nlo);
 }
 
 __device__ __noinline__ double tri_distance_nl(const double R[9], const double T[3], const double *t1,
