@@ -242,6 +242,25 @@ def contacts_batch(model_a, model_b, poses24, threshold, max_contacts=64):
     return num, recs
 
 
+def distance_batch(model_a, model_b, poses24, seed_a=None, seed_b=None, rel_err=0.0, abs_err=0.0):
+    """Batched C2A_Distance (depth-first routine): poses24 [n,24] = pose of A, pose of B.  Returns a dict with
+    distance [n], p1p2 [n,6], tri_pair [n,2], num_bv_tests [n], num_tri_tests [n]."""
+    poses24 = np.ascontiguousarray(poses24, dtype=np.float64).reshape(-1, 24)
+    n = poses24.shape[0]
+    sa = None if seed_a is None else np.ascontiguousarray(seed_a, dtype=np.int32)
+    sb = None if seed_b is None else np.ascontiguousarray(seed_b, dtype=np.int32)
+    out = {"distance": np.zeros(n), "p1p2": np.zeros((n, 6)), "tri_pair": np.zeros((n, 2), dtype=np.int32),
+           "num_bv_tests": np.zeros(n, dtype=np.int32), "num_tri_tests": np.zeros(n, dtype=np.int32)}
+    _check(lib().c2a_b200_distance_batch(model_a.h, model_b.h, poses24.ctypes.data_as(C.c_void_p),
+                                         sa.ctypes.data_as(C.c_void_p) if sa is not None else None,
+                                         sb.ctypes.data_as(C.c_void_p) if sb is not None else None,
+                                         C.c_int64(n), C.c_double(rel_err), C.c_double(abs_err),
+                                         out["distance"].ctypes.data_as(C.c_void_p), out["p1p2"].ctypes.data_as(C.c_void_p),
+                                         out["tri_pair"].ctypes.data_as(C.c_void_p), out["num_bv_tests"].ctypes.data_as(C.c_void_p),
+                                         out["num_tri_tests"].ctypes.data_as(C.c_void_p)))
+    return out
+
+
 def motions_from_poses(poses, threads=0, out=None):
     """Host half of the motion model (acos via the host libm): poses [n,48] -> motion records [n,48]."""
     poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 48)

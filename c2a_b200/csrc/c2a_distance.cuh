@@ -1,0 +1,151 @@
+// Discrete minimum-distance query on the device: C2A_Distance with the depth-first routine it takes for
+// qsize <= 2 (/root/reference/C2A/src/C2A_PQP.cpp:970-1056 and C2ADistanceRecurse :481-614).
+//
+// Not on the CCD hot path; it reuses the hot path's device functions
+// (rss_rect_dist, tri_distance).  The result depends on the visiting order exactly as in the CCD traversal
+// (res->distance shrinks as leaves are visited and gates the pruning), so a query is one thread walking the
+// reference's depth-first order with a local stack; parallelism is across queries.
+#pragma once
+#include "c2a_solve.cuh"
+
+namespace c2a {
+
+struct DistanceArgs
+{
+  DevModel A, B;
+  const double *poses;        // [n][24] pose of A, pose of B (R(9)+T(3) each)
+  const int *seedA, *seedB;   // [n] or NULL (triangle 0): o1->last_tri / o2->last_tri going in
+  long long n;
+  double rel_err, abs_err;
+  double *distance;           // [n]
+  double *p1p2;               // [n][6] or NULL: closest points, each in its own model's frame
+  int *tri_pair;              // [n][2] or NULL: closest triangle pair, builder order (o->last_tri coming out)
+  int *num_bv_tests, *num_tri_tests;  // [n] or NULL
+};
+
+constexpr int DIST_STACK = 96;  // >= depth(A)+depth(B)+2, validated on the host
+constexpr int DIST_ENTRY = 14;  // R(9) T(3) ids d
+
+__global__ void __launch_bounds__(128) c2a_distance_kernel(const DistanceArgs args)
+{
+  const DevModel &A = args.A, &B = args.B;
+  double stk[DIST_STACK * DIST_ENTRY];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < args.n; q += stride)
+  {
+    const double *pose = args.poses + 24 * q;
+    double R1[9], T1[3], R2[9], T2[3], Rrel[9], Trel[3], Tt[3], Rt[9], g1[12], g2[12], R[9], T[3];
+    load9(R1, pose); load3(T1, pose + 9); load9(R2, pose + 12); load3(T2, pose + 21);
+    // [R,T] = [R1'R2, R1'(T2-T1)], :987-990
+    mt_m(Rrel, R1, R2);
+    v_sub(Tt, T2, T1);
+    mt_v(Trel, R1, Tt);
+    int ta = args.seedA ? args.seedA[q] : 0, tb = args.seedB ? args.seedB[q] : 0;
+    double p1[3], p2[3];
+    // initial upper bound from the last closest triangle pair, :995-1000
+    double dist = tri_distance_nl(Rrel, Trel, A.tris + (size_t)9 * ta, B.tris + (size_t)9 * tb, p1, p2);
+    // root pair, :1016-1027
+#pragma unroll
+    for (int i = 0; i < 12; i++) { g1[i] = __ldg(A.geom + i); g2[i] = __ldg(B.geom + i); }
+    m_m(Rt, Rrel, g2);
+    mt_m(R, g1, Rt);
+    m_v_p(Tt, Rrel, &g2[9], Trel);
+    v_sub(Tt, Tt, &g1[9]);
+    mt_v(T, g1, Tt);
+    int nbv = 0, ntri = 0, sp = 0;
+    {
+      double *e = stk;
+#pragma unroll
+      for (int i = 0; i < 9; i++) e[i] = R[i];
+      e[9] = T[0]; e[10] = T[1]; e[11] = T[2]; e[12] = __hiloint2double(0, 0);
+      e[13] = -1.0;  // flag: the root pair is visited unconditionally
+      sp = 1;
+    }
+    while (sp > 0)
+    {
+      const double *e = stk + (sp - 1) * DIST_ENTRY;
+      sp--;
+      const double ed = e[13];
+      // the descend test, evaluated when the reference would reach this child (:589-613)
+      if (ed >= 0.0 && !((ed < (dist - args.abs_err)) || (ed * (1 + args.rel_err) < dist))) continue;
+#pragma unroll
+      for (int i = 0; i < 9; i++) R[i] = e[i];
+      T[0] = e[9]; T[1] = e[10]; T[2] = e[11];
+      const int b1 = __double2hiint(e[12]), b2 = __double2loint(e[12]);
+      const NodeMeta ma = A.meta[b1], mb = B.meta[b2];
+      const bool l1 = ma.first_child < 0, l2 = mb.first_child < 0;
+      if (l1 && l2)
+      {
+        // :494-521
+        ntri++;
+        const int t1 = -ma.first_child - 1, t2 = -mb.first_child - 1;
+        double p[3], qq[3];
+        const double d = tri_distance_nl(Rrel, Trel, A.tris + (size_t)9 * t1, B.tris + (size_t)9 * t2, p, qq);
+        if (d < dist)
+        {
+          dist = d; ta = t1; tb = t2;
+          v_cpy(p1, p); v_cpy(p2, qq);
+        }
+        continue;
+      }
+      // :527-587: both children, the nearer one first
+      double Rch[2][9], Tch[2][3], dch[2], ids[2];
+      const bool split1 = l2 || (!l1 && (ma.size > mb.size));
+#pragma unroll 1
+      for (int c = 0; c < 2; c++)
+      {
+        const double *ga, *gb;
+        if (split1)
+        {
+          const int n1 = ma.first_child + c;
+          ids[c] = __hiloint2double(n1, b2);
+          ga = A.geom + (size_t)n1 * GEOM_STRIDE; gb = B.geom + (size_t)b2 * GEOM_STRIDE;
+          double Rn[9], Tn[3];
+          load9(Rn, ga); load3(Tn, ga + 9);
+          mt_m(Rch[c], Rn, R); v_sub(Tt, T, Tn); mt_v(Tch[c], Rn, Tt);
+        }
+        else
+        {
+          const int n2 = mb.first_child + c;
+          ids[c] = __hiloint2double(b1, n2);
+          ga = A.geom + (size_t)b1 * GEOM_STRIDE; gb = B.geom + (size_t)n2 * GEOM_STRIDE;
+          double Rn[9], Tn[3];
+          load9(Rn, gb); load3(Tn, gb + 9);
+          m_m(Rch[c], R, Rn); m_v_p(Tch[c], R, Tn, T);
+        }
+        double S[3];
+        double d = rss_rect_dist(Rch[c], Tch[c], __ldg(ga + 12), __ldg(ga + 13), __ldg(gb + 12), __ldg(gb + 13), S);
+        d -= (__ldg(ga + 14) + __ldg(gb + 14));
+        dch[c] = (d < 0.0) ? 0.0 : d;
+      }
+      nbv += 2;
+      const bool c_first = dch[1] < dch[0];
+#pragma unroll 1
+      for (int k = 0; k < 2; k++)
+      {
+        const int c = (k == 0) ? (c_first ? 0 : 1) : (c_first ? 1 : 0);  // the one visited second is pushed first
+        double *o = stk + sp * DIST_ENTRY;
+#pragma unroll
+        for (int i = 0; i < 9; i++) o[i] = Rch[c][i];
+        o[9] = Tch[c][0]; o[10] = Tch[c][1]; o[11] = Tch[c][2];
+        o[12] = ids[c]; o[13] = dch[c];
+        sp++;
+      }
+    }
+    args.distance[q] = dist;
+    if (args.p1p2)
+    {
+      // res->p2 is in cs 1; transform it to cs 2, :1044-1048
+      double u[3], p2b[3];
+      v_sub(u, p2, Trel);
+      mt_v(p2b, Rrel, u);
+#pragma unroll
+      for (int i = 0; i < 3; i++) { args.p1p2[6 * q + i] = p1[i]; args.p1p2[6 * q + 3 + i] = p2b[i]; }
+    }
+    if (args.tri_pair) { args.tri_pair[2 * q] = ta; args.tri_pair[2 * q + 1] = tb; }
+    if (args.num_bv_tests) args.num_bv_tests[q] = nbv;
+    if (args.num_tri_tests) args.num_tri_tests[q] = ntri;
+  }
+}
+
+}  // namespace c2a

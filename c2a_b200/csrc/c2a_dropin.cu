@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <chrono>
 #include <vector>
 
 #include "../../include/C2A/C2A.h"
@@ -360,6 +361,38 @@ PQP_REAL C2A_QueryTimeOfContact(CInterpMotion *objmotion1, CInterpMotion *objmot
   if (last[1] >= 0) o2->last_tri = &o2->tris[last[1]];
   if (!res->collisionfree) objmotion1->integrate(toc, res->R_toc, res->T_toc);  // C2A.cpp:2143
   return toc;
+}
+
+// C2A/src/C2A_PQP.cpp:970-1056
+int C2A_Distance(C2A_DistanceResult *res, PQP_REAL R1[3][3], PQP_REAL T1[3], C2A_Model *o1, PQP_REAL R2[3][3],
+                 PQP_REAL T2[3], C2A_Model *o2, PQP_REAL rel_err, PQP_REAL abs_err, int qsize)
+{
+  if (!o1 || !o2 || !o1->gpu || !o2->gpu) return PQP_ERR_UNPROCESSED_MODEL;
+  const auto t_begin = std::chrono::steady_clock::now();
+  double pose[24];
+  for (int i = 0; i < 3; i++)
+  {
+    for (int j = 0; j < 3; j++) { pose[3 * i + j] = R1[i][j]; pose[12 + 3 * i + j] = R2[i][j]; }
+    pose[9 + i] = T1[i]; pose[21 + i] = T2[i];
+  }
+  int32_t sa = seed_index(o1, o1->last_tri), sb = seed_index(o2, o2->last_tri), pair[2] = {0, 0}, nbv = 0, ntri = 0;
+  double dist = 0, p1p2[6];
+  const int rc = c2a_b200_distance_batch(o1->gpu, o2->gpu, pose, &sa, &sb, 1, rel_err, abs_err, &dist, p1p2, pair, &nbv, &ntri);
+  if (rc) { fprintf(stderr, "c2a_b200: %s\n", c2a_b200_last_error()); return rc; }
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) res->R[i][j] = (R1[0][i] * R2[0][j] + R1[1][i] * R2[1][j] + R1[2][i] * R2[2][j]);
+  {
+    const PQP_REAL Tt[3] = {T2[0] - T1[0], T2[1] - T1[1], T2[2] - T1[2]};
+    for (int i = 0; i < 3; i++) res->T[i] = (R1[0][i] * Tt[0] + R1[1][i] * Tt[1] + R1[2][i] * Tt[2]);
+  }
+  res->distance = dist; res->rel_err = rel_err; res->abs_err = abs_err; res->qsize = qsize;
+  res->num_bv_tests = nbv; res->num_tri_tests = ntri;
+  for (int i = 0; i < 3; i++) { res->p1[i] = p1p2[i]; res->p2[i] = p1p2[3 + i]; }
+  o1->last_tri = &o1->tris[pair[0]];
+  o2->last_tri = &o2->tris[pair[1]];
+  res->t1 = o1->tris[pair[0]].id; res->t2 = o2->tris[pair[1]].id;
+  res->query_time_secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+  return PQP_OK;
 }
 
 // C2A/src/C2A.cpp:1937-1966: contact features at the motions' CURRENT poses

@@ -19,6 +19,7 @@
 #include "c2a_solve.cuh"
 #include "c2a_contact.cuh"
 #include "c2a_translation.cuh"
+#include "c2a_distance.cuh"
 
 namespace c2a {
 
@@ -402,6 +403,61 @@ int c2a_b200_contacts_batch(const c2a_b200_model *a, const c2a_b200_model *b, co
     rc = fail(C2A_B200_ERR_CUDA, cudaGetErrorString(e));
   if (rc == C2A_B200_OK && contacts && (e = cudaMemcpy(contacts, arena + o_ct, cbytes, cudaMemcpyDeviceToHost)) != cudaSuccess)
     rc = fail(C2A_B200_ERR_CUDA, cudaGetErrorString(e));
+  cudaFree(arena);
+  return rc;
+}
+
+int c2a_b200_distance_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses24, const int32_t *seed_a,
+                            const int32_t *seed_b, int64_t n, double rel_err, double abs_err, double *distance, double *p1p2,
+                            int32_t *tri_pair, int32_t *num_bv_tests, int32_t *num_tri_tests)
+{
+  if (!a || !b || n < 0 || (n > 0 && (!poses24 || !distance))) return fail(C2A_B200_ERR_ARG, "NULL argument");
+  if (a->device != b->device) return fail(C2A_B200_ERR_DEVICE, "models live on different devices");
+  if (a->depth + b->depth + 2 > DIST_STACK) return fail(C2A_B200_ERR_DEPTH, "BVH depths exceed the distance query's stack");
+  if (n == 0) return C2A_B200_OK;
+  CUDA_TRY(cudaSetDevice(a->device));
+  const size_t N = (size_t)n;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_pose = take(N * 192), o_sa = seed_a ? take(N * 4) : 0, o_sb = seed_b ? take(N * 4) : 0, o_d = take(N * 8);
+  const size_t o_pp = p1p2 ? take(N * 48) : 0, o_tp = tri_pair ? take(N * 8) : 0, o_nbv = num_bv_tests ? take(N * 4) : 0;
+  const size_t o_ntri = num_tri_tests ? take(N * 4) : 0;
+  char *arena = nullptr;
+  CUDA_TRY(cudaMalloc(&arena, off));
+  int rc = C2A_B200_OK;
+  cudaError_t e = cudaSuccess;
+#define STEP(x) if (rc == C2A_B200_OK && (e = (x)) != cudaSuccess) rc = fail(C2A_B200_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e));
+  STEP(cudaMemcpy(arena + o_pose, poses24, N * 192, cudaMemcpyHostToDevice));
+  if (seed_a) STEP(cudaMemcpy(arena + o_sa, seed_a, N * 4, cudaMemcpyHostToDevice));
+  if (seed_b) STEP(cudaMemcpy(arena + o_sb, seed_b, N * 4, cudaMemcpyHostToDevice));
+  if (rc == C2A_B200_OK)
+  {
+    DistanceArgs args;
+    args.A = DevModel{a->geom, a->rloc, a->meta, a->tris, a->n_nodes, a->n_tris};
+    args.B = DevModel{b->geom, b->rloc, b->meta, b->tris, b->n_nodes, b->n_tris};
+    args.poses = (const double *)(arena + o_pose);
+    args.seedA = seed_a ? (const int *)(arena + o_sa) : nullptr; args.seedB = seed_b ? (const int *)(arena + o_sb) : nullptr;
+    args.n = n; args.rel_err = rel_err; args.abs_err = abs_err;
+    args.distance = (double *)(arena + o_d); args.p1p2 = p1p2 ? (double *)(arena + o_pp) : nullptr;
+    args.tri_pair = tri_pair ? (int *)(arena + o_tp) : nullptr;
+    args.num_bv_tests = num_bv_tests ? (int *)(arena + o_nbv) : nullptr;
+    args.num_tri_tests = num_tri_tests ? (int *)(arena + o_ntri) : nullptr;
+    int sms = 0;
+    STEP(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, a->device));
+    long long blocks = (long long)sms * 8;
+    const long long need = (n + 127) / 128;
+    if (blocks > need) blocks = need;
+    c2a_distance_kernel<<<(unsigned)blocks, 128>>>(args);
+    g_launches.fetch_add(1);
+    STEP(cudaGetLastError());
+    STEP(cudaDeviceSynchronize());
+  }
+  STEP(cudaMemcpy(distance, arena + o_d, N * 8, cudaMemcpyDeviceToHost));
+  if (p1p2) STEP(cudaMemcpy(p1p2, arena + o_pp, N * 48, cudaMemcpyDeviceToHost));
+  if (tri_pair) STEP(cudaMemcpy(tri_pair, arena + o_tp, N * 8, cudaMemcpyDeviceToHost));
+  if (num_bv_tests) STEP(cudaMemcpy(num_bv_tests, arena + o_nbv, N * 4, cudaMemcpyDeviceToHost));
+  if (num_tri_tests) STEP(cudaMemcpy(num_tri_tests, arena + o_ntri, N * 4, cudaMemcpyDeviceToHost));
+#undef STEP
   cudaFree(arena);
   return rc;
 }

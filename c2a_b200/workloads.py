@@ -69,6 +69,16 @@ def translation_batch(n, seed, radius=BUNNY_RADIUS, move_b=False):
     return np.ascontiguousarray(np.concatenate([R1, T0, R1, T1, R2, Z, R2, Z1], 1))
 
 
+def static_pose_batch(n, seed, radius=BUNNY_RADIUS):
+    """Static pose pairs for the discrete distance query: the poses an approach_batch motion passes through at
+    a random time (far apart, close, and interpenetrating cases all occur).  Returns [n,24] = pose of A, pose of B."""
+    ap = approach_batch(n, seed, radius=radius, max_turn=0.0)
+    lam = np.random.default_rng(seed + 1).uniform(0.0, 1.0, size=(n, 1))
+    pa = ap[:, 0:12].copy()
+    pa[:, 9:12] = ap[:, 9:12] * (1.0 - lam) + ap[:, 21:24] * lam
+    return np.ascontiguousarray(np.concatenate([pa, ap[:, 24:36]], 1))
+
+
 def demo_batch(R1f, T1f, R2f, T2f):
     """Config 1: the 303 queries ``cb_display`` builds from torusknot1.ani / torusknot2.ani
     (/root/reference/CCDDemo/mainTorusknot.cpp:216-266): object 1 moves from frame step1 to step2 of

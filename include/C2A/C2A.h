@@ -244,6 +244,31 @@ struct C2A_TimeOfContactResult
   const PQP_REAL *P2() { return p2; }
 };
 
+// PQP_DistanceResult + the closest triangle pair (C2A/C2A_Internal.h:89-93)
+struct C2A_DistanceResult
+{
+  int num_bv_tests, num_tri_tests;
+  double query_time_secs;
+  PQP_REAL R[3][3], T[3];   // model 2 -> model 1
+  PQP_REAL rel_err, abs_err;
+  PQP_REAL distance;
+  PQP_REAL p1[3], p2[3];    // closest points, each in its own model's frame
+  int qsize;
+  int t1, t2;               // Tri::id of the closest pair
+  int NumBVTests() { return num_bv_tests; }
+  int NumTriTests() { return num_tri_tests; }
+  double QueryTimeSecs() { return query_time_secs; }
+  PQP_REAL Distance() { return distance; }
+  const PQP_REAL *P1() { return p1; }
+  const PQP_REAL *P2() { return p2; }
+};
+
+// C2A/C2A.h:256-261, C2A/src/C2A_PQP.cpp:970-1056.  Runs the reference's depth-first routine whatever qsize says
+// (the reference switches to a priority queue for qsize > 2, which may report another pair within the same bounds).
+// Reads and updates o1->last_tri / o2->last_tri like the reference.
+int C2A_Distance(C2A_DistanceResult *result, PQP_REAL R1[3][3], PQP_REAL T1[3], C2A_Model *o1, PQP_REAL R2[3][3],
+                 PQP_REAL T2[3], C2A_Model *o2, PQP_REAL rel_err, PQP_REAL abs_err, int qsize = 2);
+
 C2A_Result C2A_Solve(Transform *trans00, Transform *trans01, C2A_Model *obj1_tested, Transform *trans10,
                      Transform *trans11, C2A_Model *obj2_tested, Transform &trans0, Transform &trans1,
                      PQP_REAL &time_of_contact, int &number_of_iteration, int &number_of_contact, PQP_REAL th_ca,

@@ -142,6 +142,18 @@ int c2a_b200_contacts_batch(const c2a_b200_model *a, const c2a_b200_model *b, co
                             const double *threshold, int64_t n, int32_t max_contacts, int32_t *num_contact,
                             c2a_b200_contact *contacts);
 
+/* Batched C2A_Distance (C2A/C2A.h:256-261, C2A/src/C2A_PQP.cpp:970-1056): minimum distance between the two models
+ * at the static poses poses24[i] = pose of A, pose of B (R(9)+T(3) each), with the depth-first routine the reference
+ * takes for qsize <= 2 (C2ADistanceRecurse, :481-614; the result is visiting-order dependent exactly like the CCD
+ * traversal, so a priority-queue run -- qsize > 2 -- may report another pair within the same error bounds).
+ * seed_a / seed_b: [n] the models' last_tri going in (NULL = triangle 0); tri_pair [n][2]: the closest triangle pair
+ * in builder order = last_tri coming out; p1p2 [n][6]: the closest points, each in its own model's frame
+ * (PQP_DistanceResult::p1, p2).  rel_err / abs_err as PQP: a pair is skipped only if BOTH bounds allow it.
+ * Host buffers; not part of the CCD hot path (it reuses its device functions). */
+int c2a_b200_distance_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses24, const int32_t *seed_a,
+                            const int32_t *seed_b, int64_t n, double rel_err, double abs_err, double *distance, double *p1p2,
+                            int32_t *tri_pair, int32_t *num_bv_tests, int32_t *num_tri_tests);
+
 /* Host half of the motion model: what constructing the two CInterpMotion_Linear objects does in
  * C2A_Solve (C2A/src/C2A.cpp:2378-2379 -> C2A/src/InterpMotion.cpp:148-168, 486-491, 228-270).
  * poses [n][48] -> motions [n][C2A_B200_MOTION_DOUBLES]: per object R0(9) T0(3) cv(3) axis(3) angVel

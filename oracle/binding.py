@@ -27,6 +27,10 @@ CONTACT_DTYPE = np.dtype([("type_a", np.int32), ("type_b", np.int32), ("fid_a", 
                           ("dist", np.float64)], align=True)
 
 
+DISTANCE_DTYPE = np.dtype([("distance", np.float64), ("p1", np.float64, 3), ("p2", np.float64, 3), ("tri_a", np.int32),
+                           ("tri_b", np.int32), ("num_bv_tests", np.int32), ("num_tri_tests", np.int32)], align=True)
+
+
 class _Bvh(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("n_tris", C.c_int32),
                 ("R", C.c_void_p), ("Tr", C.c_void_p), ("l", C.c_void_p), ("r", C.c_void_p),
@@ -109,6 +113,17 @@ class _Port:
                                   C.c_int64(max_out), _ptr(out))
         return int(n), out[:min(int(n), max_out)]
 
+    def distance(self, bvhA, bvhB, poses24, seedA=None, seedB=None, rel_err=0.0, abs_err=0.0):
+        """C2A_Distance (depth-first routine) per query: poses24 [n,24] = pose of A, pose of B."""
+        sA, sB = bvh_struct(bvhA), bvh_struct(bvhB)
+        poses24 = np.ascontiguousarray(poses24, np.float64).reshape(-1, 24)
+        out = np.zeros(len(poses24), dtype=DISTANCE_DTYPE)
+        for i in range(len(poses24)):
+            self.lib.orc_distance(C.byref(sA), C.byref(sB), _ptr(poses24[i]), C.c_int32(0 if seedA is None else int(seedA[i])),
+                                  C.c_int32(0 if seedB is None else int(seedB[i])), C.c_double(rel_err), C.c_double(abs_err),
+                                  C.c_void_p(out[i:i + 1].ctypes.data))
+        return out
+
     def rect_dist(self, Rab, Tab, a, b):
         Rab = np.ascontiguousarray(Rab, np.float64); Tab = np.ascontiguousarray(Tab, np.float64)
         a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64)
@@ -172,6 +187,16 @@ class _Ref:
                                  C.c_int32(mode), C.c_double(tol_d), C.c_double(tol_t), _ptr(out), _ptr(ncont),
                                  C.c_int32(threads))
         return (out, ncont) if mode == 1 else out
+
+    def distance(self, mA, mB, poses24, seedA=None, seedB=None, rel_err=0.0, abs_err=0.0, qsize=2):
+        """The reference's own C2A_Distance, one query at a time (it reads and writes the models' last_tri)."""
+        poses24 = np.ascontiguousarray(poses24, np.float64).reshape(-1, 24)
+        out = np.zeros(len(poses24), dtype=DISTANCE_DTYPE)
+        for i in range(len(poses24)):
+            self.lib.ref_distance(mA.h, mB.h, _ptr(poses24[i]), C.c_int32(0 if seedA is None else int(seedA[i])),
+                                  C.c_int32(0 if seedB is None else int(seedB[i])), C.c_double(rel_err), C.c_double(abs_err),
+                                  C.c_int32(qsize), C.c_void_p(out[i:i + 1].ctypes.data))
+        return out
 
     def rect_dist(self, Rab, Tab, a, b):
         Rab = np.ascontiguousarray(Rab, np.float64); Tab = np.ascontiguousarray(Tab, np.float64)

@@ -1215,3 +1215,94 @@ extern "C" int64_t orc_contacts(const orc_bvh *A, const orc_bvh *B, const int32_
   contact_recurse(cx, R, T, 0, 0);
   return cx.count;
 }
+
+// ---- discrete distance query ---------------------------------------------------------------
+// C2A_Distance (C2A/src/C2A_PQP.cpp:970-1056) with the depth-first routine it takes for qsize <= 2,
+// C2ADistanceRecurse (:481-614).  Seeds stand in for o1->last_tri / o2->last_tri.
+namespace {
+struct DistCtx
+{
+  const orc_bvh *A, *B;
+  double Rrel[9], Trel[3];
+  double rel_err, abs_err;
+  orc_distance_result *res;
+};
+
+void distance_recurse(DistCtx &cx, const double R[9], const double T[3], int b1, int b2)
+{
+  const orc_bvh *A = cx.A, *B = cx.B;
+  const double sz1 = bv_size(A, b1), sz2 = bv_size(B, b2);
+  const int l1 = A->first_child[b1] < 0, l2 = B->first_child[b2] < 0;
+  orc_distance_result *res = cx.res;
+  if (l1 && l2)
+  {
+    res->num_tri_tests++;
+    double p[3], q[3];
+    const int ta = -A->first_child[b1] - 1, tb = -B->first_child[b2] - 1;
+    const double d = orc_tri_distance(cx.Rrel, cx.Trel, &A->tris[9 * ta], &B->tris[9 * tb], p, q);
+    if (d < res->distance)
+    {
+      res->distance = d;
+      res->tri_a = ta; res->tri_b = tb;
+      v_cpy(res->p1, p); v_cpy(res->p2, q);
+    }
+    return;
+  }
+  int a1, a2, c1, c2;
+  double R1[9], T1[3], R2[9], T2[3], Tt[3];
+  if (l2 || (!l1 && (sz1 > sz2)))
+  {
+    a1 = A->first_child[b1]; a2 = b2; c1 = a1 + 1; c2 = b2;
+    mt_m(R1, &A->R[9 * a1], R); v_sub(Tt, T, &A->Tr[3 * a1]); mt_v(T1, &A->R[9 * a1], Tt);
+    mt_m(R2, &A->R[9 * c1], R); v_sub(Tt, T, &A->Tr[3 * c1]); mt_v(T2, &A->R[9 * c1], Tt);
+  }
+  else
+  {
+    a1 = b1; a2 = B->first_child[b2]; c1 = b1; c2 = a2 + 1;
+    m_m(R1, R, &B->R[9 * a2]); m_v_p(T1, R, &B->Tr[3 * a2], T);
+    m_m(R2, R, &B->R[9 * c2]); m_v_p(T2, R, &B->Tr[3 * c2], T);
+  }
+  res->num_bv_tests += 2;
+  double S[3];
+  const double d1 = bv_distance(R1, T1, A, a1, B, a2, S);
+  const double d2 = bv_distance(R2, T2, A, c1, B, c2, S);
+#define CLOSER(d) (((d) < (res->distance - cx.abs_err)) || ((d) * (1 + cx.rel_err) < res->distance))
+  if (d2 < d1)
+  {
+    if (CLOSER(d2)) distance_recurse(cx, R2, T2, c1, c2);
+    if (CLOSER(d1)) distance_recurse(cx, R1, T1, a1, a2);
+  }
+  else
+  {
+    if (CLOSER(d1)) distance_recurse(cx, R1, T1, a1, a2);
+    if (CLOSER(d2)) distance_recurse(cx, R2, T2, c1, c2);
+  }
+#undef CLOSER
+}
+}  // namespace
+
+extern "C" void orc_distance(const orc_bvh *A, const orc_bvh *B, const double pose24[24], int32_t seedA, int32_t seedB,
+                             double rel_err, double abs_err, orc_distance_result *res)
+{
+  DistCtx cx;
+  cx.A = A; cx.B = B; cx.rel_err = rel_err; cx.abs_err = abs_err; cx.res = res;
+  const double *R1 = &pose24[0], *T1 = &pose24[9], *R2 = &pose24[12], *T2 = &pose24[21];
+  double Tt[3], Rt[9], R[9], T[3], p[3], q[3];
+  mt_m(cx.Rrel, R1, R2);
+  v_sub(Tt, T2, T1);
+  mt_v(cx.Trel, R1, Tt);
+  res->distance = orc_tri_distance(cx.Rrel, cx.Trel, &A->tris[9 * seedA], &B->tris[9 * seedB], p, q);
+  res->tri_a = seedA; res->tri_b = seedB;
+  v_cpy(res->p1, p); v_cpy(res->p2, q);
+  res->num_bv_tests = 0; res->num_tri_tests = 0;
+  m_m(Rt, cx.Rrel, &B->R[0]);
+  mt_m(R, &A->R[0], Rt);
+  m_v_p(Tt, cx.Rrel, &B->Tr[0], cx.Trel);
+  v_sub(Tt, Tt, &A->Tr[0]);
+  mt_v(T, &A->R[0], Tt);
+  distance_recurse(cx, R, T, 0, 0);
+  // res->p2 is in cs 1; transform it to cs 2 (:1046-1048)
+  double u[3];
+  v_sub(u, res->p2, cx.Trel);
+  mt_v(res->p2, cx.Rrel, u);
+}

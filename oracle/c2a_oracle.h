@@ -114,6 +114,18 @@ void orc_solve_batch(const orc_bvh *A, const orc_bvh *B, const double *poses, in
                      const int32_t *seedA, const int32_t *seedB, double tol_d, double tol_t,
                      orc_result *out, int32_t n_threads);
 
+/* C2A_Distance (C2A/src/C2A_PQP.cpp:970-1056), depth-first routine (qsize <= 2).  tri_a / tri_b: builder-order
+ * indices of the closest triangle pair (the reference reports Tri::id and leaves them in o->last_tri). */
+typedef struct orc_distance_result
+{
+  double distance;
+  double p1[3], p2[3]; /* closest points, each in its own model's frame */
+  int32_t tri_a, tri_b;
+  int32_t num_bv_tests, num_tri_tests;
+} orc_distance_result;
+void orc_distance(const orc_bvh *A, const orc_bvh *B, const double pose24[24], int32_t seedA, int32_t seedB,
+                  double rel_err, double abs_err, orc_distance_result *res);
+
 #ifdef __cplusplus
 }
 #endif

@@ -290,6 +290,25 @@ int64_t ref_solve_contacts(void *hA, void *hB, const double *poses48, int32_t se
   return nContact;
 }
 
+// The reference's C2A_Distance (C2A/src/C2A_PQP.cpp:970-1056) for one query; seeds go in through o->last_tri as
+// the reference expects, the closest pair comes back as builder-order indices (o->last_tri after the call).
+void ref_distance(void *hA, void *hB, const double *pose24, int32_t seedA, int32_t seedB, double rel_err, double abs_err,
+                  int32_t qsize, orc_distance_result *out)
+{
+  C2A_Model *A = (C2A_Model *)hA, *B = (C2A_Model *)hB;
+  PQP_REAL R1[3][3], T1[3], R2[3][3], T2[3];
+  pose_to_RT(pose24, R1, T1); pose_to_RT(pose24 + 12, R2, T2);
+  A->last_tri = A->GetTriangle(seedA);
+  B->last_tri = B->GetTriangle(seedB);
+  C2A_DistanceResult res;
+  C2A_Distance(&res, R1, T1, A, R2, T2, B, rel_err, abs_err, qsize);
+  out->distance = res.distance;
+  for (int k = 0; k < 3; k++) { out->p1[k] = res.p1[k]; out->p2[k] = res.p2[k]; }
+  out->tri_a = (int)((C2A_Tri *)A->last_tri - (C2A_Tri *)A->tris);
+  out->tri_b = (int)((C2A_Tri *)B->last_tri - (C2A_Tri *)B->tris);
+  out->num_bv_tests = res.num_bv_tests; out->num_tri_tests = res.num_tri_tests;
+}
+
 // ---- unit-level entry points for pinning the port / the device functions ----
 double ref_rect_dist(const double Rab[9], const double Tab[3], const double a[2], const double b[2], double P[3],
                      double Q[3], double S[3])

@@ -132,6 +132,19 @@ int main(int argc, char **argv)
     if (is_free != whole_free || toc != whole || sr.numCA != whole_ca || dist != whole_dist) step_bad++;
   }
   printf("STEP_MISMATCH %d\n", step_bad);
+
+  // C2A_Distance at each frame's start poses, the way PQP is used: the models' last_tri carries from call to call
+  object1_tested->last_tri = object1_tested->tris; object2_tested->last_tri = object2_tested->tris;
+  for (int f = 0; f < nframes && f < 24; f++)
+  {
+    PQP_REAL R1[3][3], T1[3], R2[3][3], T2[3];
+    t00[f].Rotation().Get_Value(R1); t00[f].Translation().Get_Value(T1);
+    t10[f].Rotation().Get_Value(R2); t10[f].Translation().Get_Value(T2);
+    C2A_DistanceResult dr;
+    if (C2A_Distance(&dr, R1, T1, object1_tested, R2, T2, object2_tested, 0.0, 0.0) != PQP_OK) return 8;
+    printf("D %a %d %d %d %d %a %a %a %a %a %a\n", dr.Distance(), dr.t1, dr.t2, dr.NumBVTests(), dr.NumTriTests(), dr.P1()[0], dr.P1()[1],
+           dr.P1()[2], dr.P2()[0], dr.P2()[1], dr.P2()[2]);
+  }
   delete[] cf;
   delete object1_tested;
   delete object2_tested;

@@ -93,9 +93,30 @@ def translation_fixtures(R, bunny):
                  {"seed_a": sa, "seed_b": sb, "last_tri": np.stack([res["last_tri_a"], res["last_tri_b"]], 1)})
 
 
+def distance_fixture(R):
+    """The reference's C2A_Distance (C2A_PQP.cpp:970-1056, depth-first routine) on static pose pairs, random seeds."""
+    tris, vi = meshes.torus_knot(128, 16)
+    a, b = R.model(tris, vi), R.model(tris, vi)  # two objects: the query reads and writes each model's last_tri
+    n = 400
+    poses24 = workloads.static_pose_batch(n, 20260021, radius=workloads.KNOT_RADIUS)
+    rng = np.random.default_rng(9)
+    sa = rng.integers(0, a.n_tris, n).astype(np.int32); sb = rng.integers(0, b.n_tris, n).astype(np.int32)
+    out = {"poses24": poses24, "seed_a": sa, "seed_b": sb}
+    for tag, rel, ab in (("exact", 0.0, 0.0), ("approx", 0.25, 2.0)):
+        r = R.distance(a, b, poses24, sa, sb, rel, ab)
+        for k in r.dtype.names:
+            out[f"{tag}_{k}"] = r[k]
+        out[f"{tag}_err"] = np.array([rel, ab])
+        print(f"ref_distance_knot_128x16 {tag}: touching {int((r['distance'] == 0).sum())}/{n} mean nbv {r['num_bv_tests'].mean():.0f}")
+    np.savez_compressed(os.path.join(HERE, "ref_distance_knot_128x16.npz"), **out)
+
+
 def main():
     oracle.build_oracle()
     R = oracle.ref()
+    if "--only-distance" in sys.argv:
+        distance_fixture(R)
+        return
     if "--only-translation" in sys.argv:
         m = np.load(os.path.join(HERE, "bunny_mesh.npz"))
         translation_fixtures(R, R.model(m["verts"][m["vidx"]].reshape(-1, 9).copy(), m["vidx"]))
@@ -186,6 +207,7 @@ def main():
     print(f"ref_contacts_knot_128x16.npz: {nq} queries, {int(np.sum(counts))} contacts, max {int(np.max(counts))}")
 
     translation_fixtures(R, bunny)
+    distance_fixture(R)
 
     with open(os.path.join(HERE, "bvh_digest.json"), "w") as f:
         json.dump(digests, f, indent=1, sort_keys=True)

@@ -166,6 +166,25 @@ def test_translation_mixed_batch_and_device_entry(models, bvhs):
         assert np.array_equal(v.cpu().numpy(), got[k]), k
 
 
+@pytest.mark.parametrize("tag", ["exact", "approx"])
+def test_distance_query_bit_exact(tag, golden, models, bvhs):
+    """Batched C2A_Distance (c2a_distance_kernel) against the reference's object code, and on fresh inputs against the port."""
+    g = golden("ref_distance_knot_128x16")
+    rel, ab = g[f"{tag}_err"]
+    m = models("knot_128x16")
+    got = api.distance_batch(m, m, g["poses24"], g["seed_a"], g["seed_b"], rel, ab)
+    assert np.array_equal(got["distance"], g[f"{tag}_distance"])
+    assert np.array_equal(got["p1p2"], np.concatenate([g[f"{tag}_p1"], g[f"{tag}_p2"]], 1))
+    assert np.array_equal(got["tri_pair"], np.stack([g[f"{tag}_tri_a"], g[f"{tag}_tri_b"]], 1))
+    assert np.array_equal(got["num_bv_tests"], g[f"{tag}_num_bv_tests"]) and np.array_equal(got["num_tri_tests"], g[f"{tag}_num_tri_tests"])
+    poses = workloads.static_pose_batch(257, 99, radius=workloads.KNOT_RADIUS)
+    ref = oracle.port().distance(bvhs("knot_128x16"), bvhs("knot_128x16"), poses, None, None, rel, ab)
+    got = api.distance_batch(m, m, poses, None, None, rel, ab)
+    assert np.array_equal(got["distance"], ref["distance"]) and np.array_equal(got["num_bv_tests"], ref["num_bv_tests"])
+    assert np.array_equal(got["tri_pair"], np.stack([ref["tri_a"], ref["tri_b"]], 1))
+    assert api.distance_batch(m, m, np.zeros((0, 24)))["distance"].shape == (0,)
+
+
 def test_fresh_batch_against_oracle_port(models, bvhs):
     """Inputs that are in no fixture: GPU vs the oracle port run here, bit-exact."""
     poses = workloads.approach_batch(300, 777, radius=workloads.KNOT_RADIUS, max_turn=3.1)

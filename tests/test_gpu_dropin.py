@@ -59,3 +59,21 @@ def test_cpp_dropin_matches_reference_fixture(tmp_path, golden):
             assert [float.fromhex(x) for x in r[12:21]] == list(g["pose_toc"][i][:9])
     assert "BATCH_MISMATCH 0" in out.stdout
     assert "STEP_MISMATCH 0" in out.stdout
+    # C2A_Distance at the first 24 start poses, last_tri carried from call to call: against the oracle port
+    import oracle
+    from c2a_b200 import api
+    tris, _ = meshes.torus_knot(128, 16)
+    bvh = api.build_bvh(tris)
+    ids = np.asarray(bvh["tri_ids"]) if "tri_ids" in bvh else None
+    drows = [l.split() for l in out.stdout.splitlines() if l.startswith("D ")]
+    assert len(drows) == 24
+    sa = sb = 0
+    for i, r in enumerate(drows):
+        pose = np.concatenate([g["poses"][i][0:12], g["poses"][i][24:36]])
+        ref = oracle.port().distance(bvh, bvh, pose[None], [sa], [sb])[0]
+        assert float.fromhex(r[1]) == ref["distance"]
+        assert int(r[4]) == ref["num_bv_tests"] and int(r[5]) == ref["num_tri_tests"]
+        assert [float.fromhex(x) for x in r[6:12]] == list(ref["p1"]) + list(ref["p2"])
+        if ids is not None:
+            assert int(r[2]) == ids[ref["tri_a"]] and int(r[3]) == ids[ref["tri_b"]]
+        sa, sb = int(ref["tri_a"]), int(ref["tri_b"])

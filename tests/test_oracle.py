@@ -172,6 +172,20 @@ def test_port_translation_matches_ref_fresh_and_mixed(bvhs):
     assert (ref["numCA"] == 0).sum() == 60
 
 
+@pytest.mark.parametrize("tag", ["exact", "approx"])
+def test_port_distance_matches_golden(tag, golden, bvhs):
+    """C2A_Distance (C2A_PQP.cpp:970-1056, depth-first routine): the port against the reference's object code."""
+    g = golden("ref_distance_knot_128x16")
+    rel, ab = g[f"{tag}_err"]
+    out = oracle.port().distance(bvhs("knot_128x16"), bvhs("knot_128x16"), g["poses24"], g["seed_a"], g["seed_b"], rel, ab)
+    for k in out.dtype.names:
+        assert np.array_equal(out[k], g[f"{tag}_{k}"]), (tag, k)
+    assert (g[f"{tag}_distance"] == 0).sum() > 20 and (g[f"{tag}_distance"] > 1).sum() > 20
+    if tag == "approx":  # both bounds non-zero: fewer BV tests, distance within the bounds of the exact one
+        assert g["approx_num_bv_tests"].sum() < g["exact_num_bv_tests"].sum()
+        assert (g["approx_distance"] >= g["exact_distance"]).all()
+
+
 def test_golden_fixtures_are_sane(golden):
     """Verdict semantics: toc == 0 for free queries, hits end within tolerance."""
     for case, _, _ in GOLDEN_CASES:
