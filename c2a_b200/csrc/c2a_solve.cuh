@@ -50,7 +50,13 @@ struct DevModel
 };
 
 constexpr int ENTRY_DOUBLES = 16;  // R(9) T(3) d mint {b1,b2} pad  -> 128 B
-constexpr int WARPS_PER_BLOCK = 4;
+#ifndef C2A_WPB
+#define C2A_WPB 4
+#endif
+#ifndef C2A_MINB
+#define C2A_MINB 2
+#endif
+constexpr int WARPS_PER_BLOCK = C2A_WPB;
 constexpr int BLOCK_THREADS = 32 * WARPS_PER_BLOCK;
 #ifndef C2A_Q
 #define C2A_Q 48
@@ -166,7 +172,7 @@ __device__ __noinline__ void motion_pose_nl(const double *rec, double t, double 
   motion_pose(m, t, R, T);
 }
 
-__global__ void __launch_bounds__(BLOCK_THREADS, 2) c2a_solve_kernel(const BatchArgs args)
+__global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(const BatchArgs args)
 {
   extern __shared__ double smem[];
   const unsigned FULL = 0xffffffffu;
