@@ -6,7 +6,7 @@ g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file_
 bvh = api.build_bvh(meshes.torus_knot(512, 32)[0]); model = api.Model(bvh, 0)
 i = int(np.argmax(g["num_bv_tests"])); f = ("status", "num_bv_tests", "num_tri_tests", "num_ca")
 api.solve_batch(model, model, g["poses"][:64], fields=f)
-L = api.lib(); st = (C.c_uint64 * 11)()
+L = api.lib(); st = (C.c_uint64 * 20)()
 L.c2a_b200_phase_stats(1, None)
 t = time.time(); out = api.solve_batch(model, model, g["poses"][i:i + 1], fields=f); dt = time.time() - t
 L.c2a_b200_phase_stats(1, st); s = list(st)

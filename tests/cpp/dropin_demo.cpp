@@ -145,6 +145,29 @@ int main(int argc, char **argv)
     printf("D %a %d %d %d %d %a %a %a %a %a %a\n", dr.Distance(), dr.t1, dr.t2, dr.NumBVTests(), dr.NumTriTests(), dr.P1()[0], dr.P1()[1],
            dr.P1()[2], dr.P2()[0], dr.P2()[1], dr.P2()[2]);
   }
+
+  // pure translations through C2A_Solve (the reference's translation-only branch): optional 4th/5th arguments =
+  // a pose file and a count; seeds are triangle 0 of each model, as the fixture was generated
+  if (argc >= 6)
+  {
+    const int nt2 = atoi(argv[5]);
+    FILE *ft = fopen(argv[4], "r");
+    std::vector<double> tp(48 * nt2);
+    for (int i = 0; i < 48 * nt2; i++) if (!ft || fscanf(ft, "%lf", &tp[i]) != 1) return 9;
+    fclose(ft);
+    for (int f = 0; f < nt2; f++)
+    {
+      Transform a0, a1, b0, b1, o0, o1;
+      set_transform(a0, &tp[48 * f]); set_transform(a1, &tp[48 * f + 12]);
+      set_transform(b0, &tp[48 * f + 24]); set_transform(b1, &tp[48 * f + 36]);
+      C2A_TimeOfContactResult tr;
+      tr.last_triA = object1_tested->tris; tr.last_triB = object2_tested->tris;
+      PQP_REAL toc; int nItr, NTr;
+      if (C2A_Solve(&a0, &a1, object1_tested, &b0, &b1, object2_tested, o0, o1, toc, nItr, NTr, 0.0, tr) != TOCFound) return 10;
+      printf("T %d %a %a %d %d %d %d %d %d\n", tr.collisionfree ? 1 : 0, toc, tr.Distance(), nItr, tr.NumBVTests(), tr.NumTriTests(), NTr,
+             (int)((C2A_Tri *)tr.last_triA - object1_tested->tris), (int)((C2A_Tri *)tr.last_triB - object2_tested->tris));
+    }
+  }
   delete[] cf;
   delete object1_tested;
   delete object2_tested;

@@ -33,8 +33,13 @@ def test_cpp_dropin_matches_reference_fixture(tmp_path, golden):
     lib = os.path.join(ROOT, "c2a_b200", "csrc")
     subprocess.run(["g++", "-std=c++14", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests/cpp/dropin_demo.cpp"),
                     "-o", str(exe), "-L" + lib, "-lc2a_b200", "-Wl,-rpath," + lib], check=True)
-    out = subprocess.run([str(exe), str(tmp_path / "mesh.txt"), str(tmp_path / "poses.txt"), str(n)], capture_output=True, text=True,
-                         timeout=600)
+    gt = golden("ref_translation_knot_128x16")  # pure translations: C2A_Solve takes the translation-only branch
+    nt = 40
+    with open(tmp_path / "tposes.txt", "w") as f:
+        for p in gt["poses"][:nt]:
+            f.write(" ".join("%.17g" % x for x in p) + "\n")
+    out = subprocess.run([str(exe), str(tmp_path / "mesh.txt"), str(tmp_path / "poses.txt"), str(n), str(tmp_path / "tposes.txt"), str(nt)],
+                         capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "end model" not in out.stdout and "dres.distance" not in out.stdout  # the drop-in does not print
     rows = [l.split() for l in out.stdout.splitlines() if l.startswith("F ")]
@@ -59,6 +64,13 @@ def test_cpp_dropin_matches_reference_fixture(tmp_path, golden):
             assert [float.fromhex(x) for x in r[12:21]] == list(g["pose_toc"][i][:9])
     assert "BATCH_MISMATCH 0" in out.stdout
     assert "STEP_MISMATCH 0" in out.stdout
+    trows = [l.split() for l in out.stdout.splitlines() if l.startswith("T ")]
+    assert len(trows) == nt
+    for i, r in enumerate(trows):
+        assert int(r[1]) == gt["collisionfree"][i] and float.fromhex(r[2]) == gt["toc"][i] and float.fromhex(r[3]) == gt["distance"][i]
+        assert int(r[4]) == 0 and int(r[5]) == gt["num_bv_tests"][i] and int(r[6]) == gt["num_tri_tests"][i]
+        assert int(r[7]) == gt["num_contact"][i]  # number_of_contact of the full, unmodified C2A_Solve
+        assert [int(r[8]), int(r[9])] == list(gt["last_tri"][i])
     # C2A_Distance at the first 24 start poses, last_tri carried from call to call: against the oracle port
     import oracle
     from c2a_b200 import api

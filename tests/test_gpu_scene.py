@@ -39,6 +39,10 @@ def test_scene_pairs_match_oracle(models, bvhs):
     pairs = api.broadphase(sc["begin"][:, 9:], sc["end"][:, 9:], radii[sc["model"]])
     assert len(pairs) > 200
     poses, ma, mb = workloads.scene_queries(sc, pairs)
+    # every 7th candidate becomes a pure translation of both bodies (end rotation = start rotation): those queries
+    # take the reference's translation-only branch, here through the per-group claim-order indirection
+    poses[::7, 12:21] = poses[::7, 0:9]
+    poses[::7, 36:45] = poses[::7, 24:33]
     rng = np.random.default_rng(3)
     ntri = np.array([bvhs(n)["tris"].shape[0] for n in names])
     sa = rng.integers(0, ntri[ma]).astype(np.int32)
@@ -57,6 +61,7 @@ def test_scene_pairs_match_oracle(models, bvhs):
             assert np.array_equal(got["last_tri"][g, 0], ref["last_tri_a"]) and np.array_equal(got["last_tri"][g, 1], ref["last_tri_b"])
             seen += 1
     assert seen == 4
+    assert (got["num_ca"][::7] == 0).all() and (np.delete(got["num_ca"], np.s_[::7]) >= 1).all()
     hits = (got["collisionfree"] == 0).sum()
     assert 0 < hits < len(pairs)  # the broadphase is conservative: some candidates are free, some collide
 
