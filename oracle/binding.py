@@ -31,6 +31,12 @@ DISTANCE_DTYPE = np.dtype([("distance", np.float64), ("p1", np.float64, 3), ("p2
                            ("tri_b", np.int32), ("num_bv_tests", np.int32), ("num_tri_tests", np.int32)], align=True)
 
 
+SPEC_STATS_DTYPE = np.dtype([("steps", np.int64), ("tasks", np.int64), ("reached", np.int64), ("valid", np.int64),
+                             ("work_seq", np.int64), ("work_fallback", np.int64), ("work_wasted", np.int64),
+                             ("work_max_task", np.int64), ("work_top", np.int64), ("par_time", np.float64, 3),
+                             ("depth", np.int32)], align=True)
+
+
 class _Bvh(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("n_tris", C.c_int32),
                 ("R", C.c_void_p), ("Tr", C.c_void_p), ("l", C.c_void_p), ("r", C.c_void_p),
@@ -99,6 +105,18 @@ class _Port:
                                  _ptr(seedB) if seedB is not None else None,
                                  C.c_double(tol_d), C.c_double(tol_t), _ptr(out), C.c_int32(threads))
         return out
+
+    def solve_spec(self, bvhA, bvhB, poses, K, tol_d=1e-4, tol_t=1e-4):
+        """Round-2 design study: every exact-mode CA step through the speculative subtree split at frontier depth K.
+        Returns (results like solve_batch, dict of accumulated statistics)."""
+        sA, sB = bvh_struct(bvhA), bvh_struct(bvhB)
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 48)
+        out = np.zeros(len(poses), dtype=RESULT_DTYPE)
+        st = np.zeros(1, dtype=SPEC_STATS_DTYPE)
+        for i in range(len(poses)):
+            self.lib.orc_solve_spec(C.byref(sA), C.byref(sB), _ptr(poses[i]), C.c_int32(0), C.c_int32(0), C.c_double(tol_d),
+                                    C.c_double(tol_t), C.c_int32(K), C.c_void_p(out[i:i + 1].ctypes.data), _ptr(st))
+        return out, {k: (st[k][0].tolist() if st[k].ndim > 1 else st[k][0].item()) for k in st.dtype.names}
 
     def contacts(self, bvhA, bvhB, pose1, pose2, threshold, vidx_a=None, vidx_b=None, max_out=4096):
         """Contact pass at the given poses; records in visiting order. Returns (count, records)."""

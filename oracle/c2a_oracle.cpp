@@ -587,7 +587,11 @@ extern "C" double orc_motion_bound_leaf(const orc_motion *m, double ang_radius, 
 }
 
 // ---- traversal + CA loop -----------------------------------------------------
+static thread_local orc_spec_stats *g_spec = nullptr;  // non-NULL: exact-mode steps run the speculative split (design study below)
+static thread_local double g_spec_prev = -1;
 namespace {
+struct Step;
+void spec_step(Step &st, const double R[9], const double T[3]);
 struct Step
 {
   const orc_bvh *A, *B;
@@ -711,6 +715,250 @@ void toc_recurse(Step &st, const double R[9], const double T[3], int b1, int b2)
 #undef DESCEND
 }
 
+// ---- design study for round 2 (TEST INFRASTRUCTURE): a CA step's traversal split into subtrees that are
+// evaluated independently under a GUESSED entry distance and stitched back exactly ------------------------------
+// The traversal's control flow depends on the running distance only through comparisons (descend: d < dist;
+// leaf: dTri <= dist).  A subtree run records, for as long as its distance is still the entry value, the interval
+// of entry values under which every one of those comparisons has the outcome it had; once a leaf inside lowers the
+// distance, later comparisons no longer involve the entry value.  If the true entry distance (known when the
+// sequential order reaches the subtree) lies in that interval, the recorded outcome -- exit distance, folded step
+// bound, counters, last improving triangle pair -- IS the sequential one; otherwise the subtree is re-run.
+// Exact mode only (abs_err = rel_err = 0: every step of a long query past its fifth).
+struct SpecOut
+{
+  double exit_dist; bool updated;
+  double mint;
+  int last_a, last_b; double p1[3], p2[3];
+  int nbv, ntri;
+  double gt, ge, le, lt;  // valid iff entry > gt && entry >= ge && entry <= le && entry < lt
+  long long work;
+};
+
+struct SpecRun
+{
+  Step *st;            // shared read-only context (models, motions, Rrel/Trel, upbound)
+  double dist; bool at_entry;
+  SpecOut *o;
+};
+
+// the two child tests of an expansion: pure functions of (pair, transform, poses), C2A.cpp:1192-1276
+struct Kids { int a1, a2, c1, c2; double R1[9], T1[3], R2[9], T2[3], d1, d2, mt1, mt2; };
+void expand_pair(const Step &st, const double R[9], const double T[3], int b1, int b2, Kids &k)
+{
+  const orc_bvh *A = st.A, *B = st.B;
+  const double *r1 = st.m1->Rc;
+  const int l1 = A->first_child[b1] < 0, l2 = B->first_child[b2] < 0;
+  double Tt[3];
+  double sz1 = bv_size(A, b1), sz2 = bv_size(B, b2);
+  if (l2 || (!l1 && (sz1 > sz2)))
+  {
+    k.a1 = A->first_child[b1]; k.a2 = b2; k.c1 = k.a1 + 1; k.c2 = b2;
+    mt_m(k.R1, &A->R[9 * k.a1], R); v_sub(Tt, T, &A->Tr[3 * k.a1]); mt_v(k.T1, &A->R[9 * k.a1], Tt);
+    mt_m(k.R2, &A->R[9 * k.c1], R); v_sub(Tt, T, &A->Tr[3 * k.c1]); mt_v(k.T2, &A->R[9 * k.c1], Tt);
+  }
+  else
+  {
+    k.a1 = b1; k.a2 = B->first_child[b2]; k.c1 = b1; k.c2 = k.a2 + 1;
+    m_m(k.R1, R, &B->R[9 * k.a2]); m_v_p(k.T1, R, &B->Tr[3 * k.a2], T);
+    m_m(k.R2, R, &B->R[9 * k.c2]); m_v_p(k.T2, R, &B->Tr[3 * k.c2], T);
+  }
+  double S1[3], S2[3], tmp[3];
+  k.d1 = bv_distance(k.R1, k.T1, A, k.a1, B, k.a2, S1);
+  if (k.d1 != 0.0)
+  {
+    m_v(tmp, &A->R_loc[9 * k.a1], S1); m_v(S1, r1, tmp);
+    S2[0] = S1[0] * -1; S2[1] = S1[1] * -1; S2[2] = S1[2] * -1;
+    double mb1 = orc_motion_bound_bv(st.m1, A->ang_radius[k.a1], S1);
+    double mb2 = orc_motion_bound_bv(st.m2, B->ang_radius[k.a2], S2);
+    k.mt1 = (k.d1) / (mb1 + mb2);
+    if (k.mt1 <= 0) k.mt1 = 0.0;
+  }
+  else k.mt1 = 0.0;
+  k.d2 = bv_distance(k.R2, k.T2, A, k.c1, B, k.c2, S1);
+  if (k.d2 != 0.0)
+  {
+    m_v(tmp, &A->R_loc[9 * k.c1], S1); m_v(S1, r1, tmp);
+    S2[0] = S1[0] * -1; S2[1] = S1[1] * -1; S2[2] = S1[2] * -1;
+    double mb1 = orc_motion_bound_bv(st.m1, A->ang_radius[k.c1], S1);
+    double mb2 = orc_motion_bound_bv(st.m2, B->ang_radius[k.c2], S2);
+    k.mt2 = (k.d2) / (mb1 + mb2);
+    if (k.mt2 <= 0) k.mt2 = 0.0;
+  }
+  else k.mt2 = 0.0;
+}
+
+void spec_recurse(SpecRun &r, const double R[9], const double T[3], int b1, int b2)
+{
+  const Step &st = *r.st;
+  const orc_bvh *A = st.A, *B = st.B;
+  SpecOut &o = *r.o;
+  o.work++;
+  const int l1 = A->first_child[b1] < 0, l2 = B->first_child[b2] < 0;
+  if (l1 && l2)
+  {
+    const double *r1 = st.m1->Rc, *tt1 = st.m1->Tc;
+    double p[3], q[3];
+    const double *t1 = &A->tris[9 * (-A->first_child[b1] - 1)];
+    const double *t2 = &B->tris[9 * (-B->first_child[b2] - 1)];
+    double dTri = orc_tri_distance(st.Rrel, st.Trel, t1, t2, p, q);
+    const bool take = dTri <= r.dist;
+    if (r.at_entry)
+    {
+      if (take) { if (dTri > o.ge) o.ge = dTri; }   // entry >= dTri
+      else if (dTri < o.lt) o.lt = dTri;            // entry <  dTri (a NaN dTri is never taken and constrains nothing)
+    }
+    if (take)
+    {
+      r.dist = dTri; r.at_entry = false;
+      o.exit_dist = dTri; o.updated = true;
+      double w1[3], w2[3], S1[3], S2[3], tmp[3];
+      m_v(tmp, r1, p); v_add(w1, tmp, tt1);
+      m_v(tmp, r1, q); v_add(w2, tmp, tt1);
+      v_sub(S1, w2, w1);
+      S2[0] = S1[0] * -1; S2[1] = S1[1] * -1; S2[2] = S1[2] * -1;
+      v_cpy(o.p1, p); v_cpy(o.p2, q);
+      double mb1 = orc_motion_bound_leaf(st.m1, A->ang_radius[b1], S1);
+      double mb2 = orc_motion_bound_leaf(st.m2, B->ang_radius[b2], S2);
+      double mint = (dTri) / (mb1 + mb2);
+      if (mint < 0.0) mint = 0.0;
+      if (mint <= o.mint) o.mint = mint;
+      o.last_a = -A->first_child[b1] - 1; o.last_b = -B->first_child[b2] - 1;
+    }
+    o.ntri++;
+    return;
+  }
+  Kids k;
+  expand_pair(st, R, T, b1, b2, k);
+  o.nbv += 2;
+  // exact mode: the descend test is mt < upbound && d < dist (d * (1 + 0) and dist - 0 are exact)
+  auto child = [&](double d, double mt, const double *Rc, const double *Tc, int n1, int n2) {
+    bool go = mt < st.upbound;
+    if (go)
+    {
+      const bool closer = d < r.dist;
+      if (r.at_entry)
+      {
+        if (closer) { if (d > o.gt) o.gt = d; }   // entry >  d
+        else if (d < o.le) o.le = d;              // entry <= d
+      }
+      go = closer;
+    }
+    if (go) spec_recurse(r, Rc, Tc, n1, n2);
+    else if (mt < o.mint) o.mint = mt;
+  };
+  if (k.d2 < k.d1) { child(k.d2, k.mt2, k.R2, k.T2, k.c1, k.c2); child(k.d1, k.mt1, k.R1, k.T1, k.a1, k.a2); }
+  else { child(k.d1, k.mt1, k.R1, k.T1, k.a1, k.a2); child(k.d2, k.mt2, k.R2, k.T2, k.c1, k.c2); }
+}
+
+struct SpecTask { double R[9], T[3]; int b1, b2; SpecOut out; bool reached; };
+// the top of the tree down to the frontier, evaluated once
+struct TopNode { int kid[2]; double d[2], mt[2]; int task; };
+
+int spec_build_top(Step &st, std::vector<TopNode> &top, std::vector<SpecTask> &tasks, const double R[9], const double T[3],
+                   int b1, int b2, int depth, int K)
+{
+  const orc_bvh *A = st.A, *B = st.B;
+  TopNode n; n.kid[0] = n.kid[1] = -1; n.task = -1; n.d[0] = n.d[1] = n.mt[0] = n.mt[1] = 0;
+  const int l1 = A->first_child[b1] < 0, l2 = B->first_child[b2] < 0;
+  const int id = (int)top.size();
+  top.push_back(n);
+  if ((l1 && l2) || depth == K)
+  {
+    SpecTask t; memcpy(t.R, R, 72); memcpy(t.T, T, 24); t.b1 = b1; t.b2 = b2; t.reached = false;
+    top[id].task = (int)tasks.size();
+    tasks.push_back(t);
+    return id;
+  }
+  Kids k;
+  expand_pair(st, R, T, b1, b2, k);
+  const bool c_first = k.d2 < k.d1;  // kid[0] = the child visited first
+  const double dd[2] = {c_first ? k.d2 : k.d1, c_first ? k.d1 : k.d2}, mm[2] = {c_first ? k.mt2 : k.mt1, c_first ? k.mt1 : k.mt2};
+  for (int j = 0; j < 2; j++)
+  {
+    top[id].d[j] = dd[j]; top[id].mt[j] = mm[j];
+    const bool isc = (j == 0) == c_first;
+    if (mm[j] < st.upbound)  // a child failing this is never descended, whatever the distance
+    {
+      const int kid = isc ? spec_build_top(st, top, tasks, k.R2, k.T2, k.c1, k.c2, depth + 1, K)
+                          : spec_build_top(st, top, tasks, k.R1, k.T1, k.a1, k.a2, depth + 1, K);
+      top[id].kid[j] = kid;
+    }
+  }
+  return id;
+}
+
+void spec_stitch(Step &st, std::vector<TopNode> &top, std::vector<SpecTask> &tasks, int id, orc_spec_stats &ss)
+{
+  if (top[id].task >= 0)
+  {
+    SpecTask &t = tasks[top[id].task];
+    t.reached = true;
+    SpecOut &o = t.out;
+    const double e = st.distance;
+    const bool valid = e > o.gt && e >= o.ge && e <= o.le && e < o.lt;
+    ss.reached++;
+    if (valid)
+    {
+      ss.valid++;
+      if (o.updated) { st.distance = o.exit_dist; v_cpy(st.p1, o.p1); v_cpy(st.p2, o.p2); st.last_a = o.last_a; st.last_b = o.last_b; }
+      if (o.mint < st.mint) st.mint = o.mint;
+      st.num_bv_tests += o.nbv; st.num_tri_tests += o.ntri;
+      ss.work_seq += o.work;
+    }
+    else
+    {
+      const int nbv0 = st.num_bv_tests, ntri0 = st.num_tri_tests;
+      toc_recurse(st, t.R, t.T, t.b1, t.b2);
+      const long long w = (st.num_bv_tests - nbv0) / 2 + (st.num_tri_tests - ntri0);
+      ss.work_seq += w; ss.work_fallback += w;
+    }
+    return;
+  }
+  st.num_bv_tests += 2;
+  ss.work_top++;
+  for (int j = 0; j < 2; j++)
+  {
+    const bool go = top[id].mt[j] < st.upbound && top[id].d[j] < st.distance;
+    if (go) spec_stitch(st, top, tasks, top[id].kid[j], ss);
+    else if (top[id].mt[j] < st.mint) st.mint = top[id].mt[j];
+  }
+}
+
+// one CA step in exact mode; on entry st.distance holds the seed distance and st.mint = 1
+void spec_step(Step &st, const double R[9], const double T[3])
+{
+  orc_spec_stats &ss = *g_spec;
+  std::vector<TopNode> top; std::vector<SpecTask> tasks;
+  spec_build_top(st, top, tasks, R, T, 0, 0, 0, ss.depth);
+  // the guess: the previous exact step's final distance (poses differ by one small advancement)
+  const double guess = (g_spec_prev >= 0 && g_spec_prev < st.distance) ? g_spec_prev : st.distance;
+  long long spec_total = 0, spec_max = 0;
+  for (auto &t : tasks)
+  {
+    SpecOut &o = t.out;
+    o.exit_dist = 0; o.updated = false; o.mint = 1e300; o.last_a = o.last_b = -1; o.nbv = o.ntri = 0; o.work = 0;
+    o.p1[0] = o.p1[1] = o.p1[2] = o.p2[0] = o.p2[1] = o.p2[2] = 0;
+    o.gt = -1e300; o.ge = -1e300; o.le = 1e300; o.lt = 1e300;
+    SpecRun r; r.st = &st; r.dist = guess; r.at_entry = true; r.o = &o;
+    spec_recurse(r, t.R, t.T, t.b1, t.b2);
+    spec_total += o.work; if (o.work > spec_max) spec_max = o.work;
+  }
+  const long long fb0 = ss.work_fallback, top0 = ss.work_top;
+  spec_stitch(st, top, tasks, 0, ss);
+  long long wasted = 0;
+  for (auto &t : tasks) if (!t.reached) wasted += t.out.work;
+  ss.steps++; ss.tasks += (long long)tasks.size(); ss.work_wasted += wasted;
+  if (spec_max > ss.work_max_task) ss.work_max_task = spec_max;
+  const long long fb = ss.work_fallback - fb0, tp = ss.work_top - top0;
+  const int P[3] = {8, 32, 128};
+  for (int j = 0; j < 3; j++)
+  {
+    const double par = (double)spec_total / P[j];
+    ss.par_time[j] += (double)top.size() / 16.0 + (par > (double)spec_max ? par : (double)spec_max) + (double)fb + (double)tp;
+  }
+  g_spec_prev = st.distance;
+}
+
 // C2A_TimeOfContactStep (rotational branch), C2A/src/C2A.cpp:1778-1931.
 // numCA / prev_mint carry res->numCA and the previous step's res->mint.
 void toc_step(Step &st, int numCA, int seedA, int seedB)
@@ -737,7 +985,8 @@ void toc_step(Step &st, int numCA, int seedA, int seedB)
     st.rel_err = (numCA <= 2) ? 3 : 0.5;
   }
   st.mint = 1;
-  toc_recurse(st, R, T, 0, 0);
+  if (g_spec && st.abs_err == 0 && st.rel_err == 0) spec_step(st, R, T);
+  else toc_recurse(st, R, T, 0, 0);
 }
 // ---- translation-only branch (both angular speeds < 1e-8, C2A.cpp:2391-2395) -------------------
 // Only objmotion1's velocity enters the inner advancement (the reference calls objmotion1->CAonRSS /
@@ -1305,4 +1554,15 @@ extern "C" void orc_distance(const orc_bvh *A, const orc_bvh *B, const double po
   double u[3];
   v_sub(u, res->p2, cx.Trel);
   mt_v(res->p2, cx.Rrel, u);
+}
+
+// Design study entry: orc_solve with every exact-mode CA step run through the speculative subtree split at
+// frontier depth K; results must equal orc_solve's bit for bit (tests/test_oracle.py), stats accumulate.
+extern "C" void orc_solve_spec(const orc_bvh *A, const orc_bvh *B, const double poses[48], int32_t seedA, int32_t seedB,
+                               double tol_d, double tol_t, int32_t K, orc_result *out, orc_spec_stats *stats)
+{
+  stats->depth = K;
+  g_spec = stats; g_spec_prev = -1;
+  orc_solve(A, B, poses, seedA, seedB, tol_d, tol_t, out);
+  g_spec = nullptr;
 }

@@ -126,6 +126,18 @@ typedef struct orc_distance_result
 void orc_distance(const orc_bvh *A, const orc_bvh *B, const double pose24[24], int32_t seedA, int32_t seedB,
                   double rel_err, double abs_err, orc_distance_result *res);
 
+/* Round-2 design study (test infrastructure): a CA step split into subtrees run under a guessed entry distance with a
+ * recorded validity interval, stitched back in the reference's order.  Work is counted in node-pair visits. */
+typedef struct orc_spec_stats
+{
+  long long steps, tasks, reached, valid;      /* exact-mode steps, frontier subtrees, those the sequential order reaches, those whose guess held */
+  long long work_seq, work_fallback, work_wasted, work_max_task, work_top;
+  double par_time[3];                          /* estimated critical path with 8 / 32 / 128 workers */
+  int32_t depth;
+} orc_spec_stats;
+void orc_solve_spec(const orc_bvh *A, const orc_bvh *B, const double poses[48], int32_t seedA, int32_t seedB, double tol_d,
+                    double tol_t, int32_t K, orc_result *out, orc_spec_stats *stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -186,6 +186,18 @@ def test_port_distance_matches_golden(tag, golden, bvhs):
         assert (g["approx_distance"] >= g["exact_distance"]).all()
 
 
+def test_speculative_step_split_is_exact(golden, bvhs):
+    """Round-2 design study (oracle/c2a_oracle.cpp, orc_solve_spec): CA steps split into subtrees run under a guessed entry
+    distance + validity interval and stitched in the reference's order reproduce the sequential result bit for bit."""
+    g = golden("ref_knot_128x16")
+    idx = np.argsort(-g["num_bv_tests"])[:12]
+    for K in (3, 7):
+        res, st = oracle.port().solve_spec(bvhs("knot_128x16"), bvhs("knot_128x16"), g["poses"][idx], K)
+        for k in ("collisionfree", "numCA", "num_bv_tests", "num_tri_tests", "toc", "distance", "mint", "pose_toc"):
+            assert np.array_equal(res[k], g[k][idx]), (K, k)
+        assert st["steps"] > 50 and 0 < st["valid"] < st["reached"]  # both the accepted and the re-run path are exercised
+
+
 def test_golden_fixtures_are_sane(golden):
     """Verdict semantics: toc == 0 for free queries, hits end within tolerance."""
     for case, _, _ in GOLDEN_CASES:
