@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(128) c2a_contact_kernel(const ContactArgs args
           // :1544-1636
           const int ta = -ma.first_child - 1, tb = -mb.first_child - 1;
           double t1[9], t2[9], tri2[9], p[3], qq[3];
-          load9(t1, A.tris + (size_t)9 * ta);
-          load9(t2, B.tris + (size_t)9 * tb);
+          load9v(t1, A.tris + (size_t)TRI_STRIDE * ta);
+          load9v(t2, B.tris + (size_t)TRI_STRIDE * tb);
           m_v_p(&tri2[0], Rrel, &t2[0], Trel); m_v_p(&tri2[3], Rrel, &t2[3], Trel); m_v_p(&tri2[6], Rrel, &t2[6], Trel);
           int f1t = -1, f1f = 0, f2t = -1, f2f = 0;
           const double d = tri_dist_features(p, qq, t1, tri2, f1t, f1f, f2t, f2f);
@@ -123,9 +123,9 @@ __global__ void __launch_bounds__(128) c2a_contact_kernel(const ContactArgs args
           a1 = ma.first_child; a2 = b2; c1 = a1 + 1; c2 = b2;
           ga = A.geom + (size_t)a1 * GEOM_STRIDE; gc = ga + GEOM_STRIDE; gb_a = gb_c = B.geom + (size_t)b2 * GEOM_STRIDE;
           double Rn[9], Tn[3];
-          load9(Rn, ga); load3(Tn, ga + 9);
+          load_node_rt(Rn, Tn, ga);
           mt_m(Ra, Rn, R); v_sub(Tt, T, Tn); mt_v(Ta, Rn, Tt);
-          load9(Rn, gc); load3(Tn, gc + 9);
+          load_node_rt(Rn, Tn, gc);
           mt_m(Rc, Rn, R); v_sub(Tt, T, Tn); mt_v(Tc, Rn, Tt);
         }
         else
@@ -133,9 +133,9 @@ __global__ void __launch_bounds__(128) c2a_contact_kernel(const ContactArgs args
           a1 = b1; a2 = mb.first_child; c1 = b1; c2 = a2 + 1;
           ga = gc = A.geom + (size_t)b1 * GEOM_STRIDE; gb_a = B.geom + (size_t)a2 * GEOM_STRIDE; gb_c = gb_a + GEOM_STRIDE;
           double Rn[9], Tn[3];
-          load9(Rn, gb_a); load3(Tn, gb_a + 9);
+          load_node_rt(Rn, Tn, gb_a);
           m_m(Ra, R, Rn); m_v_p(Ta, R, Tn, T);
-          load9(Rn, gb_c); load3(Tn, gb_c + 9);
+          load_node_rt(Rn, Tn, gb_c);
           m_m(Rc, R, Rn); m_v_p(Tc, R, Tn, T);
         }
         double d1 = rss_rect_dist(Ra, Ta, __ldg(ga + 12), __ldg(ga + 13), __ldg(gb_a + 12), __ldg(gb_a + 13), S);

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(128) c2a_distance_kernel(const DistanceArgs ar
     int ta = args.seedA ? args.seedA[q] : 0, tb = args.seedB ? args.seedB[q] : 0;
     double p1[3], p2[3];
     // initial upper bound from the last closest triangle pair, :995-1000
-    double dist = tri_distance_nl(Rrel, Trel, A.tris + (size_t)9 * ta, B.tris + (size_t)9 * tb, p1, p2);
+    double dist = tri_distance_v(Rrel, Trel, A.tris + (size_t)TRI_STRIDE * ta, B.tris + (size_t)TRI_STRIDE * tb, p1, p2);
     // root pair, :1016-1027
 #pragma unroll
     for (int i = 0; i < 12; i++) { g1[i] = __ldg(A.geom + i); g2[i] = __ldg(B.geom + i); }
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128) c2a_distance_kernel(const DistanceArgs ar
         ntri++;
         const int t1 = -ma.first_child - 1, t2 = -mb.first_child - 1;
         double p[3], qq[3];
-        const double d = tri_distance_nl(Rrel, Trel, A.tris + (size_t)9 * t1, B.tris + (size_t)9 * t2, p, qq);
+        const double d = tri_distance_v(Rrel, Trel, A.tris + (size_t)TRI_STRIDE * t1, B.tris + (size_t)TRI_STRIDE * t2, p, qq);
         if (d < dist)
         {
           dist = d; ta = t1; tb = t2;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128) c2a_distance_kernel(const DistanceArgs ar
           ids[c] = __hiloint2double(n1, b2);
           ga = A.geom + (size_t)n1 * GEOM_STRIDE; gb = B.geom + (size_t)b2 * GEOM_STRIDE;
           double Rn[9], Tn[3];
-          load9(Rn, ga); load3(Tn, ga + 9);
+          load_node_rt(Rn, Tn, ga);
           mt_m(Rch[c], Rn, R); v_sub(Tt, T, Tn); mt_v(Tch[c], Rn, Tt);
         }
         else
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(128) c2a_distance_kernel(const DistanceArgs ar
           ids[c] = __hiloint2double(b1, n2);
           ga = A.geom + (size_t)b1 * GEOM_STRIDE; gb = B.geom + (size_t)n2 * GEOM_STRIDE;
           double Rn[9], Tn[3];
-          load9(Rn, gb); load3(Tn, gb + 9);
+          load_node_rt(Rn, Tn, gb);
           m_m(Rch[c], R, Rn); m_v_p(Tch[c], R, Tn, T);
         }
         double S[3];

@@ -197,6 +197,11 @@ int c2a_b200_model_upload(const c2a_b200_bvh *bvh, int32_t device, c2a_b200_mode
     meta[i].pad = 0;
   }
 
+  // R_loc and the triangles as padded 80-byte records (128-bit loads on the device)
+  std::vector<double> rloc((size_t)n * RLOC_STRIDE, 0.0), tris((size_t)nt * TRI_STRIDE, 0.0);
+  for (int i = 0; i < n; i++) memcpy(&rloc[(size_t)i * RLOC_STRIDE], bvh->R_loc + 9 * (size_t)i, 9 * sizeof(double));
+  for (int i = 0; i < nt; i++) memcpy(&tris[(size_t)i * TRI_STRIDE], bvh->tris + 9 * (size_t)i, 9 * sizeof(double));
+
   CUDA_TRY(cudaSetDevice(device));
   c2a_b200_model *m = new c2a_b200_model();
   m->device = device; m->n_nodes = n; m->n_tris = nt; m->depth = depth;
@@ -204,13 +209,13 @@ int c2a_b200_model_upload(const c2a_b200_bvh *bvh, int32_t device, c2a_b200_mode
   m->geom = m->rloc = m->tris = nullptr; m->meta = nullptr; m->tri_vidx = nullptr;
   cudaError_t e;
   if ((e = cudaMalloc(&m->geom, geom.size() * sizeof(double))) != cudaSuccess ||
-      (e = cudaMalloc(&m->rloc, (size_t)n * 9 * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(&m->rloc, rloc.size() * sizeof(double))) != cudaSuccess ||
       (e = cudaMalloc(&m->meta, (size_t)n * sizeof(NodeMeta))) != cudaSuccess ||
-      (e = cudaMalloc(&m->tris, (size_t)nt * 9 * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(&m->tris, tris.size() * sizeof(double))) != cudaSuccess ||
       (e = cudaMemcpy(m->geom, geom.data(), geom.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
-      (e = cudaMemcpy(m->rloc, bvh->R_loc, (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(m->rloc, rloc.data(), rloc.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMemcpy(m->meta, meta.data(), (size_t)n * sizeof(NodeMeta), cudaMemcpyHostToDevice)) != cudaSuccess ||
-      (e = cudaMemcpy(m->tris, bvh->tris, (size_t)nt * 9 * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(m->tris, tris.data(), tris.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
       (bvh->tri_vidx && ((e = cudaMalloc(&m->tri_vidx, (size_t)nt * 3 * sizeof(int))) != cudaSuccess ||
                          (e = cudaMemcpy(m->tri_vidx, bvh->tri_vidx, (size_t)nt * 3 * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess)))
   {

@@ -35,10 +35,12 @@ namespace c2a {
 
 // ---- device-resident model ---------------------------------------------------------------
 // geom  [n][16]  R(9) Tr(3) l(2) r ang_radius      one 128-byte line per node; children adjacent
-// rloc  [n][9]   R_loc (only read when a BV distance is non-zero)
+// rloc  [n][10]  R_loc(9) pad (only read when a BV distance is non-zero)
 // meta  [n]      {GetSize() = sqrt(l0^2+l1^2)+2r precomputed (PQP BV::GetSize), first_child}
-// tris  [n][9]
+// tris  [n][10]  p1 p2 p3 pad
 constexpr int GEOM_STRIDE = 16;
+constexpr int RLOC_STRIDE = 10;   // R_loc(9) + pad: 80-byte records, so that they can be fetched with 128-bit loads
+constexpr int TRI_STRIDE = 10;    // p1 p2 p3 (9) + pad, likewise
 struct NodeMeta { double size; int first_child; int pad; };
 struct DevModel
 {
@@ -126,6 +128,29 @@ C2A_DEV void load9(double d[9], const double *s)
   for (int i = 0; i < 9; i++) d[i] = __ldg(s + i);
 }
 C2A_DEV void load3(double d[3], const double *s) { d[0] = __ldg(s); d[1] = __ldg(s + 1); d[2] = __ldg(s + 2); }
+// nine doubles of a 16-byte aligned, padded record (R_loc, triangle) with five 128-bit loads
+C2A_DEV void load9v(double d[9], const double *s)
+{
+  const double2 *s2 = reinterpret_cast<const double2 *>(s);
+  const double2 v0 = __ldg(s2), v1 = __ldg(s2 + 1), v2 = __ldg(s2 + 2), v3 = __ldg(s2 + 3), v4 = __ldg(s2 + 4);
+  d[0] = v0.x; d[1] = v0.y; d[2] = v1.x; d[3] = v1.y; d[4] = v2.x; d[5] = v2.y; d[6] = v3.x; d[7] = v3.y; d[8] = v4.x;
+}
+// R(9) + Tr(3) of a node record (128-byte aligned) with six 128-bit loads
+C2A_DEV void load_node_rt(double R[9], double T[3], const double *g)
+{
+  const double2 *g2 = reinterpret_cast<const double2 *>(g);
+  const double2 v0 = __ldg(g2), v1 = __ldg(g2 + 1), v2 = __ldg(g2 + 2), v3 = __ldg(g2 + 3), v4 = __ldg(g2 + 4), v5 = __ldg(g2 + 5);
+  R[0] = v0.x; R[1] = v0.y; R[2] = v1.x; R[3] = v1.y; R[4] = v2.x; R[5] = v2.y; R[6] = v3.x; R[7] = v3.y; R[8] = v4.x;
+  T[0] = v4.y; T[1] = v5.x; T[2] = v5.y;
+}
+// one 128-bit load of a node's {GetSize(), first_child}
+C2A_DEV NodeMeta load_meta(const NodeMeta *p)
+{
+  const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+  NodeMeta m;
+  m.size = v.x; m.first_child = __double2loint(v.y); m.pad = 0;
+  return m;
+}
 C2A_DEV unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 C2A_DEV void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -160,6 +185,16 @@ __device__ __noinline__ double tri_distance_nl(const double R[9], const double T
   double a[9], b[9];
   load9(a, t1);
   load9(b, t2);
+  return tri_distance(R, T, a, b, p, q);
+}
+
+// the same for triangles of an uploaded model (TRI_STRIDE records): 128-bit loads
+__device__ __noinline__ double tri_distance_v(const double R[9], const double T[3], const double *t1, const double *t2,
+                                              double p[3], double q[3])
+{
+  double a[9], b[9];
+  load9v(a, t1);
+  load9v(b, t2);
   return tri_distance(R, T, a, b, p, q);
 }
 
@@ -348,7 +383,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
             ma.size = SD(F_CURSZ1, slot); ma.first_child = SI(I_CURFC1, slot);
             mb.size = SD(F_CURSZ2, slot); mb.first_child = SI(I_CURFC2, slot);
           }
-          else { ma = A.meta[b1]; mb = B.meta[b2]; }
+          else { ma = load_meta(A.meta + b1); mb = load_meta(B.meta + b2); }
           if (ma.first_child < 0 && mb.first_child < 0)
           {
             if (t == 0)
@@ -380,22 +415,22 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
                 {
                   // expansion of side 1, C2A.cpp:1194-1209
                   n1 = cm1.first_child + bit;
-                  cm1 = A.meta[n1];
+                  cm1 = load_meta(A.meta + n1);
                   gs = A.geom + (size_t)n1 * GEOM_STRIDE; gt = B.geom + (size_t)n2 * GEOM_STRIDE;
-                  rl = A.rloc + (size_t)n1 * 9;
+                  rl = A.rloc + (size_t)n1 * RLOC_STRIDE;
                   double Rn[9], Tn[3], Tt[3];
-                  load9(Rn, gs); load3(Tn, gs + 9);
+                  load_node_rt(Rn, Tn, gs);
                   mt_m(Rc, Rn, R); v_sub(Tt, T, Tn); mt_v(Tc, Rn, Tt);
                 }
                 else
                 {
                   // expansion of side 2, C2A.cpp:1211-1225
                   n2 = cm2.first_child + bit;
-                  cm2 = B.meta[n2];
+                  cm2 = load_meta(B.meta + n2);
                   gs = A.geom + (size_t)n1 * GEOM_STRIDE; gt = B.geom + (size_t)n2 * GEOM_STRIDE;
-                  rl = A.rloc + (size_t)n1 * 9;
+                  rl = A.rloc + (size_t)n1 * RLOC_STRIDE;
                   double Rn[9], Tn[3];
-                  load9(Rn, gt); load3(Tn, gt + 9);
+                  load_node_rt(Rn, Tn, gt);
                   m_m(Rc, R, Rn); m_v_p(Tc, R, Tn, T);
                 }
 #pragma unroll
@@ -410,15 +445,17 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
             {
               prefetch_l1(rl); prefetch_l1(rl + 8);  // R_loc is only consumed after the rectangle distance
               double S[3];
-              const double a0 = __ldg(gs + 12), a1 = __ldg(gs + 13), ra = __ldg(gs + 14);
-              const double e0 = __ldg(gt + 12), e1 = __ldg(gt + 13), rb = __ldg(gt + 14);
+              // l(2) r ang_radius of both nodes: two 128-bit loads each
+              const double2 la = __ldg(reinterpret_cast<const double2 *>(gs + 12)), ra2 = __ldg(reinterpret_cast<const double2 *>(gs + 14));
+              const double2 lb = __ldg(reinterpret_cast<const double2 *>(gt + 12)), rb2 = __ldg(reinterpret_cast<const double2 *>(gt + 14));
+              const double a0 = la.x, a1 = la.y, ra = ra2.x, e0 = lb.x, e1 = lb.y, rb = rb2.x;
               d = rss_rect_dist(R, T, a0, a1, e0, e1, S);
               d -= (ra + rb);
               d = (d < 0.0) ? 0.0 : d;
               if (d != 0.0)
               {
                 double Rl[9], tmp[3], S1[3], S2[3], r1[9];
-                load9(Rl, rl);
+                load9v(Rl, rl);
                 m_v(tmp, Rl, S);
 #pragma unroll
                 for (int i = 0; i < 9; i++) r1[i] = SD(F_R1 + i, slot);
@@ -429,11 +466,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
 #pragma unroll
                 for (int i = 0; i < 3; i++) { m.cv[i] = SD(F_CV1 + i, slot); m.axis[i] = SD(F_AX1 + i, slot); }
                 m.w = SD(F_W1, slot);
-                const double mb1 = motion_bound_bv_unit(m, __ldg(gs + 15), S1);
+                const double mb1 = motion_bound_bv_unit(m, ra2.y, S1);
 #pragma unroll
                 for (int i = 0; i < 3; i++) { m.cv[i] = SD(F_CV2 + i, slot); m.axis[i] = SD(F_AX2 + i, slot); }
                 m.w = SD(F_W2, slot);
-                const double mb2 = motion_bound_bv_unit(m, __ldg(gt + 15), S2);
+                const double mb2 = motion_bound_bv_unit(m, rb2.y, S2);
                 mt = (d) / (mb1 + mb2);
                 if (mt <= 0) mt = 0.0;
               }
@@ -581,7 +618,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
 #pragma unroll
         for (int i = 0; i < 3; i++) Trel[i] = SD(F_TREL + i, slot);
         const int ta = -A.meta[b1].first_child - 1, tb = -B.meta[b2].first_child - 1;
-        const double dTri = tri_distance_nl(Rrel, Trel, A.tris + (size_t)9 * ta, B.tris + (size_t)9 * tb, p, qq);
+        const double dTri = tri_distance_v(Rrel, Trel, A.tris + (size_t)TRI_STRIDE * ta, B.tris + (size_t)TRI_STRIDE * tb, p, qq);
         if (dTri <= SD(F_DIST, slot))
         {
           SD(F_DIST, slot) = dTri;
@@ -828,8 +865,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
           mt_v(T, g1, Tt);
 
           double p[3], qq[3];
-          const double dist = tri_distance_nl(Rrel, Trel, A.tris + (size_t)9 * SI(I_SEEDA, slot),
-                                              B.tris + (size_t)9 * SI(I_SEEDB, slot), p, qq);
+          const double dist = tri_distance_v(Rrel, Trel, A.tris + (size_t)TRI_STRIDE * SI(I_SEEDA, slot),
+                                             B.tris + (size_t)TRI_STRIDE * SI(I_SEEDB, slot), p, qq);
           double mint = SD(F_MINT, slot);
           if (numCA == 0) mint = 1;
           if (mint <= 0.005 || dist <= 0.5 || numCA > 5) { SD(F_ABS, slot) = 0; SD(F_REL, slot) = 0; }

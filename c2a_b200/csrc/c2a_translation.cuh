@@ -59,7 +59,7 @@ C2A_DEV bool ca_on_rss(const Motion &m1, double delta, const double r1[9], const
                        const double *ga, const double *rl, const double *gb, double *mint, double *distance)
 {
   double S[3] = {1.0, 0.0, 0.0}, temp1[3], Tcur[3], Vel[3], Rl[9];
-  load9(Rl, rl);
+  load9v(Rl, rl);
   mt_v(temp1, r1, m1.cv);
   mt_v(Vel, Rl, temp1);
   const double ang = __ldg(ga + 15);
@@ -182,8 +182,8 @@ __global__ void __launch_bounds__(128) c2a_translation_kernel(const TransArgs ar
     {
       // seed: advancement of the two seed triangles, :1818-1852
       double t1[9], t2[9], tri2[9];
-      load9(t1, A.tris + (size_t)9 * lastA);
-      load9(t2, B.tris + (size_t)9 * lastB);
+      load9v(t1, A.tris + (size_t)TRI_STRIDE * lastA);
+      load9v(t2, B.tris + (size_t)TRI_STRIDE * lastB);
       m_v_p(&tri2[0], Rrel, &t2[0], Trel); m_v_p(&tri2[3], Rrel, &t2[3], Trel); m_v_p(&tri2[6], Rrel, &t2[6], Trel);
       double mint = 1.0, dTri = 0.0;
       if (ca_on_triangles(m1, delta, r1, t1, tri2, &mint, &dTri)) { res_mint = mint; res_dist = dTri; }
@@ -217,8 +217,8 @@ __global__ void __launch_bounds__(128) c2a_translation_kernel(const TransArgs ar
         // :1390-1420
         const int ta = -ma.first_child - 1, tb = -mb.first_child - 1;
         double t1[9], t2[9], tri2[9];
-        load9(t1, A.tris + (size_t)9 * ta);
-        load9(t2, B.tris + (size_t)9 * tb);
+        load9v(t1, A.tris + (size_t)TRI_STRIDE * ta);
+        load9v(t2, B.tris + (size_t)TRI_STRIDE * tb);
         m_v_p(&tri2[0], Rrel, &t2[0], Trel); m_v_p(&tri2[3], Rrel, &t2[3], Trel); m_v_p(&tri2[6], Rrel, &t2[6], Trel);
         if (ca_on_triangles(m1, delta, r1, t1, tri2, &res_mint, &res_dist)) { lastA = ta; lastB = tb; }
         ntri++;
@@ -236,18 +236,18 @@ __global__ void __launch_bounds__(128) c2a_translation_kernel(const TransArgs ar
         {
           const int n1 = ma.first_child + c;
           ids[c] = __hiloint2double(n1, b2);
-          ga = A.geom + (size_t)n1 * GEOM_STRIDE; gb = B.geom + (size_t)b2 * GEOM_STRIDE; rl = A.rloc + (size_t)n1 * 9;
+          ga = A.geom + (size_t)n1 * GEOM_STRIDE; gb = B.geom + (size_t)b2 * GEOM_STRIDE; rl = A.rloc + (size_t)n1 * RLOC_STRIDE;
           double Rn[9], Tn[3];
-          load9(Rn, ga); load3(Tn, ga + 9);
+          load_node_rt(Rn, Tn, ga);
           mt_m(Rch[c], Rn, R); v_sub(Tt, T, Tn); mt_v(Tch[c], Rn, Tt);
         }
         else
         {
           const int n2 = mb.first_child + c;
           ids[c] = __hiloint2double(b1, n2);
-          ga = A.geom + (size_t)b1 * GEOM_STRIDE; gb = B.geom + (size_t)n2 * GEOM_STRIDE; rl = A.rloc + (size_t)b1 * 9;
+          ga = A.geom + (size_t)b1 * GEOM_STRIDE; gb = B.geom + (size_t)n2 * GEOM_STRIDE; rl = A.rloc + (size_t)b1 * RLOC_STRIDE;
           double Rn[9], Tn[3];
-          load9(Rn, gb); load3(Tn, gb + 9);
+          load_node_rt(Rn, Tn, gb);
           m_m(Rch[c], R, Rn); m_v_p(Tch[c], R, Tn, T);
         }
         mt_ac[c] = res_mint; d_ac[c] = 1e+30;
@@ -279,8 +279,8 @@ __global__ void __launch_bounds__(128) c2a_translation_kernel(const TransArgs ar
     mt_v(Trel, Ra, Tt);
     {
       double t1[9], t2[9], tri2[9];
-      load9(t1, A.tris + (size_t)9 * lastA);
-      load9(t2, B.tris + (size_t)9 * lastB);
+      load9v(t1, A.tris + (size_t)TRI_STRIDE * lastA);
+      load9v(t2, B.tris + (size_t)TRI_STRIDE * lastB);
       m_v_p(&tri2[0], Rrel, &t2[0], Trel); m_v_p(&tri2[3], Rrel, &t2[3], Trel); m_v_p(&tri2[6], Rrel, &t2[6], Trel);
       res_dist = tri_dist_nl(p, qq, t1, tri2);
     }
