@@ -85,6 +85,8 @@ GOLDEN_CASES = [  # (fixture, model A, model B)
     ("ref_bunny_vs_knot_seeded", "bunny", "knot_512x32"),
     ("ref_knot_128x16_grazing_tol0.001", "knot_128x16", "knot_128x16"),   # config 5 flavour: grazing end poses,
     ("ref_knot_128x16_grazing_tol1e-06", "knot_128x16", "knot_128x16"),   # tolerance_t swept (verdicts flip with it)
+    ("ref_bunny_grazing_tol0.001", "bunny", "bunny"),                     # config 5 on the bunny, as BASELINE names it
+    ("ref_bunny_grazing_tol1e-06", "bunny", "bunny"),
     ("ref_knot_128x16_carry", "knot_128x16", "knot_128x16"),              # "demo mode": seeds carried through
     ("ref_demo_bunny_carry", "bunny", "bunny"),                           # o->last_tri (quirk Q4), 303 frames twice
 ]

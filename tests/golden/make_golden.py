@@ -93,6 +93,18 @@ def translation_fixtures(R, bunny):
                  {"seed_a": sa, "seed_b": sb, "last_tri": np.stack([res["last_tri_a"], res["last_tri_b"]], 1)})
 
 
+def bunny_grazing_fixture(R, bunny):
+    """Config 5 on the model BASELINE.json names for it: colliding bunny pairs re-posed so that the motion only just
+    reaches contact at its end (end pose = TOC pose pushed 0..1e-3 past contact), tolerance_t 1e-3 and 1e-6."""
+    g = np.load(os.path.join(HERE, "ref_bunny_approach.npz"))
+    hit = np.where((g["collisionfree"] == 0) & (g["num_tri_tests"] > 0))[0][:120]
+    rng = np.random.default_rng(56)
+    gp = workloads.grazing_batch(g["poses"][hit], g["toc"][hit], g["pose_toc"][hit], g["p1p2"][hit], rng.uniform(0, 1e-3, len(hit)))
+    for tol_t in (1e-3, 1e-6):
+        res = R.solve_batch(bunny, bunny, gp, tol_d=1e-4, tol_t=tol_t, threads=THREADS)
+        save_results(f"ref_bunny_grazing_tol{tol_t:g}.npz", res, gp, 1e-4, tol_t)
+
+
 def distance_fixture(R):
     """The reference's C2A_Distance (C2A_PQP.cpp:970-1056, depth-first routine) on static pose pairs, random seeds."""
     tris, vi = meshes.torus_knot(128, 16)
@@ -114,6 +126,10 @@ def distance_fixture(R):
 def main():
     oracle.build_oracle()
     R = oracle.ref()
+    if "--only-bunny-grazing" in sys.argv:
+        m = np.load(os.path.join(HERE, "bunny_mesh.npz"))
+        bunny_grazing_fixture(R, R.model(m["verts"][m["vidx"]].reshape(-1, 9).copy(), m["vidx"]))
+        return
     if "--only-distance" in sys.argv:
         distance_fixture(R)
         return
@@ -208,6 +224,7 @@ def main():
 
     translation_fixtures(R, bunny)
     distance_fixture(R)
+    bunny_grazing_fixture(R, bunny)
 
     with open(os.path.join(HERE, "bvh_digest.json"), "w") as f:
         json.dump(digests, f, indent=1, sort_keys=True)
