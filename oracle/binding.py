@@ -118,6 +118,21 @@ class _Port:
                                     C.c_double(tol_t), C.c_int32(K), C.c_void_p(out[i:i + 1].ctypes.data), _ptr(st))
         return out, {k: (st[k][0].tolist() if st[k].ndim > 1 else st[k][0].item()) for k in st.dtype.names}
 
+    def solve_visits(self, bvhA, bvhB, pose48, tol_d=1e-4, tol_t=1e-4, cap=1 << 23):
+        """Round-2 design study: one query's result plus the per-CA-step sequences of visited node pairs
+        (list of uint64 arrays, b1 << 32 | b2)."""
+        sA, sB = bvh_struct(bvhA), bvh_struct(bvhB)
+        p = np.ascontiguousarray(pose48, np.float64).reshape(48)
+        out = np.zeros(1, dtype=RESULT_DTYPE)
+        buf = np.zeros(cap, dtype=np.uint64)
+        self.lib.orc_solve_visits.restype = C.c_int64
+        n = self.lib.orc_solve_visits(C.byref(sA), C.byref(sB), _ptr(p), C.c_int32(0), C.c_int32(0), C.c_double(tol_d),
+                                      C.c_double(tol_t), _ptr(out), _ptr(buf), C.c_int64(cap))
+        v = buf[:min(n, cap)]
+        cuts = np.nonzero(v == np.uint64(0xFFFFFFFFFFFFFFFF))[0]
+        steps = [v[a + 1:b] for a, b in zip(cuts, list(cuts[1:]) + [len(v)])]
+        return out[0], steps
+
     def contacts(self, bvhA, bvhB, pose1, pose2, threshold, vidx_a=None, vidx_b=None, max_out=4096):
         """Contact pass at the given poses; records in visiting order. Returns (count, records)."""
         sA, sB = bvh_struct(bvhA), bvh_struct(bvhB)

@@ -587,6 +587,7 @@ extern "C" double orc_motion_bound_leaf(const orc_motion *m, double ang_radius, 
 }
 
 // ---- traversal + CA loop -----------------------------------------------------
+static thread_local std::vector<uint64_t> *g_visits = nullptr;  // non-NULL: toc_recurse logs every visited node pair (orc_solve_visits)
 static thread_local orc_spec_stats *g_spec = nullptr;  // non-NULL: exact-mode steps run the speculative split (design study below)
 static thread_local double g_spec_prev = -1;
 namespace {
@@ -624,6 +625,7 @@ inline double bv_distance(const double R[9], const double T[3], const orc_bvh *A
 void toc_recurse(Step &st, const double R[9], const double T[3], int b1, int b2)
 {
   const orc_bvh *A = st.A, *B = st.B;
+  if (g_visits) g_visits->push_back(((uint64_t)(uint32_t)b1 << 32) | (uint32_t)b2);
   const int l1 = A->first_child[b1] < 0, l2 = B->first_child[b2] < 0;
   const double *r1 = st.m1->Rc, *tt1 = st.m1->Tc;
 
@@ -985,6 +987,7 @@ void toc_step(Step &st, int numCA, int seedA, int seedB)
     st.rel_err = (numCA <= 2) ? 3 : 0.5;
   }
   st.mint = 1;
+  if (g_visits) g_visits->push_back(~0ull);  // step separator
   if (g_spec && st.abs_err == 0 && st.rel_err == 0) spec_step(st, R, T);
   else toc_recurse(st, R, T, 0, 0);
 }
@@ -1565,4 +1568,18 @@ extern "C" void orc_solve_spec(const orc_bvh *A, const orc_bvh *B, const double 
   g_spec = stats; g_spec_prev = -1;
   orc_solve(A, B, poses, seedA, seedB, tol_d, tol_t, out);
   g_spec = nullptr;
+}
+
+// Design study entry: orc_solve that also returns the sequence of node pairs the traversal visits (expanded pairs and
+// leaf pairs as (b1 << 32 | b2), a ~0 word before each CA step).  Returns the number of words; at most cap are written.
+extern "C" int64_t orc_solve_visits(const orc_bvh *A, const orc_bvh *B, const double poses[48], int32_t seedA, int32_t seedB,
+                                    double tol_d, double tol_t, orc_result *out, uint64_t *visits, int64_t cap)
+{
+  std::vector<uint64_t> v;
+  g_visits = &v;
+  orc_solve(A, B, poses, seedA, seedB, tol_d, tol_t, out);
+  g_visits = nullptr;
+  const int64_t n = (int64_t)v.size();
+  if (visits) memcpy(visits, v.data(), sizeof(uint64_t) * (size_t)(n < cap ? n : cap));
+  return n;
 }

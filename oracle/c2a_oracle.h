@@ -138,6 +138,9 @@ typedef struct orc_spec_stats
 void orc_solve_spec(const orc_bvh *A, const orc_bvh *B, const double poses[48], int32_t seedA, int32_t seedB, double tol_d,
                     double tol_t, int32_t K, orc_result *out, orc_spec_stats *stats);
 
+int64_t orc_solve_visits(const orc_bvh *A, const orc_bvh *B, const double poses[48], int32_t seedA, int32_t seedB, double tol_d,
+                         double tol_t, orc_result *out, uint64_t *visits, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -198,6 +198,17 @@ def test_speculative_step_split_is_exact(golden, bvhs):
         assert st["steps"] > 50 and 0 < st["valid"] < st["reached"]  # both the accepted and the re-run path are exercised
 
 
+def test_visit_sequences_account_for_the_counters(golden, bvhs):
+    """Round-2 design study hook (orc_solve_visits): every visited node pair is an expansion (2 BV tests) or a leaf
+    pair (1 triangle test), so the logged sequences must add up to the query's counters."""
+    g = golden("ref_knot_128x16")
+    i = int(np.argmax(g["num_bv_tests"]))
+    res, steps = oracle.port().solve_visits(bvhs("knot_128x16"), bvhs("knot_128x16"), g["poses"][i])
+    assert res["toc"] == g["toc"][i] and len(steps) == g["numCA"][i]
+    assert sum(len(s) for s in steps) == g["num_bv_tests"][i] // 2 + g["num_tri_tests"][i]
+    assert all(s[0] == 0 for s in steps)  # every step starts at the root pair
+
+
 def test_golden_fixtures_are_sane(golden):
     """Verdict semantics: toc == 0 for free queries, hits end within tolerance."""
     for case, _, _ in GOLDEN_CASES:
