@@ -37,6 +37,10 @@ SPEC_STATS_DTYPE = np.dtype([("steps", np.int64), ("tasks", np.int64), ("reached
                              ("depth", np.int32)], align=True)
 
 
+REPLAY_STATS_DTYPE = np.dtype([("steps", np.int64), ("visits", np.int64), ("hits", np.int64), ("seq_hits", np.int64),
+                               ("misses", np.int64), ("preeval", np.int64), ("wasted", np.int64)], align=True)
+
+
 class _Bvh(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("n_tris", C.c_int32),
                 ("R", C.c_void_p), ("Tr", C.c_void_p), ("l", C.c_void_p), ("r", C.c_void_p),
@@ -117,6 +121,19 @@ class _Port:
             self.lib.orc_solve_spec(C.byref(sA), C.byref(sB), _ptr(poses[i]), C.c_int32(0), C.c_int32(0), C.c_double(tol_d),
                                     C.c_double(tol_t), C.c_int32(K), C.c_void_p(out[i:i + 1].ctypes.data), _ptr(st))
         return out, {k: (st[k][0].tolist() if st[k].ndim > 1 else st[k][0].item()) for k in st.dtype.names}
+
+    def solve_replay(self, bvhA, bvhB, poses, seedA=None, seedB=None, tol_d=1e-4, tol_t=1e-4):
+        """Round-2 design study: every CA step replayed over the previous step's visit list.
+        Returns (results like solve_batch, dict of accumulated statistics)."""
+        sA, sB = bvh_struct(bvhA), bvh_struct(bvhB)
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 48)
+        out = np.zeros(len(poses), dtype=RESULT_DTYPE)
+        st = np.zeros(1, dtype=REPLAY_STATS_DTYPE)
+        for i in range(len(poses)):
+            self.lib.orc_solve_replay(C.byref(sA), C.byref(sB), _ptr(poses[i]), C.c_int32(0 if seedA is None else int(seedA[i])),
+                                      C.c_int32(0 if seedB is None else int(seedB[i])), C.c_double(tol_d), C.c_double(tol_t),
+                                      C.c_void_p(out[i:i + 1].ctypes.data), _ptr(st))
+        return out, {k: st[k][0].item() for k in st.dtype.names}
 
     def solve_visits(self, bvhA, bvhB, pose48, tol_d=1e-4, tol_t=1e-4, cap=1 << 23):
         """Round-2 design study: one query's result plus the per-CA-step sequences of visited node pairs

@@ -590,8 +590,11 @@ extern "C" double orc_motion_bound_leaf(const orc_motion *m, double ang_radius, 
 static thread_local std::vector<uint64_t> *g_visits = nullptr;  // non-NULL: toc_recurse logs every visited node pair (orc_solve_visits)
 static thread_local orc_spec_stats *g_spec = nullptr;  // non-NULL: exact-mode steps run the speculative split (design study below)
 static thread_local double g_spec_prev = -1;
+static thread_local orc_replay_stats *g_rp = nullptr;  // non-NULL: every CA step is replayed over the previous step's visit list
 namespace {
 struct Step;
+struct RpEntry;
+void replay_step(Step &st, const double R[9], const double T[3]);
 void spec_step(Step &st, const double R[9], const double T[3]);
 struct Step
 {
@@ -961,6 +964,135 @@ void spec_step(Step &st, const double R[9], const double T[3])
   g_spec_prev = st.distance;
 }
 
+// ---- design study for round 2 (TEST INFRASTRUCTURE): a CA step replayed over the previous step's visit list -------
+// The list keeps, per visited node pair, only its STRUCTURE (ids, parent entry, which child of the parent it is, links
+// to its own children entries); the values -- the pair's transform, its two child tests, or the triangle test of a leaf
+// pair -- are pure functions of the pair and the current poses and are re-evaluated for the whole list BEFORE the walk
+// (on the GPU: level by level across all idle warps; here in list order, parents precede children).  The walk is then
+// the reference's depth-first traversal with every evaluation replaced by a record look-up through the parent's child
+// link; a pair the previous step did not visit is evaluated on the spot.  Decisions are made with the current running
+// distance exactly as in toc_recurse, so the result is the sequential one.
+struct RpEntry
+{
+  int b1, b2, parent, slot, kid[2];
+  bool leaf, visited;
+  double R[9], T[3];
+  Kids k;                              // inner pair: both child tests
+  double dTri, p[3], q[3], leaf_mt;    // leaf pair: triangle distance, closest points, the leaf's step bound
+};
+
+thread_local std::vector<RpEntry> g_rp_prev;  // the previous step's visit list (structure only is carried over)
+void rp_reset() { std::vector<RpEntry>().swap(g_rp_prev); }
+
+void rp_eval(const Step &st, RpEntry &e)
+{
+  const orc_bvh *A = st.A, *B = st.B;
+  if (e.leaf)
+  {
+    const double *r1 = st.m1->Rc, *tt1 = st.m1->Tc;
+    const double *t1 = &A->tris[9 * (-A->first_child[e.b1] - 1)];
+    const double *t2 = &B->tris[9 * (-B->first_child[e.b2] - 1)];
+    e.dTri = orc_tri_distance(st.Rrel, st.Trel, t1, t2, e.p, e.q);
+    double w1[3], w2[3], S1[3], S2[3], tmp[3];
+    m_v(tmp, r1, e.p); v_add(w1, tmp, tt1);
+    m_v(tmp, r1, e.q); v_add(w2, tmp, tt1);
+    v_sub(S1, w2, w1);
+    S2[0] = S1[0] * -1; S2[1] = S1[1] * -1; S2[2] = S1[2] * -1;
+    double mb1 = orc_motion_bound_leaf(st.m1, A->ang_radius[e.b1], S1);
+    double mb2 = orc_motion_bound_leaf(st.m2, B->ang_radius[e.b2], S2);
+    double mint = (e.dTri) / (mb1 + mb2);
+    if (mint < 0.0) mint = 0.0;
+    e.leaf_mt = mint;
+  }
+  else expand_pair(st, e.R, e.T, e.b1, e.b2, e.k);
+}
+
+struct RpWalk { Step *st; std::vector<RpEntry> *prev, *cur; orc_replay_stats *ss; int last_prev; };
+
+void rp_visit(RpWalk &w, int pi, const double R[9], const double T[3], int b1, int b2, int parent_new, int slot)
+{
+  Step &st = *w.st;
+  const orc_bvh *A = st.A, *B = st.B;
+  RpEntry ne;
+  ne.b1 = b1; ne.b2 = b2; ne.parent = parent_new; ne.slot = slot; ne.kid[0] = ne.kid[1] = -1; ne.visited = false;
+  ne.leaf = A->first_child[b1] < 0 && B->first_child[b2] < 0;
+  const int ni = (int)w.cur->size();
+  if (parent_new >= 0) (*w.cur)[parent_new].kid[slot] = ni;
+  w.ss->visits++;
+  if (pi >= 0)
+  {
+    RpEntry &pe = (*w.prev)[pi];
+    pe.visited = true;
+    w.ss->hits++;
+    if (pi == w.last_prev + 1) w.ss->seq_hits++;
+    w.last_prev = pi;
+    // take the pre-evaluated values
+    ne.k = pe.k; ne.dTri = pe.dTri; ne.leaf_mt = pe.leaf_mt;
+    v_cpy(ne.p, pe.p); v_cpy(ne.q, pe.q);
+  }
+  else
+  {
+    w.ss->misses++;
+    memcpy(ne.R, R, 72); memcpy(ne.T, T, 24);
+    rp_eval(st, ne);
+  }
+  w.cur->push_back(ne);
+  if (ne.leaf)
+  {
+    // C2A.cpp:1141-1183 with the pure parts already evaluated
+    if (ne.dTri <= st.distance)
+    {
+      st.distance = ne.dTri;
+      v_cpy(st.p1, ne.p); v_cpy(st.p2, ne.q);
+      if (ne.leaf_mt <= st.mint) st.mint = ne.leaf_mt;
+      st.last_a = -A->first_child[b1] - 1; st.last_b = -B->first_child[b2] - 1;
+    }
+    st.num_tri_tests++;
+    return;
+  }
+  const Kids k = ne.k;  // (a copy: w.cur may grow while we recurse)
+  st.num_bv_tests += 2;
+  const bool c_first = k.d2 < k.d1;
+  for (int j = 0; j < 2; j++)
+  {
+    const bool isc = (j == 0) == c_first;
+    const double d = isc ? k.d2 : k.d1, mt = isc ? k.mt2 : k.mt1;
+    const int s = isc ? 1 : 0;
+    const bool go = mt < st.upbound && ((d < (st.distance - st.abs_err)) || (d * (1 + st.rel_err) < st.distance));
+    if (go)
+      rp_visit(w, pi >= 0 ? (*w.prev)[pi].kid[s] : -1, isc ? k.R2 : k.R1, isc ? k.T2 : k.T1, isc ? k.c1 : k.a1, isc ? k.c2 : k.a2, ni, s);
+    else if (mt < st.mint) st.mint = mt;
+  }
+}
+
+void replay_step(Step &st, const double R[9], const double T[3])
+{
+  orc_replay_stats &ss = *g_rp;
+  std::vector<RpEntry> prev;
+  prev.swap(g_rp_prev);
+  // pre-evaluation of the whole previous list for the current poses (parents precede children in visit order)
+  for (size_t i = 0; i < prev.size(); i++)
+  {
+    RpEntry &e = prev[i];
+    e.visited = false;
+    if (e.parent < 0) { memcpy(e.R, R, 72); memcpy(e.T, T, 24); }
+    else
+    {
+      const Kids &pk = prev[e.parent].k;
+      memcpy(e.R, e.slot ? pk.R2 : pk.R1, 72); memcpy(e.T, e.slot ? pk.T2 : pk.T1, 24);
+    }
+    rp_eval(st, e);
+    ss.preeval++;
+  }
+  std::vector<RpEntry> cur;
+  cur.reserve(prev.size() + 64);
+  RpWalk w; w.st = &st; w.prev = &prev; w.cur = &cur; w.ss = &ss; w.last_prev = -1;
+  rp_visit(w, prev.empty() ? -1 : 0, R, T, 0, 0, -1, 0);
+  for (auto &e : prev) if (!e.visited) ss.wasted++;
+  ss.steps++;
+  g_rp_prev.swap(cur);
+}
+
 // C2A_TimeOfContactStep (rotational branch), C2A/src/C2A.cpp:1778-1931.
 // numCA / prev_mint carry res->numCA and the previous step's res->mint.
 void toc_step(Step &st, int numCA, int seedA, int seedB)
@@ -988,7 +1120,8 @@ void toc_step(Step &st, int numCA, int seedA, int seedB)
   }
   st.mint = 1;
   if (g_visits) g_visits->push_back(~0ull);  // step separator
-  if (g_spec && st.abs_err == 0 && st.rel_err == 0) spec_step(st, R, T);
+  if (g_rp) replay_step(st, R, T);
+  else if (g_spec && st.abs_err == 0 && st.rel_err == 0) spec_step(st, R, T);
   else toc_recurse(st, R, T, 0, 0);
 }
 // ---- translation-only branch (both angular speeds < 1e-8, C2A.cpp:2391-2395) -------------------
@@ -1582,4 +1715,15 @@ extern "C" int64_t orc_solve_visits(const orc_bvh *A, const orc_bvh *B, const do
   const int64_t n = (int64_t)v.size();
   if (visits) memcpy(visits, v.data(), sizeof(uint64_t) * (size_t)(n < cap ? n : cap));
   return n;
+}
+
+// Design study entry: orc_solve with every CA step replayed over the previous step's visit list (see replay_step).
+extern "C" void orc_solve_replay(const orc_bvh *A, const orc_bvh *B, const double poses[48], int32_t seedA, int32_t seedB,
+                                 double tol_d, double tol_t, orc_result *out, orc_replay_stats *stats)
+{
+  g_rp = stats;
+  rp_reset();
+  orc_solve(A, B, poses, seedA, seedB, tol_d, tol_t, out);
+  rp_reset();
+  g_rp = nullptr;
 }

@@ -138,6 +138,16 @@ typedef struct orc_spec_stats
 void orc_solve_spec(const orc_bvh *A, const orc_bvh *B, const double poses[48], int32_t seedA, int32_t seedB, double tol_d,
                     double tol_t, int32_t K, orc_result *out, orc_spec_stats *stats);
 
+/* Round-2 design study: every CA step replayed over the previous step's visit list (records re-evaluated for the
+ * current poses before the walk, misses evaluated on the spot).  Counts are node-pair visits. */
+typedef struct orc_replay_stats
+{
+  long long steps, visits, hits, seq_hits, misses; /* walk: visits = hits + misses; seq_hits = hits on the next record of the list */
+  long long preeval, wasted;                       /* records evaluated before the walks; of those, never visited */
+} orc_replay_stats;
+void orc_solve_replay(const orc_bvh *A, const orc_bvh *B, const double poses[48], int32_t seedA, int32_t seedB, double tol_d,
+                      double tol_t, orc_result *out, orc_replay_stats *stats);
+
 int64_t orc_solve_visits(const orc_bvh *A, const orc_bvh *B, const double poses[48], int32_t seedA, int32_t seedB, double tol_d,
                          double tol_t, orc_result *out, uint64_t *visits, int64_t cap);
 

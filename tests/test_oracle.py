@@ -198,6 +198,20 @@ def test_speculative_step_split_is_exact(golden, bvhs):
         assert st["steps"] > 50 and 0 < st["valid"] < st["reached"]  # both the accepted and the re-run path are exercised
 
 
+def test_replay_over_previous_visit_list_is_exact(golden, bvhs):
+    """Round-2 design study (orc_solve_replay): CA steps walked over the previous step's visit list, with the records
+    re-evaluated for the current poses beforehand and misses evaluated on the spot, give the sequential result."""
+    for case, model in (("ref_knot_128x16", "knot_128x16"), ("ref_knot_128x16_grazing_tol1e-06", "knot_128x16")):
+        g = golden(case)
+        idx = np.argsort(-g["num_bv_tests"])[:25]
+        res, st = oracle.port().solve_replay(bvhs(model), bvhs(model), g["poses"][idx], tol_d=float(g["tol_d"]), tol_t=float(g["tol_t"]))
+        for k in ("collisionfree", "numCA", "num_bv_tests", "num_tri_tests", "toc", "distance", "mint", "pose_toc"):
+            assert np.array_equal(res[k], g[k][idx]), (case, k)
+        upd = (res["p1"] != 0).any(1)
+        assert np.array_equal(np.concatenate([res["p1"], res["p2"]], 1)[upd], g["p1p2"][idx][upd])
+        assert st["visits"] == st["hits"] + st["misses"] and st["hits"] > st["misses"] > 0
+
+
 def test_visit_sequences_account_for_the_counters(golden, bvhs):
     """Round-2 design study hook (orc_solve_visits): every visited node pair is an expansion (2 BV tests) or a leaf
     pair (1 triangle test), so the logged sequences must add up to the query's counters."""
