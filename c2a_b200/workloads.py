@@ -79,6 +79,28 @@ def static_pose_batch(n, seed, radius=BUNNY_RADIUS):
     return np.ascontiguousarray(np.concatenate([pa, ap[:, 24:36]], 1))
 
 
+def degenerate_batch(seed=5, radius=BUNNY_RADIUS):
+    """Edge-case motions (70 queries): no motion at all at three separations (far apart, close, interpenetrating);
+    pure rotation in place; start pose already deep in contact (with and without rotation); motions of 1e-9 of the
+    approach.  Zero or vanishing velocities exercise the floors and NaN paths of the motion bounds."""
+    base = approach_batch(60, seed, radius=radius)
+    out = []
+    for lam in (0.0, 0.45, 0.9):
+        p = base[:10].copy()
+        T = p[:, 9:12] * (1 - lam) + p[:, 21:24] * lam
+        p[:, 9:12] = T; p[:, 12:21] = p[:, 0:9]; p[:, 21:24] = T
+        out.append(p)
+    p = base[10:20].copy(); T = p[:, 9:12] * 0.4 + p[:, 21:24] * 0.6; p[:, 9:12] = T; p[:, 21:24] = T
+    out.append(p)
+    p = base[20:30].copy(); p[:, 9:12] = 0.02 * p[:, 9:12]
+    out.append(p)
+    q = p.copy(); q[:, 12:21] = q[:, 0:9]
+    out.append(q)
+    p = base[30:40].copy(); p[:, 21:24] = p[:, 9:12] + 1e-9 * (p[:, 21:24] - p[:, 9:12]); p[:, 12:21] = p[:, 0:9]
+    out.append(p)
+    return np.ascontiguousarray(np.concatenate(out))
+
+
 def demo_batch(R1f, T1f, R2f, T2f):
     """Config 1: the 303 queries ``cb_display`` builds from torusknot1.ani / torusknot2.ani
     (/root/reference/CCDDemo/mainTorusknot.cpp:216-266): object 1 moves from frame step1 to step2 of

@@ -185,6 +185,16 @@ def test_distance_query_bit_exact(tag, golden, models, bvhs):
     assert api.distance_batch(m, m, np.zeros((0, 24)))["distance"].shape == (0,)
 
 
+def test_degenerate_motions_against_oracle_port(models, bvhs):
+    """No motion at all, rotation in place, contact at the start pose, vanishing motions (both branches)."""
+    poses = workloads.degenerate_batch(radius=workloads.KNOT_RADIUS)
+    ref = oracle.port().solve_batch(bvhs("knot_128x16"), bvhs("knot_128x16"), poses, threads=8)
+    got = api.solve_batch(models("knot_128x16"), models("knot_128x16"), poses)
+    assert (got["status"] == 0).all()
+    for a, b in FIELDS:
+        assert np.array_equal(got[a], ref[b], equal_nan=True), (a, np.nonzero([not np.array_equal(x, y, equal_nan=True) for x, y in zip(got[a], ref[b])])[0][:8])
+
+
 def test_fresh_batch_against_oracle_port(models, bvhs):
     """Inputs that are in no fixture: GPU vs the oracle port run here, bit-exact."""
     poses = workloads.approach_batch(300, 777, radius=workloads.KNOT_RADIUS, max_turn=3.1)

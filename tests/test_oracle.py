@@ -198,6 +198,22 @@ def test_speculative_step_split_is_exact(golden, bvhs):
         assert st["steps"] > 50 and 0 < st["valid"] < st["reached"]  # both the accepted and the re-run path are exercised
 
 
+@needs_ref
+def test_port_matches_ref_on_degenerate_motions(bvhs):
+    """No motion, rotation in place, contact at the start pose, vanishing motions: the port against the reference's
+    object code (both branches; NaN-tolerant comparison, none occurs)."""
+    from c2a_b200 import meshes
+    tris, vi = meshes.torus_knot(128, 16)
+    R = oracle.ref()
+    m = R.model(tris, vi)
+    poses = workloads.degenerate_batch(radius=workloads.KNOT_RADIUS)
+    ref = R.solve_batch(m, m, poses, threads=1)
+    out = oracle.port().solve_batch(bvhs("knot_128x16"), bvhs("knot_128x16"), poses, threads=1)
+    for k in ("collisionfree", "numCA", "num_bv_tests", "num_tri_tests", "toc", "distance", "mint", "pose_toc"):
+        assert np.array_equal(out[k], ref[k], equal_nan=True), k
+    assert (ref["numCA"] == 0).sum() == 50 and (ref["collisionfree"] == 0).sum() > 30
+
+
 def test_replay_over_previous_visit_list_is_exact(golden, bvhs):
     """Round-2 design study (orc_solve_replay): CA steps walked over the previous step's visit list, with the records
     re-evaluated for the current poses beforehand and misses evaluated on the spot, give the sequential result."""
