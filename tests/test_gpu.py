@@ -183,6 +183,15 @@ def test_distance_query_bit_exact(tag, golden, models, bvhs):
     assert np.array_equal(got["distance"], ref["distance"]) and np.array_equal(got["num_bv_tests"], ref["num_bv_tests"])
     assert np.array_equal(got["tri_pair"], np.stack([ref["tri_a"], ref["tri_b"]], 1))
     assert api.distance_batch(m, m, np.zeros((0, 24)))["distance"].shape == (0,)
+    # coincident models (distance 0 at once) and models very far apart
+    sp = workloads.static_pose_batch(20, 77, radius=workloads.KNOT_RADIUS)
+    same = sp.copy(); same[:, 12:24] = same[:, 0:12]
+    far = sp.copy(); far[:, 9:12] *= 50.0
+    poses = np.ascontiguousarray(np.concatenate([same, far]))
+    ref = oracle.port().distance(bvhs("knot_128x16"), bvhs("knot_128x16"), poses, None, None, rel, ab)
+    got = api.distance_batch(m, m, poses, None, None, rel, ab)
+    assert np.array_equal(got["distance"], ref["distance"]) and np.array_equal(got["num_bv_tests"], ref["num_bv_tests"])
+    assert np.array_equal(got["p1p2"], np.concatenate([ref["p1"], ref["p2"]], 1)) and (got["distance"][:20] == 0).all()
 
 
 def test_degenerate_motions_against_oracle_port(models, bvhs):
