@@ -263,16 +263,16 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   args.step_in = step_in;
   args.order = order;
 
-  static std::atomic<bool> attr_set{false};
-  if (!attr_set.exchange(true))
-    CUDA_TRY(cudaFuncSetAttribute(c2a_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BLOCK_SMEM_BYTES));
   {
-    // keep the per-launch scratch (traversal stacks, staging arena) in the stream-ordered pool between launches
+    // once per device (function attributes and memory pools are per device; the callers have made a->device current):
+    // opt in to the 106 KB of dynamic shared memory per block, and keep the per-launch scratch (traversal stacks,
+    // staging arena) in the stream-ordered pool between launches
     static std::mutex m;
     static std::vector<int> done;
     std::lock_guard<std::mutex> lk(m);
     if (std::find(done.begin(), done.end(), a->device) == done.end())
     {
+      CUDA_TRY(cudaFuncSetAttribute(c2a_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BLOCK_SMEM_BYTES));
       cudaMemPool_t pool;
       if (cudaDeviceGetDefaultMemPool(&pool, a->device) == cudaSuccess)
       {
