@@ -2,15 +2,15 @@
 For the heaviest queries of a fixture, replay each step's sequence of visited node pairs against the previous
 step's as a STREAM: a cursor walks the previous sequence; a visit found at the cursor is a sequential hit, one found
 elsewhere in the previous sequence a jump (the memoised record exists but the stream has to be re-positioned), one
-not found a miss (the pair has to be evaluated on the spot).  Usage: python scripts/replay_study.py [fixture] [n]"""
+not found a miss (the pair has to be evaluated on the spot).  Usage: python tests/analysis/replay_study.py [fixture] [n]"""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import oracle
 from c2a_b200 import api, meshes
 fx = sys.argv[1] if len(sys.argv) > 1 else "ref_knot_512x32"
 nq = int(sys.argv[2]) if len(sys.argv) > 2 else 6
-g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests/golden", fx + ".npz"))
+g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests/golden", fx + ".npz"))
 nu, nv = (int(x) for x in fx.split("_")[2].split("x"))
 bvh = api.build_bvh(meshes.torus_knot(nu, nv)[0]); P = oracle.port()
 tot = dict(visits=0, seq=0, jump=0, miss=0, steps=0, runs=0)
