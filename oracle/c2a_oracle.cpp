@@ -7,9 +7,13 @@
 #include "c2a_oracle.h"
 
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <thread>
 #include <vector>
+#include <algorithm>
+#include <limits>
 
 namespace {
 
@@ -591,11 +595,13 @@ static thread_local std::vector<uint64_t> *g_visits = nullptr;  // non-NULL: toc
 static thread_local orc_spec_stats *g_spec = nullptr;  // non-NULL: exact-mode steps run the speculative split (design study below)
 static thread_local double g_spec_prev = -1;
 static thread_local orc_replay_stats *g_rp = nullptr;  // non-NULL: every CA step is replayed over the previous step's visit list
+static thread_local orc_wide_stats *g_wide = nullptr;  // non-NULL: exact-mode CA steps run as sequential prefix + level-synchronous wide phase
 namespace {
 struct Step;
 struct RpEntry;
 void replay_step(Step &st, const double R[9], const double T[3]);
 void spec_step(Step &st, const double R[9], const double T[3]);
+void wide_step(Step &st, const double R[9], const double T[3]);
 struct Step
 {
   const orc_bvh *A, *B;
@@ -640,6 +646,7 @@ void toc_recurse(Step &st, const double R[9], const double T[3], int b1, int b2)
     double dTri = orc_tri_distance(st.Rrel, st.Trel, t1, t2, p, q);
     if (dTri <= st.distance)
     {
+      if (getenv("ORC_DPROFILE")) fprintf(stderr, "  event at bv %d tri %d: D %.6f -> %.6f\n", st.num_bv_tests, st.num_tri_tests, st.distance, dTri);
       st.distance = dTri;
       double w1[3], w2[3], S1[3], S2[3], tmp[3];
       m_v(tmp, r1, p); v_add(w1, tmp, tt1);
@@ -1093,6 +1100,191 @@ void replay_step(Step &st, const double R[9], const double T[3])
   g_rp_prev.swap(cur);
 }
 
+// ---- round-2 algorithm (TEST INFRASTRUCTURE: the CPU statement of what c2a_wide.cuh does on the device) ---------
+// One exact-mode CA step (abs_err = rel_err = 0, so the descend test is "mt < upbound && d < dist") as a depth-first
+// traversal that pops W node pairs at a time:
+//   * the pending pairs live on a stack ordered by the reference's visiting order (top = visited next).  A round pops
+//     the top W pairs, runs their child tests (or the triangle test of a leaf pair) side by side, and pushes the
+//     children back in visiting order (of one pair: the closer child above the other; of the window: the first
+//     pair's children on top) -- so the stack stays in visiting order without any sorting;
+//   * every node carries a pre-order key (one bit per level: 0 = the child visited first) and M = the maximum, over
+//     its path from the root, of its ancestors' and its own test value d (+inf where mt >= upbound);
+//   * the running distance changes only at leaves with dTri <= dist ("events").  Everything that precedes the top
+//     of the stack has been evaluated, so the events up to there can be resolved exactly, in key order: Dw, the
+//     distance in force at the top of the stack.  A popped pair is expanded iff its value < Dw and its children are
+//     pushed iff theirs are: the distance only shrinks, so this is a superset of what the reference expands; the
+//     pairs of one window are expanded without regard to the events inside the window (the speculation);
+//   * when the stack is empty all events are known.  FOLD: with D(key) the distance in force at a node's pre-order
+//     position, a node was visited iff M < D(key); visited parents count their two child tests, children that fail
+//     their own test at their own position fold their step bound, visited leaves count a triangle test, event
+//     leaves fold theirs and the last one gives distance, p1/p2 and last_tri.
+// "visited <=> M(n) < D(key(n))": => is immediate (D never grows).  <= could only fail if some ancestor test value
+// of an event leaf l is >= dTri(l): that edge passed under an earlier, larger distance and descendants visited
+// after l would be mis-classified.  A bounding-volume distance never exceeds the distance of the triangles inside
+// up to rounding, so this is rare; it is DETECTED (M of the leaf's parent >= dTri, dTri != 0) and the step is then
+// redone sequentially.  With that check the result is the sequential one, bit for bit; W = 1 is the sequential walk.
+struct WNode
+{
+  uint64_t key[2]; int depth;    // path bits, left-aligned (bit 127 = first level)
+  double Mpar, val, mt;          // M of the parent (-inf for the root), own test value (d, or +inf if mt >= upbound), own step bound
+  int b1, b2; bool leafpair, expanded;
+  double R[9], T[3];
+  double dTri, p[3], q[3], leaf_mt;  // leaf pairs that were evaluated
+};
+constexpr int WKEY_BITS = 128;
+inline void wkey_child(uint64_t out[2], const uint64_t key[2], int depth, int bit)  // depth = the parent's
+{
+  out[0] = key[0]; out[1] = key[1];
+  if (bit) out[depth >> 6] |= (uint64_t)1 << (63 - (depth & 63));
+}
+inline void wkey_parent(uint64_t out[2], const uint64_t key[2], int depth)  // depth = the child's (>= 1)
+{
+  out[0] = key[0]; out[1] = key[1];
+  out[(depth - 1) >> 6] &= ~((uint64_t)1 << (63 - ((depth - 1) & 63)));
+}
+inline bool wkey_less(const uint64_t a[2], const uint64_t b[2]) { return a[0] < b[0] || (a[0] == b[0] && a[1] < b[1]); }
+
+inline void wide_leaf_eval(const Step &st, WNode &n)
+{
+  const orc_bvh *A = st.A, *B = st.B;
+  const double *r1 = st.m1->Rc, *tt1 = st.m1->Tc;
+  const double *t1 = &A->tris[9 * (-A->first_child[n.b1] - 1)];
+  const double *t2 = &B->tris[9 * (-B->first_child[n.b2] - 1)];
+  n.dTri = orc_tri_distance(st.Rrel, st.Trel, t1, t2, n.p, n.q);
+  double w1[3], w2[3], S1[3], S2[3], tmp[3];
+  m_v(tmp, r1, n.p); v_add(w1, tmp, tt1);
+  m_v(tmp, r1, n.q); v_add(w2, tmp, tt1);
+  v_sub(S1, w2, w1);
+  S2[0] = S1[0] * -1; S2[1] = S1[1] * -1; S2[2] = S1[2] * -1;
+  double mb1 = orc_motion_bound_leaf(st.m1, A->ang_radius[n.b1], S1);
+  double mb2 = orc_motion_bound_leaf(st.m2, B->ang_radius[n.b2], S2);
+  double mint = (n.dTri) / (mb1 + mb2);
+  if (mint < 0.0) mint = 0.0;
+  n.leaf_mt = mint;
+}
+
+void wide_step(Step &st, const double R[9], const double T[3])
+{
+  orc_wide_stats &ws = *g_wide;
+  const orc_bvh *A = st.A, *B = st.B;
+  const Step st0 = st;  // for the sequential redo
+  const double INF = std::numeric_limits<double>::infinity();
+  const int W = (int)ws.window;
+  ws.steps++;
+
+  std::vector<WNode> nodes;     // every evaluated node, in evaluation order (the records of the fold)
+  std::vector<int> stack;       // indices into nodes; back() = visited next
+  std::vector<int> unresolved;  // evaluated leaves whose event status is still open
+  std::vector<int> eleaf;       // event leaves, in key order
+  double Dw = st.distance;      // the distance in force at the top of the stack
+  bool anomaly = false, overflow = false;
+  {
+    WNode n; n.key[0] = n.key[1] = 0; n.depth = 0; n.Mpar = -INF; n.val = -INF; n.mt = 0; n.expanded = false;
+    n.b1 = 0; n.b2 = 0; memcpy(n.R, R, 72); memcpy(n.T, T, 24);
+    n.leafpair = A->first_child[0] < 0 && B->first_child[0] < 0;
+    nodes.push_back(n); stack.push_back(0);
+  }
+  long long rounds = 0;
+  std::vector<int> win, kids;
+  while (!stack.empty() && !anomaly && !overflow)
+  {
+    rounds++;
+    // pop the window: entries that fail under Dw are dropped (their step bound is folded at the end, from the records)
+    win.clear();
+    while (!stack.empty() && (int)win.size() < W)
+    {
+      const int i = stack.back(); stack.pop_back();
+      if (nodes[i].val < Dw) win.push_back(i);
+    }
+    if ((long long)win.size() > ws.max_width) ws.max_width = (long long)win.size();
+    kids.clear();
+    for (int wi : win)
+    {
+      nodes[wi].expanded = true;
+      if (nodes[wi].leafpair) { wide_leaf_eval(st, nodes[wi]); unresolved.push_back(wi); ws.wide_leaves++; continue; }
+      if (nodes[wi].depth + 1 > WKEY_BITS) { overflow = true; break; }
+      Kids k;
+      expand_pair(st, nodes[wi].R, nodes[wi].T, nodes[wi].b1, nodes[wi].b2, k);
+      ws.wide_tests += 2;
+      const bool c_first = k.d2 < k.d1;
+      const double Mn = nodes[wi].Mpar > nodes[wi].val ? nodes[wi].Mpar : nodes[wi].val;
+      int kid_idx[2];
+      for (int j = 0; j < 2; j++)  // j = 0: the child visited first
+      {
+        const bool isc = (j == 0) == c_first;
+        WNode c; c.depth = nodes[wi].depth + 1; c.expanded = false;
+        wkey_child(c.key, nodes[wi].key, nodes[wi].depth, j);
+        c.Mpar = Mn;
+        const double d = isc ? k.d2 : k.d1, mt = isc ? k.mt2 : k.mt1;
+        c.val = (mt < st.upbound) ? d : INF; c.mt = mt;
+        c.b1 = isc ? k.c1 : k.a1; c.b2 = isc ? k.c2 : k.a2;
+        memcpy(c.R, isc ? k.R2 : k.R1, 72); memcpy(c.T, isc ? k.T2 : k.T1, 24);
+        c.leafpair = A->first_child[c.b1] < 0 && B->first_child[c.b2] < 0;
+        nodes.push_back(c);
+        kid_idx[j] = (int)nodes.size() - 1;
+      }
+      kids.push_back(kid_idx[0]); kids.push_back(kid_idx[1]);
+    }
+    // push the children in reverse visiting order (the window's first pair's first child ends up on top)
+    for (int i = (int)kids.size() - 1; i >= 0; i--)
+      if (nodes[kids[i]].val < Dw) stack.push_back(kids[i]);
+    if ((long long)stack.size() > ws.max_stack) ws.max_stack = (long long)stack.size();
+    // resolve the events that precede the new top of the stack, in key order
+    std::vector<int> ready, later;
+    for (int li : unresolved)
+      if (stack.empty() || wkey_less(nodes[li].key, nodes[stack.back()].key)) ready.push_back(li); else later.push_back(li);
+    std::sort(ready.begin(), ready.end(), [&](int x, int y) { return wkey_less(nodes[x].key, nodes[y].key); });
+    if ((long long)later.size() > ws.max_unresolved) ws.max_unresolved = (long long)later.size();
+    for (int li : ready)
+    {
+      const WNode &n = nodes[li];
+      const double M = n.Mpar > n.val ? n.Mpar : n.val;
+      if (M < Dw && n.dTri <= Dw)
+      {
+        if (n.dTri != 0.0 && !(n.Mpar < n.dTri)) { anomaly = true; break; }
+        Dw = n.dTri; eleaf.push_back(li);
+      }
+    }
+    unresolved.swap(later);
+  }
+  ws.rounds += rounds;
+  if (anomaly || overflow) { ws.anomalies += anomaly ? 1 : 0; ws.redo++; st = st0; toc_recurse(st, R, T, 0, 0); return; }
+  ws.events += (long long)eleaf.size();
+
+  // ---- fold
+  auto D_at = [&](const uint64_t key[2]) {
+    double d = st0.distance;
+    for (size_t i = 0; i < eleaf.size(); i++) if (wkey_less(nodes[eleaf[i]].key, key)) d = nodes[eleaf[i]].dTri; else break;
+    return d;
+  };
+  for (const WNode &n : nodes)
+  {
+    bool reached = true;
+    if (n.depth > 0)
+    {
+      uint64_t pk[2]; wkey_parent(pk, n.key, n.depth);
+      reached = n.Mpar < D_at(pk);
+      if (reached) { st.num_bv_tests += 1; ws.wide_tests_visited += 1; }
+    }
+    if (!reached) continue;
+    const bool pass = n.val < D_at(n.key);
+    if (!pass) { if (n.mt < st.mint) st.mint = n.mt; continue; }
+    if (!n.expanded) { ws.redo++; ws.closure_fail++; st = st0; toc_recurse(st, R, T, 0, 0); return; }  // cannot happen (superset); checked all the same
+    if (n.leafpair) { st.num_tri_tests++; ws.wide_leaves_visited++; }
+  }
+  for (size_t i = 0; i < eleaf.size(); i++)
+  {
+    const WNode &n = nodes[eleaf[i]];
+    if (n.leaf_mt <= st.mint) st.mint = n.leaf_mt;
+  }
+  if (!eleaf.empty())
+  {
+    const WNode &n = nodes[eleaf.back()];
+    st.distance = n.dTri; v_cpy(st.p1, n.p); v_cpy(st.p2, n.q);
+    st.last_a = -A->first_child[n.b1] - 1; st.last_b = -B->first_child[n.b2] - 1;
+  }
+}
+
 // C2A_TimeOfContactStep (rotational branch), C2A/src/C2A.cpp:1778-1931.
 // numCA / prev_mint carry res->numCA and the previous step's res->mint.
 void toc_step(Step &st, int numCA, int seedA, int seedB)
@@ -1119,8 +1311,10 @@ void toc_step(Step &st, int numCA, int seedA, int seedB)
     st.rel_err = (numCA <= 2) ? 3 : 0.5;
   }
   st.mint = 1;
+  if (getenv("ORC_DPROFILE")) fprintf(stderr, "step numCA %d seed dist %.6f abs_err %g (bv so far %d)\n", numCA, st.distance, st.abs_err, st.num_bv_tests);
   if (g_visits) g_visits->push_back(~0ull);  // step separator
   if (g_rp) replay_step(st, R, T);
+  else if (g_wide && st.abs_err == 0 && st.rel_err == 0) wide_step(st, R, T);
   else if (g_spec && st.abs_err == 0 && st.rel_err == 0) spec_step(st, R, T);
   else toc_recurse(st, R, T, 0, 0);
 }
@@ -1715,6 +1909,17 @@ extern "C" int64_t orc_solve_visits(const orc_bvh *A, const orc_bvh *B, const do
   const int64_t n = (int64_t)v.size();
   if (visits) memcpy(visits, v.data(), sizeof(uint64_t) * (size_t)(n < cap ? n : cap));
   return n;
+}
+
+// Round-2 algorithm entry: orc_solve with every exact-mode CA step run as prefix + wide phase (see wide_step); results must
+// equal orc_solve's bit for bit.  stats->window (pairs popped per round) is an input (0 -> 16).
+extern "C" void orc_solve_wide(const orc_bvh *A, const orc_bvh *B, const double poses[48], int32_t seedA, int32_t seedB,
+                               double tol_d, double tol_t, orc_result *out, orc_wide_stats *stats)
+{
+  if (stats->window <= 0) stats->window = 16;
+  g_wide = stats;
+  orc_solve(A, B, poses, seedA, seedB, tol_d, tol_t, out);
+  g_wide = nullptr;
 }
 
 // Design study entry: orc_solve with every CA step replayed over the previous step's visit list (see replay_step).

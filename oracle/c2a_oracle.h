@@ -148,6 +148,17 @@ typedef struct orc_replay_stats
 void orc_solve_replay(const orc_bvh *A, const orc_bvh *B, const double poses[48], int32_t seedA, int32_t seedB, double tol_d,
                       double tol_t, orc_result *out, orc_replay_stats *stats);
 
+/* Round-2 algorithm (the CPU statement of c2a_b200/csrc/c2a_wide.cuh): exact-mode CA steps as a depth-first traversal
+ * that pops `window` node pairs per round, resolves the distance updates in key order and folds at the end. */
+typedef struct orc_wide_stats
+{
+  long long window;                                 /* in: node pairs popped per round */
+  long long steps, redo, anomalies, closure_fail, events, rounds, max_width, max_stack, max_unresolved;
+  long long wide_tests, wide_tests_visited, wide_leaves, wide_leaves_visited;
+} orc_wide_stats;
+void orc_solve_wide(const orc_bvh *A, const orc_bvh *B, const double poses[48], int32_t seedA, int32_t seedB, double tol_d,
+                    double tol_t, orc_result *out, orc_wide_stats *stats);
+
 int64_t orc_solve_visits(const orc_bvh *A, const orc_bvh *B, const double poses[48], int32_t seedA, int32_t seedB, double tol_d,
                          double tol_t, orc_result *out, uint64_t *visits, int64_t cap);
 
