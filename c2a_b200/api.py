@@ -178,6 +178,34 @@ def solve_batch(model_a, model_b, poses, seed_a=None, seed_b=None, tol_d=1e-4, t
     return out
 
 
+def solve_batch_multi(models_a, models_b, poses, seed_a=None, seed_b=None, tol_d=1e-4, tol_t=1e-4, fields=None):
+    """One batch sharded over several GPUs of the box: ``models_a[d]`` / ``models_b[d]`` are replicas of the two
+    models on distinct devices.  Same results as ``solve_batch`` for any number of devices."""
+    poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 48)
+    n = poses.shape[0]
+    assert len(models_a) == len(models_b) and len(models_a) >= 1
+    res = Results()
+    out = {}
+    for name, dt, shape in RESULT_FIELDS:
+        if fields is not None and name not in fields:
+            continue
+        a = np.zeros((n,) + shape, dtype=dt)
+        out[name] = a
+        setattr(res, name, a.ctypes.data)
+    if fields is None or "last_tri" in fields:
+        out["last_tri"] = np.full((n, 2), -1, dtype=np.int32)
+        res.last_tri = out["last_tri"].ctypes.data
+    sa = None if seed_a is None else np.ascontiguousarray(seed_a, dtype=np.int32)
+    sb = None if seed_b is None else np.ascontiguousarray(seed_b, dtype=np.int32)
+    ha = (C.c_void_p * len(models_a))(*[m.h for m in models_a])
+    hb = (C.c_void_p * len(models_b))(*[m.h for m in models_b])
+    _check(lib().c2a_b200_solve_batch_multi(ha, hb, C.c_int32(len(models_a)), poses.ctypes.data_as(C.c_void_p),
+                                            sa.ctypes.data_as(C.c_void_p) if sa is not None else None,
+                                            sb.ctypes.data_as(C.c_void_p) if sb is not None else None,
+                                            C.c_int64(n), C.c_double(tol_d), C.c_double(tol_t), C.byref(res)))
+    return out
+
+
 def solve_pairs(models, model_a, model_b, poses, seed_a=None, seed_b=None, tol_d=1e-4, tol_t=1e-4, fields=None):
     """Heterogeneous batch (per-query model handles): ``models`` is a list of Model on one device,
     ``model_a`` / ``model_b`` [n] index into it.  Returns the same dict as ``solve_batch``."""

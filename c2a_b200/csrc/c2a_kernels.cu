@@ -17,6 +17,7 @@
 
 #include "../../include/c2a_b200.h"
 #include "c2a_solve.cuh"
+#include "c2a_wide.cuh"
 #include "c2a_contact.cuh"
 #include "c2a_translation.cuh"
 #include "c2a_distance.cuh"
@@ -247,6 +248,13 @@ int c2a_b200_model_info(const c2a_b200_model *m, int32_t *device, int32_t *n_nod
 
 static unsigned long long *g_stats_dev = nullptr;  // phase statistics (c2a_b200_phase_stats), off by default
 static unsigned long long *g_trace_dev = nullptr;  // per-query claim / finish times (c2a_b200_query_trace), off by default
+static unsigned long long *g_wide_stats_dev = nullptr;  // counters of c2a_wide_kernel (c2a_b200_wide_stats), off by default
+
+static long long env_ll(const char *name, long long dflt)
+{
+  const char *v = getenv(name);
+  return (v && *v) ? atoll(v) : dflt;
+}
 static int64_t g_trace_n = 0;
 
 // per-device scratch: the claim counter
@@ -273,6 +281,7 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
     if (std::find(done.begin(), done.end(), a->device) == done.end())
     {
       CUDA_TRY(cudaFuncSetAttribute(c2a_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BLOCK_SMEM_BYTES));
+      CUDA_TRY(cudaFuncSetAttribute(c2a_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIDE_BLOCK_SMEM));
       cudaMemPool_t pool;
       if (cudaDeviceGetDefaultMemPool(&pool, a->device) == cudaSuccess)
       {
@@ -287,32 +296,55 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c2a_solve_kernel, BLOCK_THREADS, BLOCK_SMEM_BYTES));
   if (per_sm < 1) per_sm = 1;
   long long blocks = (long long)sms * per_sm;  // persistent: one resident wave (a multiple of the SM count)
-  // small batches spread out, one query per warp before any warp takes a second one: a warp that holds few
-  // queries spends its idle lanes on look-ahead, so each query finishes sooner (the GPU is not full anyway)
+  // small batches spread out over all warps: a warp uses ceil(n / warps) of its Q query slots, and with fewer queries
+  // than warps one query per warp.  A warp that holds few queries spends its idle lanes on look-ahead, and hands its
+  // queries to the wide kernel as soon as they are past their fifth CA step
   const long long need = (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
   if (blocks > need) blocks = need;
   if (const char *cap = getenv("C2A_B200_MAX_BLOCKS"))  // development aid: profile a slice of the GPU
     if (atoll(cap) > 0 && blocks > atoll(cap)) blocks = atoll(cap);
   if (blocks < 1) blocks = 1;
+  const long long warps = blocks * WARPS_PER_BLOCK;
+  long long max_slots = (n + warps - 1) / warps;
+  if (max_slots > Q) max_slots = Q;
+  if (max_slots < 1) max_slots = 1;
+  args.max_slots = (int)max_slots;
   // traversal stacks: one per query slot, depth(A)+depth(B)+2 entries of 128 B
   args.stack_entries = a->depth + b->depth + 2;
   const size_t stack_bytes = (size_t)blocks * WARPS_PER_BLOCK * Q * args.stack_entries * ENTRY_DOUBLES * sizeof(double);
-  // tail hand-over mailbox (whole-query mode only): control words | ready flags | records
-  const bool handover = !step_in && getenv("C2A_B200_HANDOVER");  // experimental, off by default (no gain measured yet)
-  const size_t mb_cap = handover ? (size_t)blocks * WARPS_PER_BLOCK * Q : 0;
-  const size_t ctl_bytes = 64, ready_bytes = (mb_cap * sizeof(int) + 63) & ~(size_t)63, recs_bytes = mb_cap * MB_DOUBLES * sizeof(double);
+
+  // hand-over to the wide kernel (whole-query mode only): spill records | spill count, claim counter | per-warp arenas
+  const bool wide = !step_in && !getenv("C2A_B200_NO_WIDE");
+  int wsms_per = 0;
+  if (wide) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wsms_per, c2a_wide_kernel, WIDE_THREADS, WIDE_BLOCK_SMEM));
+  if (wsms_per < 1) wsms_per = 1;
+  long long wblocks = (long long)sms * wsms_per;
+  const long long wneed = (n + WIDE_WPB - 1) / WIDE_WPB;
+  if (wblocks > wneed) wblocks = wneed;
+  if (const char *cap = getenv("C2A_B200_MAX_BLOCKS"))
+    if (atoll(cap) > 0 && wblocks > atoll(cap)) wblocks = atoll(cap);
+  if (wblocks < 1) wblocks = 1;
+  const long long wwarps = wblocks * WIDE_WPB;
+  const int w_stack_cap = (int)std::max<long long>(env_ll("C2A_B200_WIDE_STACK", 4096), args.stack_entries + 64);
+  const int w_rec_cap = (int)env_ll("C2A_B200_WIDE_RECS", 131072);
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t spill_bytes = wide ? up((size_t)n * MB_DOUBLES * sizeof(double)) : 0, wctl_bytes = wide ? 256 : 0;
+  const size_t wstack_bytes = wide ? up((size_t)wwarps * w_stack_cap * ENTRY_DOUBLES * sizeof(double)) : 0;
+  const size_t wrec_bytes = wide ? up((size_t)wwarps * w_rec_cap * 4 * sizeof(double)) : 0;
+  const size_t wleaf_bytes = wide ? up((size_t)wwarps * WIDE_UL * WIDE_LEAFOUT_DOUBLES * sizeof(double)) : 0;
   double *stacks = nullptr;
-  CUDA_TRY(cudaMallocAsync(&stacks, stack_bytes + (handover ? ctl_bytes + ready_bytes + recs_bytes : 0), stream));
+  CUDA_TRY(cudaMallocAsync(&stacks, up(stack_bytes) + spill_bytes + wctl_bytes + wstack_bytes + wrec_bytes + wleaf_bytes, stream));
+  struct Freer { void *p; cudaStream_t s; ~Freer() { cudaFreeAsync(p, s); } } freer{stacks, stream};
   args.stacks = stacks;
-  args.ctl = nullptr; args.mb_ready = nullptr; args.mb_recs = nullptr; args.mb_cap = 0;
-  if (handover)
+  args.spill_recs = nullptr; args.spill_count = nullptr; args.spill_cap = 0; args.spill_live = 0;
+  char *extra = reinterpret_cast<char *>(stacks) + up(stack_bytes);
+  if (wide)
   {
-    char *extra = reinterpret_cast<char *>(stacks) + stack_bytes;
-    args.ctl = reinterpret_cast<unsigned long long *>(extra);
-    args.mb_ready = reinterpret_cast<int *>(extra + ctl_bytes);
-    args.mb_recs = reinterpret_cast<double *>(extra + ctl_bytes + ready_bytes);
-    args.mb_cap = (int)mb_cap;
-    CUDA_TRY(cudaMemsetAsync(extra, 0, ctl_bytes + ready_bytes, stream));
+    args.spill_recs = reinterpret_cast<double *>(extra);
+    args.spill_count = reinterpret_cast<unsigned long long *>(extra + spill_bytes);
+    args.spill_cap = n;
+    args.spill_live = (int)env_ll("C2A_B200_SPILL_LIVE", 20);
+    CUDA_TRY(cudaMemsetAsync(extra + spill_bytes, 0, wctl_bytes, stream));
   }
   args.stats = g_stats_dev;
   args.trace = (g_trace_dev && n <= g_trace_n && !step_in) ? g_trace_dev : nullptr;
@@ -320,8 +352,23 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   c2a_solve_kernel<<<(unsigned)blocks, BLOCK_THREADS, BLOCK_SMEM_BYTES, stream>>>(args);
   g_launches.fetch_add(1);
   cudaError_t le = cudaGetLastError();
-  cudaFreeAsync(stacks, stream);
   if (le != cudaSuccess) return fail(C2A_B200_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(le));
+  if (wide)
+  {
+    WideArgs w;
+    w.A = args.A; w.B = args.B; w.motions = poses; w.seedA = sa; w.seedB = sb; w.tol_d = tol_d; w.tol_t = tol_t; w.out = *out;
+    w.items = args.spill_recs; w.n_items = args.spill_count; w.counter = args.spill_count + 1;
+    w.stack = reinterpret_cast<double *>(extra + spill_bytes + wctl_bytes);
+    w.recs = reinterpret_cast<double *>(extra + spill_bytes + wctl_bytes + wstack_bytes);
+    w.leafout = reinterpret_cast<double *>(extra + spill_bytes + wctl_bytes + wstack_bytes + wrec_bytes);
+    w.stack_cap = w_stack_cap; w.rec_cap = w_rec_cap;
+    w.window = (int)std::min<long long>(16, std::max<long long>(1, env_ll("C2A_B200_WIDE_WINDOW", 16)));
+    w.stats = g_wide_stats_dev; w.trace = args.trace;
+    c2a_wide_kernel<<<(unsigned)wblocks, WIDE_THREADS, WIDE_BLOCK_SMEM, stream>>>(w);
+    g_launches.fetch_add(1);
+    le = cudaGetLastError();
+    if (le != cudaSuccess) return fail(C2A_B200_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(le));
+  }
   if (!step_in)
   {
     // translation-only queries (both angular speeds < 1e-8) were skipped by the kernel above: the reference
@@ -504,28 +551,30 @@ int c2a_b200_solve_batch_device(const c2a_b200_model *a, const c2a_b200_model *b
 // (concurrent callers fall back to a private allocation).
 namespace {
 std::mutex g_pin_mutex;
-void *g_pin_buf = nullptr;
-size_t g_pin_cap = 0;
-bool g_pin_busy = false;
+constexpr int PIN_DEVICES = 64;
+struct PinSlot { void *buf = nullptr; size_t cap = 0; bool busy = false; };
+PinSlot g_pin[PIN_DEVICES];  // one grow-only staging buffer per device (the multi-device entry runs one call per device at a time)
 struct PinnedLease
 {
   void *ptr = nullptr;
-  bool shared = false;
-  cudaError_t acquire(size_t bytes)
+  int slot = -1;
+  cudaError_t acquire(size_t bytes, int device)
   {
+    if (device >= 0 && device < PIN_DEVICES)
     {
       std::lock_guard<std::mutex> lk(g_pin_mutex);
-      if (!g_pin_busy)
+      PinSlot &p = g_pin[device];
+      if (!p.busy)
       {
-        if (g_pin_cap < bytes)
+        if (p.cap < bytes)
         {
-          if (g_pin_buf) cudaFreeHost(g_pin_buf);
-          g_pin_buf = nullptr; g_pin_cap = 0;
-          cudaError_t e = cudaMallocHost(&g_pin_buf, bytes);
+          if (p.buf) cudaFreeHost(p.buf);
+          p.buf = nullptr; p.cap = 0;
+          cudaError_t e = cudaMallocHost(&p.buf, bytes);
           if (e != cudaSuccess) return e;
-          g_pin_cap = bytes;
+          p.cap = bytes;
         }
-        g_pin_busy = true; shared = true; ptr = g_pin_buf;
+        p.busy = true; slot = device; ptr = p.buf;
         return cudaSuccess;
       }
     }
@@ -534,7 +583,7 @@ struct PinnedLease
   ~PinnedLease()
   {
     if (!ptr) return;
-    if (shared) { std::lock_guard<std::mutex> lk(g_pin_mutex); g_pin_busy = false; }
+    if (slot >= 0) { std::lock_guard<std::mutex> lk(g_pin_mutex); g_pin[slot].busy = false; }
     else cudaFreeHost(ptr);
   }
 };
@@ -546,9 +595,11 @@ static double now_s() { return std::chrono::duration<double>(std::chrono::steady
 
 // host-buffer path shared by the three public host entries: inputs are poses (motion constants computed
 // here) or ready motion records; step_in != NULL selects single-step mode
+// gather != NULL (multi-device entry): element i of this call is element gather[i] of motions / seed_a / seed_b
+// (the outputs stay in call order: the caller scatters them)
 static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses, const double *motions,
                       const double *step_in, const int32_t *seed_a, const int32_t *seed_b, int64_t n, double tol_d,
-                      double tol_t, const c2a_b200_results *out)
+                      double tol_t, const c2a_b200_results *out, const int32_t *gather = nullptr)
 {
   int rc = check_pair(a, b, n, poses ? poses : motions, out);
   if (rc) return rc;
@@ -607,12 +658,13 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
   STEP(cudaMemsetAsync(arena + o_pose + ((N * 48 * 8 + 255) & ~(size_t)255), 0, off - (o_pose + ((N * 48 * 8 + 255) & ~(size_t)255)), stream));  // outputs start zeroed
   // motion constants on the host (libm acos), straight into pinned staging memory
   PinnedLease pin;
-  STEP(pin.acquire(N * 48 * 8));
+  STEP(pin.acquire(N * 48 * 8, a->device));
   double *staging = (double *)pin.ptr;
   const double t_alloc = now_s();
   if (rc == C2A_B200_OK)
   {
     if (poses) motions_from_poses_mt(poses, n, staging, 0);
+    else if (gather) for (size_t i = 0; i < N; i++) memcpy(staging + 48 * i, motions + 48 * (size_t)gather[i], 48 * 8);
     else memcpy(staging, motions, N * 48 * 8);
   }
   const double t_motions = now_s();
@@ -626,6 +678,13 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
   }
   const double t_order = now_s();
   STEP(cudaMemcpyAsync(arena + o_pose, staging, N * 48 * 8, cudaMemcpyHostToDevice, stream));
+  std::vector<int32_t> seeds_g;
+  if (gather && (seed_a || seed_b) && rc == C2A_B200_OK)
+  {
+    seeds_g.resize(2 * N);
+    for (size_t i = 0; i < N; i++) { seeds_g[i] = seed_a ? seed_a[gather[i]] : 0; seeds_g[N + i] = seed_b ? seed_b[gather[i]] : 0; }
+    seed_a = seed_a ? seeds_g.data() : nullptr; seed_b = seed_b ? seeds_g.data() + N : nullptr;
+  }
   if (seed_a) STEP(cudaMemcpyAsync(arena + o_sa, seed_a, N * 4, cudaMemcpyHostToDevice, stream));
   if (seed_b) STEP(cudaMemcpyAsync(arena + o_sb, seed_b, N * 4, cudaMemcpyHostToDevice, stream));
   if (out->pose_toc) STEP(cudaMemsetAsync(arena + o_pt, 0, N * 192, stream));
@@ -668,6 +727,94 @@ int c2a_b200_host_timing(double *out8)
 {
   if (!out8) return fail(C2A_B200_ERR_ARG, "NULL argument");
   memcpy(out8, g_host_timing, sizeof(g_host_timing));
+  return C2A_B200_OK;
+}
+
+// ---- one batch over several devices ---------------------------------------------------------
+// Queries are independent: every device holds a replica of the two models and solves its own shard; there is no
+// collective, the "gather" is each device's D2H into its own slice.  The shards interleave the cost-sorted claim
+// order (device d takes order[d], order[d + D], ...), so that the queries expected to run long are spread over the
+// devices instead of ending up in one contiguous range; one host thread + stream per device.
+int c2a_b200_solve_batch_multi(const c2a_b200_model *const *a, const c2a_b200_model *const *b, int32_t n_devices,
+                               const double *poses, const int32_t *seed_a, const int32_t *seed_b, int64_t n, double tol_d,
+                               double tol_t, const c2a_b200_results *out)
+{
+  if (!a || !b || n_devices <= 0 || !out || n < 0 || (n > 0 && !poses)) return fail(C2A_B200_ERR_ARG, "NULL argument");
+  if (n > 0x7fffffff) return fail(C2A_B200_ERR_ARG, "batch too large for 32-bit query indices");
+  if (out->num_contact || out->contacts) return fail(C2A_B200_ERR_ARG, "the contact pass is not available for multi-device batches");
+  for (int32_t d = 0; d < n_devices; d++)
+  {
+    if (!a[d] || !b[d]) return fail(C2A_B200_ERR_ARG, "NULL model handle");
+    if (a[d]->device != b[d]->device) return fail(C2A_B200_ERR_DEVICE, "models of one shard live on different devices");
+    if (a[d]->n_nodes != a[0]->n_nodes || a[d]->n_tris != a[0]->n_tris || b[d]->n_nodes != b[0]->n_nodes || b[d]->n_tris != b[0]->n_tris)
+      return fail(C2A_B200_ERR_ARG, "the per-device models are not replicas of one another");
+    for (int32_t e = 0; e < d; e++)
+      if (a[e]->device == a[d]->device) return fail(C2A_B200_ERR_DEVICE, "two shards on the same device");
+  }
+  if (n == 0) return C2A_B200_OK;
+  if (n_devices == 1) return c2a_b200_solve_batch(a[0], b[0], poses, seed_a, seed_b, n, tol_d, tol_t, out);
+  const size_t N = (size_t)n;
+  const int D = n_devices;
+  const double t0 = now_s();
+  // host half of the motion model once, on all cores; the claim order over the whole batch
+  std::vector<double> motions(N * 48);
+  motions_from_poses_mt(poses, n, motions.data(), 0);
+  std::vector<int32_t> order(N);
+  if (n >= 4096) schedule_order(motions.data(), n, a[0]->root_ang_radius, b[0]->root_ang_radius, order.data());
+  else for (size_t i = 0; i < N; i++) order[i] = (int32_t)i;
+  const double t1 = now_s();
+  std::vector<int> rcs(D, 0);
+  std::vector<std::string> errs(D);
+  std::vector<double> shard_s(D, 0.0);
+  auto work = [&](int d) {
+    const double ts = now_s();
+    const size_t nd = (N - (size_t)d + D - 1) / D;
+    std::vector<int32_t> idx(nd);
+    for (size_t k = 0; k < nd; k++) idx[k] = order[(size_t)d + k * D];
+    // per-shard outputs in call order, scattered to the caller's arrays below
+    std::vector<int32_t> status, cf, nca, nbv, ntri, lt;
+    std::vector<double> toc, dist, mint, pp, pt;
+    c2a_b200_results o;
+    memset(&o, 0, sizeof(o));
+    if (out->status) { status.resize(nd); o.status = status.data(); }
+    if (out->collisionfree) { cf.resize(nd); o.collisionfree = cf.data(); }
+    if (out->num_ca) { nca.resize(nd); o.num_ca = nca.data(); }
+    if (out->num_bv_tests) { nbv.resize(nd); o.num_bv_tests = nbv.data(); }
+    if (out->num_tri_tests) { ntri.resize(nd); o.num_tri_tests = ntri.data(); }
+    if (out->toc) { toc.resize(nd); o.toc = toc.data(); }
+    if (out->distance) { dist.resize(nd); o.distance = dist.data(); }
+    if (out->mint) { mint.resize(nd); o.mint = mint.data(); }
+    if (out->p1p2) { pp.resize(nd * 6); o.p1p2 = pp.data(); }
+    if (out->pose_toc) { pt.resize(nd * 24); o.pose_toc = pt.data(); }
+    if (out->last_tri) { lt.resize(nd * 2); o.last_tri = lt.data(); }
+    rcs[d] = solve_host(a[d], b[d], nullptr, motions.data(), nullptr, seed_a, seed_b, (int64_t)nd, tol_d, tol_t, &o, idx.data());
+    if (rcs[d]) { errs[d] = g_err; return; }
+    for (size_t k = 0; k < nd; k++)
+    {
+      const size_t q = (size_t)idx[k];
+      if (out->status) out->status[q] = status[k];
+      if (out->collisionfree) out->collisionfree[q] = cf[k];
+      if (out->num_ca) out->num_ca[q] = nca[k];
+      if (out->num_bv_tests) out->num_bv_tests[q] = nbv[k];
+      if (out->num_tri_tests) out->num_tri_tests[q] = ntri[k];
+      if (out->toc) out->toc[q] = toc[k];
+      if (out->distance) out->distance[q] = dist[k];
+      if (out->mint) out->mint[q] = mint[k];
+      if (out->p1p2) memcpy(out->p1p2 + 6 * q, &pp[6 * k], 48);
+      if (out->pose_toc) memcpy(out->pose_toc + 24 * q, &pt[24 * k], 192);
+      if (out->last_tri) memcpy(out->last_tri + 2 * q, &lt[2 * k], 8);
+    }
+    shard_s[d] = now_s() - ts;
+  };
+  std::vector<std::thread> th;
+  for (int d = 0; d < D; d++) th.emplace_back(work, d);
+  for (auto &t : th) t.join();
+  for (int d = 0; d < D; d++)
+    if (rcs[d]) return fail(rcs[d], "device shard " + std::to_string(d) + ": " + errs[d]);
+  const double t2 = now_s();
+  g_host_timing[0] = 0; g_host_timing[1] = t1 - t0; g_host_timing[2] = 0; g_host_timing[3] = 0;
+  g_host_timing[4] = *std::max_element(shard_s.begin(), shard_s.end()); g_host_timing[5] = *std::min_element(shard_s.begin(), shard_s.end());
+  g_host_timing[6] = 0; g_host_timing[7] = t2 - t0;
   return C2A_B200_OK;
 }
 
@@ -744,7 +891,7 @@ int c2a_b200_solve_pairs(const c2a_b200_model *const *models, int32_t n_models, 
   if (rc == C2A_B200_OK && (e = (x)) != cudaSuccess) rc = fail(C2A_B200_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e));
   STEP(cudaMemsetAsync(arena + o_zero, 0, off - o_zero, stream));
   PinnedLease pin;
-  STEP(pin.acquire(N * 48 * 8));
+  STEP(pin.acquire(N * 48 * 8, models[0]->device));
   std::vector<int32_t> order(N);
   if (rc == C2A_B200_OK)
   {
@@ -1062,6 +1209,27 @@ int c2a_b200_phase_stats(int32_t enable, uint64_t *out20)
     CUDA_TRY(cudaMemcpy(g_stats_dev, init, sizeof(init), cudaMemcpyHostToDevice));
   }
   if (!enable && g_stats_dev) { cudaFree(g_stats_dev); g_stats_dev = nullptr; }
+  return C2A_B200_OK;
+}
+
+// Counters of c2a_wide_kernel (development aid): enable != 0 arms / re-zeroes, out (WIDE_NSTATS = 16 words) reads the
+// counters accumulated since: steps, redone steps, rounds, leaf passes, child tests, triangle tests, events, cycles in
+// EXPAND / LEAF / resolve / fold / set-up, queries, one-pair-per-round steps, first / last globaltimer ns.
+int c2a_b200_wide_stats(int32_t enable, uint64_t *out16)
+{
+  if (out16 && g_wide_stats_dev)
+  {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out16, g_wide_stats_dev, WIDE_NSTATS * 8, cudaMemcpyDeviceToHost));
+  }
+  if (enable && !g_wide_stats_dev) CUDA_TRY(cudaMalloc(&g_wide_stats_dev, WIDE_NSTATS * 8));
+  if (enable)
+  {
+    unsigned long long init[WIDE_NSTATS] = {0};
+    init[WS_T_FIRST] = ~0ull;
+    CUDA_TRY(cudaMemcpy(g_wide_stats_dev, init, sizeof(init), cudaMemcpyHostToDevice));
+  }
+  if (!enable && g_wide_stats_dev) { cudaFree(g_wide_stats_dev); g_wide_stats_dev = nullptr; }
   return C2A_B200_OK;
 }
 

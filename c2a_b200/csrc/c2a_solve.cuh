@@ -81,13 +81,15 @@ struct BatchArgs
   const double *step_in;  // optional [n][STEP_IN_DOUBLES]: single-step mode (C2A_TimeOfContactStep), see below
   unsigned long long *stats;  // optional [14], see c2a_b200_phase_stats; NULL = off
   unsigned long long *trace;  // optional [n][2]: globaltimer at claim / at result write-out (development aid)
-  // Tail hand-over (NULL = off): once the claim queue is empty, a warp that still holds several queries
-  // passes one on, at a CA-step boundary (where a query's state is ~64 bytes: no stack), to a warp that
-  // has run out of work; alone on a warp, a query gets all 32 lanes for look-ahead.
-  unsigned long long *ctl;   // [0] hand-over tickets issued  [1] taken  [2] queries finished  [3] warps waiting for work
-  int *mb_ready;             // [mb_cap] record i is complete
-  double *mb_recs;           // [mb_cap][MB_DOUBLES]
-  int mb_cap;
+  // Hand-over to c2a_wide_kernel (c2a_wide.cuh; spill_recs = NULL: off).  Once the claim queue is empty and a warp holds
+  // at most spill_live queries, a query past its fifth CA step is written out at its next step boundary (where its
+  // state is 64 bytes: no stack) and the slot retires; the wide kernel, launched next on the stream, finishes it with
+  // parallelism inside the traversal.
+  double *spill_recs;                 // [spill_cap][MB_DOUBLES]
+  unsigned long long *spill_count;
+  long long spill_cap;
+  int spill_live;
+  int max_slots;                      // query slots a warp uses (<= Q): small batches spread over all warps
 };
 constexpr int MB_DOUBLES = 8;  // q, lamda, lastLamda, mint, UpboundTOC, {numCA, nItrs}, {nbv, ntri}, {lastA, lastB}
 
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
   if (args.stats && threadIdx.x == 0) atomicMin(args.stats + 6, global_ns());  // launch start
   for (int sl = lane; sl < Q; sl += 32)
   {
-    SI(I_STATE, sl) = ST_ADVANCE;
+    SI(I_STATE, sl) = sl < args.max_slots ? ST_ADVANCE : ST_EXIT;
     SI(I_QLO, sl) = -1; SI(I_QHI, sl) = -1;
     SI(I_PENDING, sl) = 0;
   }
@@ -239,59 +241,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
     const unsigned long long mL = __ballot_sync(FULL, st == ST_LEAF) | ((unsigned long long)__ballot_sync(FULL, st2 == ST_LEAF) << 32);
     const unsigned long long mA = __ballot_sync(FULL, st == ST_ADVANCE) | ((unsigned long long)__ballot_sync(FULL, st2 == ST_ADVANCE) << 32);
     const int n_live = __popcll(mT | mL | mA);
-    if (n_live == 0)
-    {
-      if (!args.ctl) break;
-      // out of work: wait for a query handed over by a busier warp, until every query of the batch is finished
-      long long got = -1;
-      if (lane == 0)
-      {
-        atomicAdd(args.ctl + 3, 1ull);
-        while (true)
-        {
-          if (*(volatile unsigned long long *)(args.ctl + 2) >= (unsigned long long)args.n) { got = -2; break; }
-          const unsigned long long h = *(volatile unsigned long long *)(args.ctl + 1), r = *(volatile unsigned long long *)(args.ctl + 0);
-          if (h < r && h < (unsigned long long)args.mb_cap && *(volatile int *)(args.mb_ready + h) != 0 &&
-              atomicCAS(args.ctl + 1, h, h + 1) == h)
-          {
-            got = (long long)h;
-            break;
-          }
-          __nanosleep(1000);
-        }
-        atomicAdd(args.ctl + 3, ~0ull);  // -1
-        if (got >= 0)
-        {
-          __threadfence();
-          const double *r = args.mb_recs + (size_t)got * MB_DOUBLES;
-          const long long q = __double_as_longlong(__ldcg(r + 0));
-          const double *rec = args.motions + (size_t)(2 * MOTION_DOUBLES) * q;
-          const int slot = 0;
-#pragma unroll
-          for (int i = 0; i < 3; i++)
-          {
-            SD(F_CV1 + i, slot) = __ldg(rec + 12 + i); SD(F_AX1 + i, slot) = __ldg(rec + 15 + i);
-            SD(F_CV2 + i, slot) = __ldg(rec + MOTION_DOUBLES + 12 + i); SD(F_AX2 + i, slot) = __ldg(rec + MOTION_DOUBLES + 15 + i);
-          }
-          SD(F_W1, slot) = __ldg(rec + 18); SD(F_W2, slot) = __ldg(rec + MOTION_DOUBLES + 18);
-          SI(I_SEEDA, slot) = args.seedA ? args.seedA[q] : 0;
-          SI(I_SEEDB, slot) = args.seedB ? args.seedB[q] : 0;
-          SD(F_LAMDA, slot) = __ldcg(r + 1); SD(F_LASTL, slot) = __ldcg(r + 2); SD(F_MINT, slot) = __ldcg(r + 3); SD(F_UPB, slot) = __ldcg(r + 4);
-          const double c5 = __ldcg(r + 5), c6 = __ldcg(r + 6), c7 = __ldcg(r + 7);
-          SI(I_NUMCA, slot) = __double2hiint(c5); SI(I_NITRS, slot) = __double2loint(c5);
-          SI(I_NBV, slot) = __double2hiint(c6); SI(I_NTRI, slot) = __double2loint(c6);
-          SI(I_LASTA, slot) = __double2hiint(c7); SI(I_LASTB, slot) = __double2loint(c7);
-          SD(F_DIST, slot) = 0;
-          SI(I_QLO, slot) = (int)(unsigned)(q & 0xffffffffll); SI(I_QHI, slot) = (int)(q >> 32);
-          SI(I_PENDING, slot) = 1;
-          SI(I_STATE, slot) = ST_ADVANCE;
-        }
-      }
-      got = __shfl_sync(FULL, got, 0);
-      if (got == -2) break;
-      __syncwarp();
-      continue;
-    }
+    if (n_live == 0) break;
     const int nT = __popcll(mT), nL = min(__popcll(mL), 32), nA = min(__popcll(mA), 32);  // a pass serves at most 32 slots
     // Phase choice: a full expansion pass (16 slots x 2 lanes) whenever one is available; otherwise
     // first turn waiting slots back into traversable ones (the larger of the LEAF / ADVANCE groups),
@@ -302,7 +252,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
     else if (nL > 0 || nA > 0) phase = (nL >= nA) ? ST_LEAF : ST_ADVANCE;
     else phase = ST_TRAVERSE;
 
-    const bool steady = (mT | mL | mA) == ((1ull << Q) - 1ull);  // statistics cover warps whose slots are all live (not the tail)
+    const bool steady = n_live == args.max_slots && n_live == Q;  // statistics cover warps whose slots are all live (not the tail)
     if (args.stats && lane == 0 && steady)
     {
       const int k = phase == ST_TRAVERSE ? 0 : (phase == ST_LEAF ? 2 : 4);
@@ -750,32 +700,25 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
             if (o.distance) o.distance[q] = dist;
             if (o.mint) o.mint[q] = mint;
             if (o.last_tri) { o.last_tri[2 * q] = SI(I_LASTA, slot); o.last_tri[2 * q + 1] = SI(I_LASTB, slot); }
-            if (args.ctl) atomicAdd(args.ctl + 2, 1ull);
             if (args.trace) args.trace[2 * q + 1] = global_ns();
             q = -1;
           }
         }
 
-        // tail hand-over: the queue is empty (this warp holds exited slots), the warp has other live
-        // queries, and some warp is waiting for work -> pass this query on at its step boundary
-        if (args.ctl && just_continued && lane == 0 && n_live > 1 && n_live < Q)
+        // hand-over to the wide kernel: the queue is empty, the warp is running out of queries, and this query's
+        // remaining steps are all in exact mode (numCA > 5, C2A.cpp:1869) -> write its CA-loop state out and retire
+        if (args.spill_recs && just_continued && numCA > 5 && n_live <= args.spill_live &&
+            *(volatile unsigned long long *)args.counter >= (unsigned long long)args.n)
         {
-          const unsigned long long waiting = *(volatile unsigned long long *)(args.ctl + 3);
-          const unsigned long long issued = *(volatile unsigned long long *)(args.ctl + 0), taken = *(volatile unsigned long long *)(args.ctl + 1);
-          if (waiting > issued - taken)
+          const unsigned long long idx = atomicAdd(args.spill_count, 1ull);
+          if (idx < (unsigned long long)args.spill_cap)
           {
-            const unsigned long long idx = atomicAdd(args.ctl + 0, 1ull);
-            if (idx < (unsigned long long)args.mb_cap)
-            {
-              double *r = args.mb_recs + (size_t)idx * MB_DOUBLES;
-              r[0] = __longlong_as_double(q); r[1] = lamda; r[2] = SD(F_LASTL, slot); r[3] = SD(F_MINT, slot); r[4] = SD(F_UPB, slot);
-              r[5] = __hiloint2double(numCA, SI(I_NITRS, slot)); r[6] = __hiloint2double(SI(I_NBV, slot), SI(I_NTRI, slot));
-              r[7] = __hiloint2double(SI(I_LASTA, slot), SI(I_LASTB, slot));
-              __threadfence();
-              *(volatile int *)(args.mb_ready + idx) = 1;
-              SI(I_STATE, slot) = ST_EXIT;
-              q = -1; pending = false; handed_over = true;
-            }
+            double *r = args.spill_recs + (size_t)idx * MB_DOUBLES;
+            r[0] = __longlong_as_double(q); r[1] = lamda; r[2] = SD(F_LASTL, slot); r[3] = SD(F_MINT, slot); r[4] = SD(F_UPB, slot);
+            r[5] = __hiloint2double(numCA, SI(I_NITRS, slot)); r[6] = __hiloint2double(SI(I_NBV, slot), SI(I_NTRI, slot));
+            r[7] = __hiloint2double(SI(I_LASTA, slot), SI(I_LASTB, slot));
+            SI(I_STATE, slot) = ST_EXIT;
+            q = -1; pending = false; handed_over = true;
           }
         }
 
@@ -798,7 +741,6 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
             {
               // translation-only branch of the reference (C2A.cpp:2391-2395): solved by c2a_translation_kernel,
               // which the host launches over the same batch right after this kernel
-              if (args.ctl) atomicAdd(args.ctl + 2, 1ull);
               q = -1;  // stay in ADVANCE: claim another one next round
             }
             else

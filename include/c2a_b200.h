@@ -136,6 +136,17 @@ int c2a_b200_solve_batch(const c2a_b200_model *a, const c2a_b200_model *b, const
                          const int32_t *seed_a, const int32_t *seed_b, int64_t n, double tol_d, double tol_t,
                          const c2a_b200_results *out);
 
+/* The same batch sharded over n_devices GPUs of one box (no counterpart in the reference, whose
+ * C2A_Solve is single-threaded: global b_TanslationCCD, C2A/src/C2A.cpp:33).  a[d], b[d]: replicas of the two models
+ * uploaded to n_devices distinct devices.  Queries are independent, so there is no collective: the host computes the
+ * motion constants and the claim order once, device d solves the queries order[d], order[d + n_devices], ... (the
+ * cost-sorted order interleaved, so that long-running queries spread over the devices) on its own host thread and
+ * stream, and the "gather" is each device's D2H followed by a scatter into the caller's arrays.  Host buffers;
+ * results are identical to c2a_b200_solve_batch's for any n_devices.  The contact pass is not available here. */
+int c2a_b200_solve_batch_multi(const c2a_b200_model *const *a, const c2a_b200_model *const *b, int32_t n_devices,
+                               const double *poses, const int32_t *seed_a, const int32_t *seed_b, int64_t n, double tol_d,
+                               double tol_t, const c2a_b200_results *out);
+
 /* Batched C2A_QueryContact (C2A/C2A.h:284-289, C2A/src/C2A.cpp:1937-1966): all triangle pairs within
  * threshold[i] at the poses poses24[i] = pose of A, pose of B (R(9)+T(3) each).  Host buffers. */
 int c2a_b200_contacts_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses24,

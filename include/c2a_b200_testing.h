@@ -32,6 +32,9 @@ int c2a_b200_host_sincos(const double *x, int64_t n, double *s, double *c);
 /* Phase statistics of the solve kernel (development aid): see c2a_kernels.cu. */
 int c2a_b200_phase_stats(int32_t enable, uint64_t *out20);
 
+/* Counters of the wide traversal kernel (development aid): see c2a_kernels.cu. */
+int c2a_b200_wide_stats(int32_t enable, uint64_t *out16);
+
 /* Per-query timeline (development aid): n > 0 arms a [n][2] device buffer that the next batches of <= n queries fill
  * with the globaltimer (ns) at claim and at result write-out; n == 0 copies it to out; n < 0 frees it. */
 int c2a_b200_query_trace(int64_t n, uint64_t *out);

@@ -41,7 +41,7 @@ REPLAY_STATS_DTYPE = np.dtype([("steps", np.int64), ("visits", np.int64), ("hits
                                ("misses", np.int64), ("preeval", np.int64), ("wasted", np.int64)], align=True)
 
 
-WIDE_STATS_DTYPE = np.dtype([(k, np.int64) for k in ("window", "steps", "redo", "anomalies", "closure_fail", "events", "rounds",
+WIDE_STATS_DTYPE = np.dtype([(k, np.int64) for k in ("window", "leaf_batch", "leaf_passes", "steps", "redo", "anomalies", "closure_fail", "events", "rounds",
                                                     "max_width", "max_stack", "max_unresolved", "wide_tests",
                                                     "wide_tests_visited", "wide_leaves", "wide_leaves_visited")], align=True)
 
@@ -140,7 +140,7 @@ class _Port:
                                       C.c_void_p(out[i:i + 1].ctypes.data), _ptr(st))
         return out, {k: st[k][0].item() for k in st.dtype.names}
 
-    def solve_wide(self, bvhA, bvhB, poses, seedA=None, seedB=None, tol_d=1e-4, tol_t=1e-4, window=16):
+    def solve_wide(self, bvhA, bvhB, poses, seedA=None, seedB=None, tol_d=1e-4, tol_t=1e-4, window=16, leaf_batch=0):
         """Round-2 algorithm on the CPU: exact-mode CA steps as a depth-first traversal popping `window` pairs per round.
         Returns (results like solve_batch, dict of accumulated statistics)."""
         sA, sB = bvh_struct(bvhA), bvh_struct(bvhB)
@@ -148,6 +148,7 @@ class _Port:
         out = np.zeros(len(poses), dtype=RESULT_DTYPE)
         st = np.zeros(1, dtype=WIDE_STATS_DTYPE)
         st["window"] = window
+        st["leaf_batch"] = leaf_batch
         for i in range(len(poses)):
             self.lib.orc_solve_wide(C.byref(sA), C.byref(sB), _ptr(poses[i]), C.c_int32(0 if seedA is None else int(seedA[i])),
                                     C.c_int32(0 if seedB is None else int(seedB[i])), C.c_double(tol_d), C.c_double(tol_t),

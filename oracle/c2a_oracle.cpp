@@ -1184,20 +1184,39 @@ void wide_step(Step &st, const double R[9], const double T[3])
     n.leafpair = A->first_child[0] < 0 && B->first_child[0] < 0;
     nodes.push_back(n); stack.push_back(0);
   }
-  long long rounds = 0;
+  long long rounds = 0, leaf_passes = 0;
   std::vector<int> win, kids;
-  while (!stack.empty() && !anomaly && !overflow)
+  std::vector<int> pending;     // leaf pairs waiting for a LEAF pass (device: batched, 32 lanes per pass); empty when leaf_batch = 0
+  const int LB = (int)ws.leaf_batch;
+  while ((!stack.empty() || !pending.empty()) && !anomaly && !overflow)
   {
+    kids.clear();
+    if (LB > 0 && ((int)pending.size() >= LB || stack.empty()))
+    {
+      // LEAF pass: up to 32 waiting leaf pairs, oldest first; those that no longer pass are dropped
+      leaf_passes++;
+      int done = 0; size_t i = 0;
+      for (; i < pending.size() && done < 32; i++)
+      {
+        WNode &n = nodes[pending[i]];
+        const double M = n.Mpar > n.val ? n.Mpar : n.val;
+        if (!(M < Dw)) continue;
+        n.expanded = true; wide_leaf_eval(st, n); unresolved.push_back(pending[i]); ws.wide_leaves++; done++;
+      }
+      pending.erase(pending.begin(), pending.begin() + i);
+    }
+    else
+    {
     rounds++;
     // pop the window: entries that fail under Dw are dropped (their step bound is folded at the end, from the records)
     win.clear();
     while (!stack.empty() && (int)win.size() < W)
     {
       const int i = stack.back(); stack.pop_back();
-      if (nodes[i].val < Dw) win.push_back(i);
+      const double M = nodes[i].Mpar > nodes[i].val ? nodes[i].Mpar : nodes[i].val;
+      if (M < Dw) win.push_back(i);
     }
     if ((long long)win.size() > ws.max_width) ws.max_width = (long long)win.size();
-    kids.clear();
     for (int wi : win)
     {
       nodes[wi].expanded = true;
@@ -1227,12 +1246,18 @@ void wide_step(Step &st, const double R[9], const double T[3])
     }
     // push the children in reverse visiting order (the window's first pair's first child ends up on top)
     for (int i = (int)kids.size() - 1; i >= 0; i--)
-      if (nodes[kids[i]].val < Dw) stack.push_back(kids[i]);
+      if (nodes[kids[i]].val < Dw)
+      {
+        if (LB > 0 && nodes[kids[i]].leafpair) pending.push_back(kids[i]); else stack.push_back(kids[i]);
+      }
     if ((long long)stack.size() > ws.max_stack) ws.max_stack = (long long)stack.size();
-    // resolve the events that precede the new top of the stack, in key order
+    }
+    // resolve the events that precede everything still to be evaluated (the top of the stack, the waiting leaf pairs), in key order
+    const uint64_t *front = stack.empty() ? nullptr : nodes[stack.back()].key;
+    for (int pi : pending) if (!front || wkey_less(nodes[pi].key, front)) front = nodes[pi].key;
     std::vector<int> ready, later;
     for (int li : unresolved)
-      if (stack.empty() || wkey_less(nodes[li].key, nodes[stack.back()].key)) ready.push_back(li); else later.push_back(li);
+      if (!front || wkey_less(nodes[li].key, front)) ready.push_back(li); else later.push_back(li);
     std::sort(ready.begin(), ready.end(), [&](int x, int y) { return wkey_less(nodes[x].key, nodes[y].key); });
     if ((long long)later.size() > ws.max_unresolved) ws.max_unresolved = (long long)later.size();
     for (int li : ready)
@@ -1247,6 +1272,7 @@ void wide_step(Step &st, const double R[9], const double T[3])
     }
     unresolved.swap(later);
   }
+  ws.leaf_passes += leaf_passes;
   ws.rounds += rounds;
   if (anomaly || overflow) { ws.anomalies += anomaly ? 1 : 0; ws.redo++; st = st0; toc_recurse(st, R, T, 0, 0); return; }
   ws.events += (long long)eleaf.size();
@@ -1917,6 +1943,7 @@ extern "C" void orc_solve_wide(const orc_bvh *A, const orc_bvh *B, const double 
                                double tol_d, double tol_t, orc_result *out, orc_wide_stats *stats)
 {
   if (stats->window <= 0) stats->window = 16;
+  if (stats->leaf_batch < 0) stats->leaf_batch = 0;
   g_wide = stats;
   orc_solve(A, B, poses, seedA, seedB, tol_d, tol_t, out);
   g_wide = nullptr;

@@ -153,6 +153,9 @@ void orc_solve_replay(const orc_bvh *A, const orc_bvh *B, const double poses[48]
 typedef struct orc_wide_stats
 {
   long long window;                                 /* in: node pairs popped per round */
+  long long leaf_batch;                             /* in: 0 = leaf pairs are tested in the window they are popped in; n > 0 = they wait for a
+                                                       LEAF pass, run when n are waiting or nothing else is left (32 per pass), as on the device */
+  long long leaf_passes;
   long long steps, redo, anomalies, closure_fail, events, rounds, max_width, max_stack, max_unresolved;
   long long wide_tests, wide_tests_visited, wide_leaves, wide_leaves_visited;
 } orc_wide_stats;

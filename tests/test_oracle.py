@@ -228,6 +228,33 @@ def test_replay_over_previous_visit_list_is_exact(golden, bvhs):
         assert st["visits"] == st["hits"] + st["misses"] and st["hits"] > st["misses"] > 0
 
 
+def test_wide_traversal_is_exact(golden, bvhs):
+    """The round-2 device algorithm stated on the CPU (orc_solve_wide, the checker of c2a_wide.cuh): exact-mode CA steps
+    as a depth-first traversal that pops W node pairs per round, with keys, the M rule, in-order event resolution and
+    the fold, give the reference's results bit for bit -- for any window, with and without batched leaf passes, on
+    the bunny as well (seeded, non-default tolerances)."""
+    P = oracle.port()
+    cases = (("ref_knot_128x16", "knot_128x16", "knot_128x16", 40), ("ref_knot_128x16_grazing_tol1e-06", "knot_128x16", "knot_128x16", 30),
+             ("ref_bunny_vs_knot_seeded", "bunny", "knot_512x32", 25), ("ref_bunny_grazing_tol1e-06", "bunny", "bunny", 20))
+    for case, ma, mb, k in cases:
+        g = golden(case)
+        idx = np.concatenate([np.argsort(-g["num_bv_tests"])[:k], np.arange(k)])
+        for W, lb in ((1, 0), (16, 32), (5, 7), (64, 0)):
+            res, st = P.solve_wide(bvhs(ma), bvhs(mb), g["poses"][idx], None if "seed_a" not in g else g["seed_a"][idx],
+                                   None if "seed_b" not in g else g["seed_b"][idx], tol_d=float(g["tol_d"]), tol_t=float(g["tol_t"]),
+                                   window=W, leaf_batch=lb)
+            for f in ("collisionfree", "numCA", "num_bv_tests", "num_tri_tests", "toc", "distance", "mint", "pose_toc"):
+                assert np.array_equal(res[f], g[f][idx]), (case, W, f)
+            upd = (res["p1"] != 0).any(1)
+            assert np.array_equal(np.concatenate([res["p1"], res["p2"]], 1)[upd], g["p1p2"][idx][upd]), (case, W)
+            if "last_tri" in g:
+                assert np.array_equal(np.stack([res["last_tri_a"], res["last_tri_b"]], 1), g["last_tri"][idx]), (case, W)
+            assert st["steps"] > 0 and st["closure_fail"] == 0
+            assert st["wide_tests_visited"] <= st["wide_tests"]
+            if W == 1:
+                assert st["wide_tests_visited"] == st["wide_tests"] and st["redo"] == 0  # the sequential walk itself
+
+
 def test_visit_sequences_account_for_the_counters(golden, bvhs):
     """Round-2 design study hook (orc_solve_visits): every visited node pair is an expansion (2 BV tests) or a leaf
     pair (1 triangle test), so the logged sequences must add up to the query's counters."""
