@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(128) c2a_distance_kernel(const DistanceArgs ar
     mt_m(Rrel, R1, R2);
     v_sub(Tt, T2, T1);
     mt_v(Trel, R1, Tt);
-    int ta = args.seedA ? args.seedA[q] : 0, tb = args.seedB ? args.seedB[q] : 0;
+    int ta = seed_or_zero(args.seedA, q, args.A.n_tris), tb = seed_or_zero(args.seedB, q, args.B.n_tris);
     double p1[3], p2[3];
     // initial upper bound from the last closest triangle pair, :995-1000
     double dist = tri_distance_v(Rrel, Trel, A.tris + (size_t)TRI_STRIDE * ta, B.tris + (size_t)TRI_STRIDE * tb, p1, p2);

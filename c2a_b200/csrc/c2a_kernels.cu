@@ -250,6 +250,10 @@ static unsigned long long *g_stats_dev = nullptr;  // phase statistics (c2a_b200
 static unsigned long long *g_trace_dev = nullptr;  // per-query claim / finish times (c2a_b200_query_trace), off by default
 static unsigned long long *g_wide_stats_dev = nullptr;  // counters of c2a_wide_kernel (c2a_b200_wide_stats), off by default
 
+// CUDA events round the kernels of this thread's last launch_batch (c2a_b200_kernel_times): measurement aid
+struct KernelEvents { int device = -1; cudaEvent_t e[4]; bool recorded = false; };
+static thread_local KernelEvents g_kev;
+
 static long long env_ll(const char *name, long long dflt)
 {
   const char *v = getenv(name);
@@ -349,7 +353,19 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   args.stats = g_stats_dev;
   args.trace = (g_trace_dev && n <= g_trace_n && !step_in) ? g_trace_dev : nullptr;
   CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+  if (g_kev.device != a->device)
+  {
+    if (g_kev.device >= 0) for (auto &ev : g_kev.e) cudaEventDestroy(ev);
+    g_kev.device = -1;
+    bool ok = true;
+    for (auto &ev : g_kev.e) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
+    if (ok) g_kev.device = a->device;
+  }
+  const bool kev = g_kev.device == a->device;
+  g_kev.recorded = false;
+  if (kev) cudaEventRecord(g_kev.e[0], stream);
   c2a_solve_kernel<<<(unsigned)blocks, BLOCK_THREADS, BLOCK_SMEM_BYTES, stream>>>(args);
+  if (kev) cudaEventRecord(g_kev.e[1], stream);
   g_launches.fetch_add(1);
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) return fail(C2A_B200_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(le));
@@ -369,6 +385,7 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
     le = cudaGetLastError();
     if (le != cudaSuccess) return fail(C2A_B200_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(le));
   }
+  if (kev) cudaEventRecord(g_kev.e[2], stream);
   if (!step_in)
   {
     // translation-only queries (both angular speeds < 1e-8) were skipped by the kernel above: the reference
@@ -386,6 +403,7 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
     le = cudaGetLastError();
     if (le != cudaSuccess) return fail(C2A_B200_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(le));
   }
+  if (kev) { cudaEventRecord(g_kev.e[3], stream); g_kev.recorded = true; }
   return C2A_B200_OK;
 }
 
@@ -412,6 +430,17 @@ static int launch_contacts(const c2a_b200_model *a, const c2a_b200_model *b, con
   c2a_contact_kernel<<<(unsigned)blocks, 128, 0, stream>>>(args);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
+  return C2A_B200_OK;
+}
+
+// host-side seed check (the device-pointer entry cannot look at its seeds: the kernels map bad ones to triangle 0)
+static int check_seeds(const int32_t *seeds, int64_t n, int n_tris, const char *which)
+{
+  if (!seeds) return C2A_B200_OK;
+  for (int64_t i = 0; i < n; i++)
+    if ((uint32_t)seeds[i] >= (uint32_t)n_tris)
+      return fail(C2A_B200_ERR_ARG, std::string(which) + "[" + std::to_string(i) + "] = " + std::to_string(seeds[i]) + " is not a triangle of the model (" +
+                                        std::to_string(n_tris) + " triangles)");
   return C2A_B200_OK;
 }
 
@@ -467,6 +496,8 @@ int c2a_b200_distance_batch(const c2a_b200_model *a, const c2a_b200_model *b, co
   if (a->device != b->device) return fail(C2A_B200_ERR_DEVICE, "models live on different devices");
   if (a->depth + b->depth + 2 > DIST_STACK) return fail(C2A_B200_ERR_DEPTH, "BVH depths exceed the distance query's stack");
   if (n == 0) return C2A_B200_OK;
+  if (int rc = check_seeds(seed_a, n, a->n_tris, "seed_a")) return rc;
+  if (int rc = check_seeds(seed_b, n, b->n_tris, "seed_b")) return rc;
   CUDA_TRY(cudaSetDevice(a->device));
   const size_t N = (size_t)n;
   size_t off = 0;
@@ -604,6 +635,7 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
   int rc = check_pair(a, b, n, poses ? poses : motions, out);
   if (rc) return rc;
   if (n == 0) return C2A_B200_OK;
+  if (!gather && ((rc = check_seeds(seed_a, n, a->n_tris, "seed_a")) || (rc = check_seeds(seed_b, n, b->n_tris, "seed_b")))) return rc;
   const bool want_contacts = !step_in && (out->num_contact || out->contacts);
   if (want_contacts && out->contacts && out->max_contacts <= 0) return fail(C2A_B200_ERR_ARG, "contacts requested with max_contacts <= 0");
   CUDA_TRY(cudaSetDevice(a->device));
@@ -752,6 +784,8 @@ int c2a_b200_solve_batch_multi(const c2a_b200_model *const *a, const c2a_b200_mo
       if (a[e]->device == a[d]->device) return fail(C2A_B200_ERR_DEVICE, "two shards on the same device");
   }
   if (n == 0) return C2A_B200_OK;
+  if (int rc = check_seeds(seed_a, n, a[0]->n_tris, "seed_a")) return rc;
+  if (int rc = check_seeds(seed_b, n, b[0]->n_tris, "seed_b")) return rc;
   if (n_devices == 1) return c2a_b200_solve_batch(a[0], b[0], poses, seed_a, seed_b, n, tol_d, tol_t, out);
   const size_t N = (size_t)n;
   const int D = n_devices;
@@ -840,6 +874,8 @@ int c2a_b200_solve_pairs(const c2a_b200_model *const *models, int32_t n_models, 
   {
     if (model_a[i] < 0 || model_a[i] >= n_models || model_b[i] < 0 || model_b[i] >= n_models)
       return fail(C2A_B200_ERR_ARG, "model index out of range");
+    if ((seed_a && (uint32_t)seed_a[i] >= (uint32_t)models[model_a[i]]->n_tris) || (seed_b && (uint32_t)seed_b[i] >= (uint32_t)models[model_b[i]]->n_tris))
+      return fail(C2A_B200_ERR_ARG, "seed of query " + std::to_string(i) + " is not a triangle of its model");
     start[(size_t)model_a[i] * n_models + model_b[i] + 1]++;
   }
   for (size_t g = 0; g < (size_t)n_models * n_models; g++) start[g + 1] += start[g];
@@ -1209,6 +1245,23 @@ int c2a_b200_phase_stats(int32_t enable, uint64_t *out20)
     CUDA_TRY(cudaMemcpy(g_stats_dev, init, sizeof(init), cudaMemcpyHostToDevice));
   }
   if (!enable && g_stats_dev) { cudaFree(g_stats_dev); g_stats_dev = nullptr; }
+  return C2A_B200_OK;
+}
+
+// Durations (ms) of the kernels of the calling thread's last batch launch -- c2a_solve_kernel, c2a_wide_kernel,
+// c2a_translation_kernel -- from CUDA events on the launching stream; waits for that launch to finish.
+int c2a_b200_kernel_times(double *out3)
+{
+  if (!out3) return fail(C2A_B200_ERR_ARG, "NULL argument");
+  if (!g_kev.recorded) return fail(C2A_B200_ERR_ARG, "no batch launch on this thread yet");
+  CUDA_TRY(cudaSetDevice(g_kev.device));
+  CUDA_TRY(cudaEventSynchronize(g_kev.e[3]));
+  for (int i = 0; i < 3; i++)
+  {
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, g_kev.e[i], g_kev.e[i + 1]));
+    out3[i] = ms;
+  }
   return C2A_B200_OK;
 }
 

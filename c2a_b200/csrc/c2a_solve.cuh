@@ -153,6 +153,14 @@ C2A_DEV NodeMeta load_meta(const NodeMeta *p)
   m.size = v.x; m.first_child = __double2loint(v.y); m.pad = 0;
   return m;
 }
+// per-query seed triangle (res->last_triA/B); an index outside the model falls back to triangle 0 (the state after
+// EndModel, C2A_PQP.cpp:401) instead of reading out of bounds -- the host entries reject such seeds with ERR_ARG
+C2A_DEV int seed_or_zero(const int *seeds, long long q, int n_tris)
+{
+  if (!seeds) return 0;
+  const int s = seeds[q];
+  return ((unsigned)s < (unsigned)n_tris) ? s : 0;
+}
 C2A_DEV unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 C2A_DEV void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -752,8 +760,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
                 SD(F_CV2 + i, slot) = __ldg(rec + MOTION_DOUBLES + 12 + i); SD(F_AX2 + i, slot) = __ldg(rec + MOTION_DOUBLES + 15 + i);
               }
               SD(F_W1, slot) = w1; SD(F_W2, slot) = w2;
-              SI(I_SEEDA, slot) = args.seedA ? args.seedA[q] : 0;
-              SI(I_SEEDB, slot) = args.seedB ? args.seedB[q] : 0;
+              SI(I_SEEDA, slot) = seed_or_zero(args.seedA, q, A.n_tris);
+              SI(I_SEEDB, slot) = seed_or_zero(args.seedB, q, B.n_tris);
               numCA = 0; lamda = 0;
               SI(I_NITRS, slot) = 0; SI(I_NBV, slot) = 0; SI(I_NTRI, slot) = 0;
               SI(I_LASTA, slot) = -1; SI(I_LASTB, slot) = -1;

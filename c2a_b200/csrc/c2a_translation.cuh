@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(128) c2a_translation_kernel(const TransArgs ar
     v_sub(Tt, Tt, &g1[9]);
     mt_v(T, g1, Tt);
 
-    int lastA = args.seedA ? args.seedA[q] : 0, lastB = args.seedB ? args.seedB[q] : 0;  // res->last_triA / last_triB
+    int lastA = seed_or_zero(args.seedA, q, args.A.n_tris), lastB = seed_or_zero(args.seedB, q, args.B.n_tris);  // res->last_triA / last_triB
     double res_mint, res_dist;
     {
       // seed: advancement of the two seed triangles, :1818-1852

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
     int nbv = __double2hiint(c6), ntri = __double2loint(c6);
     int lastA = __double2hiint(c7), lastB = __double2loint(c7);
     const double *rec = args.motions + (size_t)(2 * MOTION_DOUBLES) * q;
-    const int seedA = args.seedA ? args.seedA[q] : 0, seedB = args.seedB ? args.seedB[q] : 0;
+    const int seedA = seed_or_zero(args.seedA, q, A.n_tris), seedB = seed_or_zero(args.seedB, q, B.n_tris);
     double dist = 0;
     if (args.stats && lane == 0) atomicAdd(args.stats + WS_QUERIES, 1ull);
 

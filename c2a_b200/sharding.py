@@ -1,7 +1,14 @@
-"""Multi-GPU plumbing: independent queries shard across ranks with no data-path collective
-(SURVEY.md section 8e).  Each rank owns one GPU, holds a replica of every model and solves a
-contiguous slice of the batch; the only exchange is the final gather of per-query results."""
+"""Multi-GPU plumbing for one rank per GPU (bench.py under torchrun): independent queries shard across ranks with no
+data-path collective.  Each rank holds a replica of the models and solves every world-th entry
+of the batch's cost-sorted claim order -- the same split the library's multi-device entry
+(c2a_b200_solve_batch_multi) makes over the devices of one process -- so that the queries expected to run long are
+spread over the GPUs; the only exchange is the final gather of per-query results, scattered back to batch order."""
 import numpy as np
+
+
+def shard_indices(order, rank, world):
+    """Queries of rank ``rank``: order[rank], order[rank + world], ...  (order = api.schedule_order, or arange)."""
+    return np.ascontiguousarray(np.asarray(order)[int(rank)::int(world)])
 
 
 def shard_bounds(n, rank, world):
@@ -11,18 +18,25 @@ def shard_bounds(n, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def gather_results(local, n_total, rank, world, dist=None, dst=0):
-    """Gather per-rank result dicts (field -> ndarray over the local slice) on rank ``dst``.
-    Returns the full dict on ``dst`` and None elsewhere.  ``dist`` is torch.distributed (any backend);
-    with world == 1 nothing is exchanged."""
-    if world == 1:
-        return local
-    parts = [None] * world if rank == dst else None
-    dist.gather_object(local, parts, dst=dst)
-    if rank != dst:
-        return None
+def gather_results(local, idx, n_total, rank, world, dist=None, dst=0):
+    """Gather per-rank result dicts (field -> ndarray over the rank's queries ``idx``) on rank ``dst`` and scatter them
+    to batch order.  Returns the full dict on ``dst`` and None elsewhere.  ``dist`` is torch.distributed (any
+    backend); with world == 1 nothing is exchanged."""
+    parts = [(np.asarray(idx), local)]
+    if world > 1:
+        got = [None] * world if rank == dst else None
+        dist.gather_object((np.asarray(idx), local), got, dst=dst)
+        if rank != dst:
+            return None
+        parts = got
     out = {}
-    for k in parts[0]:
-        out[k] = np.concatenate([p[k] for p in parts], 0)
-        assert out[k].shape[0] == n_total
+    seen = np.zeros(n_total, dtype=bool)
+    for ix, res in parts:
+        assert not seen[ix].any()
+        seen[ix] = True
+        for k, v in res.items():
+            if k not in out:
+                out[k] = np.zeros((n_total,) + v.shape[1:], dtype=v.dtype)
+            out[k][ix] = v
+    assert seen.all()
     return out

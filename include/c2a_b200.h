@@ -126,7 +126,9 @@ int c2a_b200_model_info(const c2a_b200_model *m, int32_t *device, int32_t *n_nod
  * queries on the models' device.  poses: [n][48] = trans00, trans01, trans10, trans11, each R (9,
  * row-major) + T (3) (the four Transform* of C2A_Solve).  seed_a / seed_b: [n] triangle indices
  * standing in for res->last_triA / last_triB (C2A/src/C2A.cpp:1816-1817; NULL = triangle 0, the
- * state after EndModel, C2A/src/C2A_PQP.cpp:401).  tol_d / tol_t: C2A_Solve hard-codes 1e-4 for
+ * state after EndModel, C2A/src/C2A_PQP.cpp:401); every seed must be a triangle index of its model: the host-buffer
+ * entries return C2A_B200_ERR_ARG otherwise, the device-pointer entry cannot inspect its seeds and treats an
+ * out-of-range one as triangle 0.  tol_d / tol_t: C2A_Solve hard-codes 1e-4 for
  * both (C2A/src/C2A.cpp:2384-2385); C2A_QueryTimeOfContact takes them as arguments.
  * Queries whose two angular speeds are both < 1e-8 take the reference's translation-only branch
  * (C2A/src/C2A.cpp:2391-2395, :1362-1521; CInterpMotion::m_toc_delta = tol_d as C2A_Solve sets it): toc = the

@@ -32,6 +32,9 @@ int c2a_b200_host_sincos(const double *x, int64_t n, double *s, double *c);
 /* Phase statistics of the solve kernel (development aid): see c2a_kernels.cu. */
 int c2a_b200_phase_stats(int32_t enable, uint64_t *out20);
 
+/* Durations (ms) of the three kernels of the calling thread's last batch launch (CUDA events on its stream). */
+int c2a_b200_kernel_times(double *out3);
+
 /* Counters of the wide traversal kernel (development aid): see c2a_kernels.cu. */
 int c2a_b200_wide_stats(int32_t enable, uint64_t *out16);
 

@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 #include <thread>
 #include <vector>
 #include <algorithm>
@@ -1626,9 +1627,17 @@ extern "C" void orc_solve_batch(const orc_bvh *A, const orc_bvh *B, const double
                                 orc_result *out, int32_t n_threads)
 {
   if (n_threads < 1) n_threads = 1;
-  auto work = [&](int tid) {
-    for (int64_t i = tid; i < n; i += n_threads)
-      orc_solve(A, B, poses + 48 * i, seedA ? seedA[i] : 0, seedB ? seedB[i] : 0, tol_d, tol_t, &out[i]);
+  // dynamic queue of 16-query chunks: the cost per query has a long tail, a static split would time the unluckiest thread
+  std::atomic<int64_t> next(0);
+  auto work = [&](int) {
+    while (true)
+    {
+      const int64_t lo = next.fetch_add(16);
+      if (lo >= n) break;
+      const int64_t hi = lo + 16 < n ? lo + 16 : n;
+      for (int64_t i = lo; i < hi; i++)
+        orc_solve(A, B, poses + 48 * i, seedA ? seedA[i] : 0, seedB ? seedB[i] : 0, tol_d, tol_t, &out[i]);
+    }
   };
   if (n_threads == 1) { work(0); return; }
   std::vector<std::thread> th;

@@ -11,6 +11,7 @@
 #include <string.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -231,11 +232,19 @@ void ref_solve_batch(void *hA, void *hB, const double *poses, int64_t n, const i
   }
   // threaded phase: rotational queries only (b_TanslationCCD stays false, written with the same value)
   b_TanslationCCD = false;
+  // dynamic queue of 16-query chunks: the cost per query has a long tail, a static split would time the unluckiest thread
   std::vector<std::thread> th;
+  std::atomic<int64_t> next(0);
   for (int t = 0; t < n_threads; t++)
-    th.emplace_back([=]() {
-      for (int64_t i = t; i < n; i += n_threads)
-        query_toc(A, B, poses + 48 * i, seedA ? seedA[i] : 0, seedB ? seedB[i] : 0, tol_d, tol_t, &out[i], false);
+    th.emplace_back([=, &next]() {
+      while (true)
+      {
+        const int64_t lo = next.fetch_add(16);
+        if (lo >= n) break;
+        const int64_t hi = lo + 16 < n ? lo + 16 : n;
+        for (int64_t i = lo; i < hi; i++)
+          query_toc(A, B, poses + 48 * i, seedA ? seedA[i] : 0, seedB ? seedB[i] : 0, tol_d, tol_t, &out[i], false);
+      }
     });
   for (auto &t : th) t.join();
   // serial phase: translation-only queries

@@ -119,6 +119,17 @@ def test_no_cpu_fallback_without_gpu(bvhs):
         api.Model(bvhs("knot_128x16"), 0)
 
 
+def test_shard_indices_partition():
+    rng = np.random.default_rng(3)
+    for n in (1, 7, 8, 1003):
+        order = rng.permutation(n)
+        for w in (1, 2, 3, 8):
+            parts = [sharding.shard_indices(order, r, w) for r in range(w)]
+            assert sorted(np.concatenate(parts).tolist()) == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+            assert all(np.array_equal(p, order[r::w]) for r, p in enumerate(parts))
+
+
 def test_shard_bounds_cover():
     for n in (0, 1, 7, 8, 1000003):
         for w in (1, 2, 3, 8):
@@ -139,15 +150,17 @@ dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int
 rank, world = dist.get_rank(), dist.get_world_size()
 bvh = api.build_bvh(meshes.torus_knot(64, 8)[0])
 poses = workloads.approach_batch(41, 5, radius=workloads.KNOT_RADIUS)
-lo, hi = sharding.shard_bounds(len(poses), rank, world)
+# the split bench.py makes: every world-th entry of the cost-sorted claim order (host half of the product, no GPU needed)
+order = np.random.default_rng(0).permutation(len(poses))  # (the real order comes from api.schedule_order, which needs device models)
+idx = sharding.shard_indices(order, rank, world)
 # stand-in solver for the CPU test: the oracle port plays the GPU's role (the checker, not the product)
-r = oracle.port().solve_batch(bvh, bvh, poses[lo:hi])
-local = {"toc": r["toc"].copy(), "collisionfree": r["collisionfree"].copy(), "num_ca": r["numCA"].copy()}
-full = sharding.gather_results(local, len(poses), rank, world, dist)
+r = oracle.port().solve_batch(bvh, bvh, poses[idx])
+local = {"toc": r["toc"].copy(), "collisionfree": r["collisionfree"].copy(), "num_ca": r["numCA"].copy(), "pose_toc": r["pose_toc"].copy()}
+full = sharding.gather_results(local, idx, len(poses), rank, world, dist)
 if rank == 0:
     ref = oracle.port().solve_batch(bvh, bvh, poses)
     assert np.array_equal(full["toc"], ref["toc"]) and np.array_equal(full["collisionfree"], ref["collisionfree"])
-    assert np.array_equal(full["num_ca"], ref["numCA"])
+    assert np.array_equal(full["num_ca"], ref["numCA"]) and np.array_equal(full["pose_toc"], ref["pose_toc"])
     print("GATHER_OK")
 else:
     assert full is None
@@ -157,7 +170,8 @@ dist.destroy_process_group()
 
 
 def test_two_rank_gloo_shard_and_gather(tmp_path):
-    """world_size-2 gloo run of the N>1 host logic: contiguous shards, per-rank solve, gather on rank 0."""
+    """world_size-2 gloo run of the N>1 host logic: interleaved shards of the claim order, per-rank solve, gather +
+    scatter to batch order on rank 0."""
     import socket
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     script = tmp_path / "worker.py"
