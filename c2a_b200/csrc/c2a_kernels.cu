@@ -286,6 +286,8 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
     {
       CUDA_TRY(cudaFuncSetAttribute(c2a_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BLOCK_SMEM_BYTES));
       CUDA_TRY(cudaFuncSetAttribute(c2a_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIDE_BLOCK_SMEM));
+      // the wide kernel wants L1, not shared memory: two 30 KB blocks per SM
+      cudaFuncSetAttribute(c2a_wide_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)env_ll("C2A_B200_WIDE_CARVEOUT", 29));
       cudaMemPool_t pool;
       if (cudaDeviceGetDefaultMemPool(&pool, a->device) == cudaSuccess)
       {
@@ -332,12 +334,13 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   const int w_stack_cap = (int)std::max<long long>(env_ll("C2A_B200_WIDE_STACK", 4096), args.stack_entries + 64);
   const int w_rec_cap = (int)env_ll("C2A_B200_WIDE_RECS", 131072);
   auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  const size_t spill_bytes = wide ? up((size_t)n * MB_DOUBLES * sizeof(double)) : 0, wctl_bytes = wide ? 256 : 0;
+  const size_t spill_bytes = wide ? up((size_t)SPILL_BUCKETS * n * MB_DOUBLES * sizeof(double)) : 0, wctl_bytes = wide ? 256 : 0;
   const size_t wstack_bytes = wide ? up((size_t)wwarps * w_stack_cap * ENTRY_DOUBLES * sizeof(double)) : 0;
   const size_t wrec_bytes = wide ? up((size_t)wwarps * w_rec_cap * 4 * sizeof(double)) : 0;
   const size_t wleaf_bytes = wide ? up((size_t)wwarps * WIDE_UL * WIDE_LEAFOUT_DOUBLES * sizeof(double)) : 0;
+  const size_t waux_bytes = wide ? up((size_t)wwarps * WIDE_AUX_DOUBLES * sizeof(double)) : 0;
   double *stacks = nullptr;
-  CUDA_TRY(cudaMallocAsync(&stacks, up(stack_bytes) + spill_bytes + wctl_bytes + wstack_bytes + wrec_bytes + wleaf_bytes, stream));
+  CUDA_TRY(cudaMallocAsync(&stacks, up(stack_bytes) + spill_bytes + wctl_bytes + wstack_bytes + wrec_bytes + wleaf_bytes + waux_bytes, stream));
   struct Freer { void *p; cudaStream_t s; ~Freer() { cudaFreeAsync(p, s); } } freer{stacks, stream};
   args.stacks = stacks;
   args.spill_recs = nullptr; args.spill_count = nullptr; args.spill_cap = 0; args.spill_live = 0;
@@ -373,10 +376,11 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   {
     WideArgs w;
     w.A = args.A; w.B = args.B; w.motions = poses; w.seedA = sa; w.seedB = sb; w.tol_d = tol_d; w.tol_t = tol_t; w.out = *out;
-    w.items = args.spill_recs; w.n_items = args.spill_count; w.counter = args.spill_count + 1;
+    w.items = args.spill_recs; w.n_items = args.spill_count; w.items_cap = n; w.counter = args.spill_count + SPILL_BUCKETS;
     w.stack = reinterpret_cast<double *>(extra + spill_bytes + wctl_bytes);
     w.recs = reinterpret_cast<double *>(extra + spill_bytes + wctl_bytes + wstack_bytes);
     w.leafout = reinterpret_cast<double *>(extra + spill_bytes + wctl_bytes + wstack_bytes + wrec_bytes);
+    w.aux = reinterpret_cast<double *>(extra + spill_bytes + wctl_bytes + wstack_bytes + wrec_bytes + wleaf_bytes);
     w.stack_cap = w_stack_cap; w.rec_cap = w_rec_cap;
     w.window = (int)std::min<long long>(16, std::max<long long>(1, env_ll("C2A_B200_WIDE_WINDOW", 16)));
     w.stats = g_wide_stats_dev; w.trace = args.trace;

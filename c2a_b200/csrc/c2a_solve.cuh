@@ -85,12 +85,13 @@ struct BatchArgs
   // at most spill_live queries, a query past its fifth CA step is written out at its next step boundary (where its
   // state is 64 bytes: no stack) and the slot retires; the wide kernel, launched next on the stream, finishes it with
   // parallelism inside the traversal.
-  double *spill_recs;                 // [spill_cap][MB_DOUBLES]
-  unsigned long long *spill_count;
+  double *spill_recs;                 // [SPILL_BUCKETS][spill_cap][MB_DOUBLES]
+  unsigned long long *spill_count;    // [SPILL_BUCKETS]
   long long spill_cap;
   int spill_live;
   int max_slots;                      // query slots a warp uses (<= Q): small batches spread over all warps
 };
+constexpr int SPILL_BUCKETS = 3, SPILL_CA_HEAVY = 40, SPILL_CA_MID = 16;
 constexpr int MB_DOUBLES = 8;  // q, lamda, lastLamda, mint, UpboundTOC, {numCA, nItrs}, {nbv, ntri}, {lastA, lastB}
 
 // Single-step mode (the device side of C2A_TimeOfContactStep, C2A.cpp:1778-1931): per query the caller
@@ -718,10 +719,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
         if (args.spill_recs && just_continued && numCA > 5 && n_live <= args.spill_live &&
             *(volatile unsigned long long *)args.counter >= (unsigned long long)args.n)
         {
-          const unsigned long long idx = atomicAdd(args.spill_count, 1ull);
+          // three lists, claimed in this order by the wide kernel: the more steps a query has taken, the more it is
+          // likely to have left (longest-expected first)
+          const int bucket = numCA >= SPILL_CA_HEAVY ? 0 : (numCA >= SPILL_CA_MID ? 1 : 2);
+          const unsigned long long idx = atomicAdd(args.spill_count + bucket, 1ull);
           if (idx < (unsigned long long)args.spill_cap)
           {
-            double *r = args.spill_recs + (size_t)idx * MB_DOUBLES;
+            double *r = args.spill_recs + ((size_t)bucket * args.spill_cap + idx) * MB_DOUBLES;
             r[0] = __longlong_as_double(q); r[1] = lamda; r[2] = SD(F_LASTL, slot); r[3] = SD(F_MINT, slot); r[4] = SD(F_UPB, slot);
             r[5] = __hiloint2double(numCA, SI(I_NITRS, slot)); r[6] = __hiloint2double(SI(I_NBV, slot), SI(I_NTRI, slot));
             r[7] = __hiloint2double(SI(I_LASTA, slot), SI(I_LASTB, slot));

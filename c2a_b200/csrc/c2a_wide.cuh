@@ -43,8 +43,13 @@ constexpr int WIDE_PL = 96;                 // waiting leaf pairs (never more th
 constexpr int WIDE_UL = 128;                // evaluated leaves whose event status is open
 constexpr int WIDE_EV = 768;                // events per step
 constexpr int WIDE_CST = 40;                // step constants (doubles)
+constexpr int WIDE_RND = 1024;              // rounds of a step whose {first record, events resolved so far} are kept for the fold
 constexpr int WIDE_KEY_LEVELS = 56;         // path bits in a key (bits 63..8); bit 7 = leaf pair, bits 5..0 = depth
-constexpr size_t WIDE_WARP_SMEM = (size_t)WIDE_CST * 8 + (size_t)WIDE_PL * (8 + 8 + 8 + 4 + 4) + (size_t)WIDE_UL * 32 + (size_t)WIDE_EV * 16;
+// shared memory per warp: step constants, waiting leaves, open leaves -- kept small (7.5 KB) on purpose: the node and
+// stack fetches live in L1, and every KB of shared memory is a KB less of it (with the events and the round table in
+// shared memory as well, 24 KB per warp, a round took 27 k cycles instead of 14.5 k)
+constexpr size_t WIDE_WARP_SMEM = (size_t)WIDE_CST * 8 + (size_t)WIDE_PL * (8 + 8 + 8 + 4 + 4) + (size_t)WIDE_UL * 32;
+constexpr size_t WIDE_AUX_DOUBLES = (size_t)WIDE_EV * 2 + (size_t)WIDE_RND;   // per warp, global: events {key, d}, round table {rec0, nev}
 constexpr size_t WIDE_BLOCK_SMEM = WIDE_WARP_SMEM * WIDE_WPB;
 constexpr int WIDE_LEAFOUT_DOUBLES = 8;     // p(3) q(3) leaf step bound, {ta, tb}
 
@@ -55,12 +60,14 @@ struct WideArgs
   const int *seedA, *seedB;
   double tol_d, tol_t;
   c2a_b200_results out;
-  const double *items;                  // [*n_items][MB_DOUBLES]: CA-loop state of the queries handed over
-  const unsigned long long *n_items;    // device-resident count
+  const double *items;                  // [SPILL_BUCKETS][items_cap][MB_DOUBLES]: CA-loop state of the queries handed over
+  const unsigned long long *n_items;    // [SPILL_BUCKETS] device-resident counts
+  long long items_cap;
   unsigned long long *counter;          // claim counter
   double *stack;                        // [warps][stack_cap][ENTRY_DOUBLES]
   double *recs;                         // [warps][rec_cap][4]
   double *leafout;                      // [warps][WIDE_UL][WIDE_LEAFOUT_DOUBLES]
+  double *aux;                          // [warps][WIDE_AUX_DOUBLES]
   int stack_cap, rec_cap;
   int window;                           // pairs per round (1..16)
   unsigned long long *stats;            // optional [WIDE_NSTATS]
@@ -102,8 +109,11 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
   double *ul_mpar = reinterpret_cast<double *>(ul_key + WIDE_UL);
   double *ul_val = ul_mpar + WIDE_UL;
   double *ul_dtri = ul_val + WIDE_UL;
-  unsigned long long *ev_key = reinterpret_cast<unsigned long long *>(ul_dtri + WIDE_UL);
-  double *ev_d = reinterpret_cast<double *>(ev_key + WIDE_EV);
+  // events and round table: per-warp global memory (written and read by this warp only; L1/L2 resident)
+  double *const aux = args.aux + (size_t)gw * WIDE_AUX_DOUBLES;
+  unsigned long long *ev_key = reinterpret_cast<unsigned long long *>(aux);
+  double *ev_d = aux + WIDE_EV;
+  int2 *rnd_tab = reinterpret_cast<int2 *>(aux + 2 * WIDE_EV);   // {first record of round r, events resolved when it started}
   enum { C_R1 = 0, C_TT1 = 9, C_CV1 = 12, C_AX1 = 15, C_W1 = 18, C_CV2 = 19, C_AX2 = 22, C_W2 = 25, C_RREL = 26, C_TREL = 35, C_X = 38 };
 
   double *const stk = args.stack + (size_t)gw * args.stack_cap * ENTRY_DOUBLES;
@@ -117,8 +127,12 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
     unsigned long long item = 0;
     if (lane == 0) item = atomicAdd(args.counter, 1ull);
     item = shfl_u64(FULL, item, 0);
-    if (item >= *args.n_items) break;
-    const double *r = args.items + (size_t)item * MB_DOUBLES;
+    // the hand-over lists in order: most CA steps taken so far first
+    const unsigned long long c0 = args.n_items[0], c1 = args.n_items[1], c2 = args.n_items[2];
+    if (item >= c0 + c1 + c2) break;
+    const int bucket = item < c0 ? 0 : (item < c0 + c1 ? 1 : 2);
+    const unsigned long long bi = item - (bucket == 0 ? 0 : (bucket == 1 ? c0 : c0 + c1));
+    const double *r = args.items + ((size_t)bucket * args.items_cap + bi) * MB_DOUBLES;
     const long long q = __double_as_longlong(__ldcg(r + 0));
     double lamda = __ldcg(r + 1), lastLamda = __ldcg(r + 2), mint = __ldcg(r + 3), upb = __ldcg(r + 4);
     const double c5 = __ldcg(r + 5), c6 = __ldcg(r + 6), c7 = __ldcg(r + 7);
@@ -201,7 +215,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
       while (true)
       {
         // (re)start the step's traversal
-        int sp = 1, nrec = 0, npl = 0, nev = 0;
+        int sp = 1, nrec = 0, npl = 0, nev = 0, nrnd = 0;
         unsigned ulm0 = 0, ulm1 = 0, ulm2 = 0, ulm3 = 0;  // occupied slots of the open-leaf list
         double Dw = seed_dist;
         bool redo = false;
@@ -510,6 +524,8 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
             {
               const int depth = (int)(key & 0x3full);
               if (__any_sync(FULL, have && depth >= WIDE_KEY_LEVELS)) { redo = true; break; }
+              if (lane == 0 && nrnd < WIDE_RND) rnd_tab[nrnd] = make_int2(nrec, nev);
+              nrnd++;
               if (have)
               {
                 ckey = (key & ~0xffull) | ((unsigned long long)j << (63 - depth)) | (unsigned long long)(depth + 1) | (my_leafpair ? 0x80ull : 0ull);
@@ -562,53 +578,58 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
           // ---------------------------------------------------------------- resolve events
           // everything that precedes F (the top of the stack, the waiting leaf pairs) has been evaluated
           const long long t_res = args.stats ? clock64() : 0;
-          unsigned long long F = ~0ull;
-          if (sp > 0) F = top_known ? top_key : (unsigned long long)__double_as_longlong(__ldcg(stk + (size_t)(sp - 1) * ENTRY_DOUBLES + 14));
-          if (npl > 0)
+          if (ulm0 | ulm1 | ulm2 | ulm3)
           {
-            unsigned long long k = ~0ull;
-            if (lane < npl) k = pl_key[lane];
-            if (lane + 32 < npl) { const unsigned long long k2 = pl_key[lane + 32]; k = k2 < k ? k2 : k; }
-            k = warp_min_u64(k);
-            F = k < F ? k : F;
-          }
-          (void)did_leaf;
-          while (true)
-          {
-            // my open leaves below F: the smallest key
-            unsigned long long mk = ~0ull; int ms = -1;
-#pragma unroll
-            for (int g = 0; g < 4; g++)
+            unsigned long long F = ~0ull;
+            if (sp > 0) F = top_known ? top_key : (unsigned long long)__double_as_longlong(__ldcg(stk + (size_t)(sp - 1) * ENTRY_DOUBLES + 14));
+            if (npl > 0)
             {
-              const unsigned occ = g == 0 ? ulm0 : (g == 1 ? ulm1 : (g == 2 ? ulm2 : ulm3));
-              if ((occ >> lane) & 1u)
+              unsigned long long k = ~0ull;
+              if (lane < npl) k = pl_key[lane];
+              if (lane + 32 < npl) { const unsigned long long k2 = pl_key[lane + 32]; k = k2 < k ? k2 : k; }
+              k = warp_min_u64(k);
+              F = k < F ? k : F;
+            }
+            // my open leaves (slots lane, lane + 32, ...) below F
+            unsigned long long k0 = ~0ull, k1 = ~0ull, k2 = ~0ull, k3 = ~0ull;
+            if ((ulm0 >> lane) & 1u) { const unsigned long long k = ul_key[lane]; if (k < F) k0 = k; }
+            if ((ulm1 >> lane) & 1u) { const unsigned long long k = ul_key[32 + lane]; if (k < F) k1 = k; }
+            if ((ulm2 >> lane) & 1u) { const unsigned long long k = ul_key[64 + lane]; if (k < F) k2 = k; }
+            if ((ulm3 >> lane) & 1u) { const unsigned long long k = ul_key[96 + lane]; if (k < F) k3 = k; }
+            while (true)
+            {
+              // the smallest key among them: two hardware min-reductions (high, then low word)
+              unsigned long long mk = k0; int ms = lane;
+              if (k1 < mk) { mk = k1; ms = 32 + lane; }
+              if (k2 < mk) { mk = k2; ms = 64 + lane; }
+              if (k3 < mk) { mk = k3; ms = 96 + lane; }
+              const unsigned hi = (unsigned)(mk >> 32), lo = (unsigned)mk;
+              const unsigned mhi = __reduce_min_sync(FULL, hi);
+              const unsigned mlo = __reduce_min_sync(FULL, hi == mhi ? lo : 0xffffffffu);
+              if (mhi == 0xffffffffu && mlo == 0xffffffffu) break;   // (no key is all ones: the depth byte is < 64)
+              const unsigned owner = __ballot_sync(FULL, hi == mhi && lo == mlo);
+              const int s = __shfl_sync(FULL, ms, __ffs(owner) - 1);
+              const unsigned long long best = ((unsigned long long)mhi << 32) | mlo;
+              const double mpar = ul_mpar[s], val = ul_val[s], dTri = ul_dtri[s];
+              const double M = mpar > val ? mpar : val;
+              if (M < Dw && dTri <= Dw)
               {
-                const unsigned long long k = ul_key[g * 32 + lane];
-                if (k < F && k < mk) { mk = k; ms = g * 32 + lane; }
+                if (dTri != 0.0 && !(mpar < dTri)) { redo = true; break; }  // ancestor anomaly: redo the step sequentially
+                if (nev >= WIDE_EV) { redo = true; break; }
+                Dw = dTri;
+                if (lane == 0) { ev_key[nev] = best; ev_d[nev] = dTri; }
+                nev++;
+                const double2 *lo2 = reinterpret_cast<const double2 *>(leafout + (size_t)s * WIDE_LEAFOUT_DOUBLES);
+                const double2 l0 = __ldcg(lo2), l1 = __ldcg(lo2 + 1), l2 = __ldcg(lo2 + 2), l3 = __ldcg(lo2 + 3);
+                best_p[0] = l0.x; best_p[1] = l0.y; best_p[2] = l1.x; best_q[0] = l1.y; best_q[1] = l2.x; best_q[2] = l2.y;
+                if (l3.x <= step_mint) step_mint = l3.x;
+                step_lastA = __double2hiint(l3.y); step_lastB = __double2loint(l3.y);
+                have_best = true;
               }
+              const unsigned bit = 1u << (s & 31);
+              if (s < 32) ulm0 &= ~bit; else if (s < 64) ulm1 &= ~bit; else if (s < 96) ulm2 &= ~bit; else ulm3 &= ~bit;
+              if ((s & 31) == lane) { if (s < 32) k0 = ~0ull; else if (s < 64) k1 = ~0ull; else if (s < 96) k2 = ~0ull; else k3 = ~0ull; }
             }
-            const unsigned long long best = warp_min_u64(mk);
-            if (best == ~0ull) break;
-            const unsigned owner = __ballot_sync(FULL, mk == best);
-            const int s = __shfl_sync(FULL, ms, __ffs(owner) - 1);
-            const double mpar = ul_mpar[s], val = ul_val[s], dTri = ul_dtri[s];
-            const double M = mpar > val ? mpar : val;
-            if (M < Dw && dTri <= Dw)
-            {
-              if (dTri != 0.0 && !(mpar < dTri)) { redo = true; break; }  // ancestor anomaly: redo the step sequentially
-              if (nev >= WIDE_EV) { redo = true; break; }
-              Dw = dTri;
-              if (lane == 0) { ev_key[nev] = best; ev_d[nev] = dTri; }
-              nev++;
-              const double2 *lo = reinterpret_cast<const double2 *>(leafout + (size_t)s * WIDE_LEAFOUT_DOUBLES);
-              const double2 l0 = __ldcg(lo), l1 = __ldcg(lo + 1), l2 = __ldcg(lo + 2), l3 = __ldcg(lo + 3);
-              best_p[0] = l0.x; best_p[1] = l0.y; best_p[2] = l1.x; best_q[0] = l1.y; best_q[1] = l2.x; best_q[2] = l2.y;
-              if (l3.x <= step_mint) step_mint = l3.x;
-              step_lastA = __double2hiint(l3.y); step_lastB = __double2loint(l3.y);
-              have_best = true;
-            }
-            const unsigned bit = 1u << (s & 31);
-            if (s < 32) ulm0 &= ~bit; else if (s < 64) ulm1 &= ~bit; else if (s < 96) ulm2 &= ~bit; else ulm3 &= ~bit;
           }
           __syncwarp();
           if (args.stats && lane == 0) atomicAdd(args.stats + WS_CYC_RESOLVE, (unsigned long long)(clock64() - t_res));
@@ -656,21 +677,27 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
         {
           int f_nbv = 0, f_ntri = root_leaf ? 1 : 0;
           double f_mint = step_mint;
+          // records were written round by round; the events resolved before a record's round precede its node, so the
+          // search for "the last event before this position" starts there and is short
+          const int nr = nrnd < WIDE_RND ? nrnd : WIDE_RND;
+          int rc = 0;
+          double2 n0 = make_double2(0, 0), n1 = make_double2(0, 0);
+          if (lane < nrec) { n0 = __ldcg(reinterpret_cast<const double2 *>(recs + (size_t)lane * 4)); n1 = __ldcg(reinterpret_cast<const double2 *>(recs + (size_t)lane * 4) + 1); }
           for (int i = lane; i < nrec; i += 32)
           {
-            const double2 r0 = __ldcg(reinterpret_cast<const double2 *>(recs + (size_t)i * 4));
-            const double2 r1 = __ldcg(reinterpret_cast<const double2 *>(recs + (size_t)i * 4) + 1);
+            const double2 r0 = n0, r1 = n1;
+            if (i + 32 < nrec) { n0 = __ldcg(reinterpret_cast<const double2 *>(recs + (size_t)(i + 32) * 4)); n1 = __ldcg(reinterpret_cast<const double2 *>(recs + (size_t)(i + 32) * 4) + 1); }
+            while (rc + 1 < nr && rnd_tab[rc + 1].x <= i) rc++;
             const unsigned long long key = (unsigned long long)__double_as_longlong(r0.x);
             const int depth = (int)(key & 0x3full);
             const unsigned long long pkey = ((key & ~0xffull) & ~(1ull << (64 - depth))) | (unsigned long long)(depth - 1);
-            // D in force at the parent's and at the node's own position: the last event before it (binary search)
-            int lo = 0, hi = nev;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (ev_key[mid] < pkey) lo = mid + 1; else hi = mid; }
+            // D in force at the parent's and at the node's own position: the last event before it
+            int lo = rnd_tab[rc].y;
+            while (lo < nev && ev_key[lo] < pkey) lo++;
             const double Dp = lo ? ev_d[lo - 1] : seed_dist;
             if (!(r0.y < Dp)) continue;  // the parent was not visited
             f_nbv++;
-            hi = nev;  // (own position is not before the parent's: continue from lo)
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (ev_key[mid] < key) lo = mid + 1; else hi = mid; }
+            while (lo < nev && ev_key[lo] < key) lo++;   // (own position is not before the parent's)
             const double Dn = lo ? ev_d[lo - 1] : seed_dist;
             if (!(r1.x < Dn)) { if (r1.y < f_mint) f_mint = r1.y; }
             else if (key & 0x80ull) f_ntri++;

@@ -34,11 +34,7 @@ for n in sizes:
         import oracle
         k = min(check, n)
         idx = np.unique(np.concatenate([np.argsort(-out["num_bv_tests"])[:k // 2], np.random.default_rng(1).choice(n, k - k // 2, replace=False)])) if n > k else np.arange(n)
-        if oracle.have_ref():
-            R = oracle.ref(); m = R.model(tris)
-            ref = R.solve_batch(m, m, poses[idx], threads=os.cpu_count())
-        else:
-            ref = oracle.port().solve_batch(bvh, bvh, poses[idx], threads=os.cpu_count())
+        ref = oracle.port().solve_batch(bvh, bvh, poses[idx], threads=os.cpu_count())  # (the port also reports p1/p2 and last_tri)
         bad = {}
         for name, rn in (("collisionfree", "collisionfree"), ("num_ca", "numCA"), ("num_bv_tests", "num_bv_tests"), ("num_tri_tests", "num_tri_tests"),
                          ("toc", "toc"), ("distance", "distance"), ("mint", "mint")):
@@ -51,5 +47,5 @@ for n in sizes:
         if not np.array_equal(out["last_tri"][idx], lt): bad["last_tri"] = int((out["last_tri"][idx] != lt).any(axis=1).sum())
         hit = ref["collisionfree"] == 0
         if not np.array_equal(out["pose_toc"][idx][hit], ref["pose_toc"][hit]): bad["pose_toc"] = 1
-        print(f"  check vs {'reference' if oracle.have_ref() else 'port'} on {len(idx)} queries (heaviest {k // 2} + random): {'BIT-EXACT' if not bad else 'MISMATCH ' + str(bad)}")
+        print(f"  check vs port on {len(idx)} queries (heaviest {k // 2} + random): {'BIT-EXACT' if not bad else 'MISMATCH ' + str(bad)}")
 L.c2a_b200_phase_stats(0, None); L.c2a_b200_wide_stats(0, None)

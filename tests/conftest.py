@@ -25,7 +25,28 @@ def _native_built():
 
 
 def load_golden(name):
-    return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    """A committed fixture as a dict.  The large ones are stored compact (tests/golden/make_golden.py save_compact):
+    the reference's outputs plus a recipe for the poses, rebuilt here and checked against the stored sha256."""
+    d = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    if "gen" in d:
+        import hashlib
+        from c2a_b200 import workloads
+        gen = json.loads(str(d["gen"]))
+        if gen["fn"] == "approach_batch":
+            poses = workloads.approach_batch(gen["n"], gen["seed"])
+        elif gen["fn"] == "grazing_of":
+            src = load_golden(gen["src"])
+            g = np.load(os.path.join(GOLDEN, gen["poses"] + ".npz"))
+            poses = src["poses"][g["src"]].copy()
+            poses[:, 12:24] = g["end1"]
+        else:
+            raise ValueError(gen["fn"])
+        poses = np.ascontiguousarray(poses)
+        assert hashlib.sha256(poses.tobytes()).hexdigest() == str(d["pose_sha256"]), f"{name}: the pose generator no longer reproduces the fixture's inputs"
+        d["poses"] = poses
+        for k in ("collisionfree", "numCA"):
+            d[k] = d[k].astype(np.int32)
+    return d
 
 
 @pytest.fixture(scope="session")
@@ -89,4 +110,11 @@ GOLDEN_CASES = [  # (fixture, model A, model B)
     ("ref_bunny_grazing_tol1e-06", "bunny", "bunny"),
     ("ref_knot_128x16_carry", "knot_128x16", "knot_128x16"),              # "demo mode": seeds carried through
     ("ref_demo_bunny_carry", "bunny", "bunny"),                           # o->last_tri (quirk Q4), 303 frames twice
+    ("ref_knot_512x32_heavy", "knot_512x32", "knot_512x32"),              # the 1M bench batch's heaviest: all 81 queries at the
+                                                                          # reference's 150-iteration cap + the 200 with most BV tests
+    ("ref_bunny_approach_10k", "bunny", "bunny"),                         # config 2 at its full 10 000 (compact fixture)
+    ("ref_bunny_grazing_2k_tol0.001", "bunny", "bunny"),                  # config 5 at its full 2 000 x four tolerances
+    ("ref_bunny_grazing_2k_tol0.0001", "bunny", "bunny"),
+    ("ref_bunny_grazing_2k_tol1e-05", "bunny", "bunny"),
+    ("ref_bunny_grazing_2k_tol1e-06", "bunny", "bunny"),
 ]

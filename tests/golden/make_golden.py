@@ -123,9 +123,57 @@ def distance_fixture(R):
     np.savez_compressed(os.path.join(HERE, "ref_distance_knot_128x16.npz"), **out)
 
 
+def save_compact(name, res, gen, poses, tol_d, tol_t, extra=None):
+    """Large fixtures keep the reference's outputs and a recipe for the poses (generator + seed, or a source fixture
+    plus the doubles that differ) instead of the poses themselves; tests/conftest.py rebuilds them and checks the
+    sha256.  pose_toc is dropped (a pure function of toc, covered by the small fixtures)."""
+    d = {"collisionfree": res["collisionfree"].astype(np.int8), "numCA": res["numCA"].astype(np.int16),
+         "num_bv_tests": res["num_bv_tests"], "num_tri_tests": res["num_tri_tests"], "toc": res["toc"],
+         "distance": res["distance"], "mint": res["mint"], "p1p2": np.concatenate([res["p1"], res["p2"]], 1),
+         "gen": np.array(json.dumps(gen)), "pose_sha256": np.array(hashlib.sha256(np.ascontiguousarray(poses).tobytes()).hexdigest()),
+         "tol_d": np.float64(tol_d), "tol_t": np.float64(tol_t)}
+    if extra:
+        d.update(extra)
+    np.savez_compressed(os.path.join(HERE, name), **d)
+    print(f"{name}: n={len(res)} hits={int((res['collisionfree'] == 0).sum())} mean numCA={res['numCA'].mean():.2f} max numCA={res['numCA'].max()} "
+          f"mean nbv={res['num_bv_tests'].mean():.0f} max nbv={res['num_bv_tests'].max()}")
+
+
+def big_fixtures(R, bunny):
+    """SURVEY section 8d at full size: config 2 (10 000 bunny approach queries), config 5 (2 000 grazing re-poses of
+    its colliding queries x tolerance_t 1e-3..1e-6), and the heaviest queries of the 1M-query bench batch (config 3):
+    every query that runs into the reference's 150-iteration cap (C2A.cpp:2079) plus the 200 with the most BV tests.
+    The heavy indices were picked from a GPU run's per-query counters (tests/golden/heavy_indices.npy); what is pinned
+    here is the reference's own output for those poses."""
+    n = 10000
+    poses = workloads.approach_batch(n, 20260001)
+    res = R.solve_batch(bunny, bunny, poses, threads=THREADS)
+    save_compact("ref_bunny_approach_10k.npz", res, {"fn": "approach_batch", "n": n, "seed": 20260001, "radius": "bunny"}, poses, 1e-4, 1e-4)
+    hit = np.where((res["collisionfree"] == 0) & (res["num_tri_tests"] > 0))[0][:2000]
+    rng = np.random.default_rng(57)
+    p1p2 = np.concatenate([res["p1"], res["p2"]], 1)
+    gp = workloads.grazing_batch(poses[hit], res["toc"][hit], res["pose_toc"][hit], p1p2[hit], rng.uniform(0, 1e-3, len(hit)))
+    np.savez_compressed(os.path.join(HERE, "bunny_grazing_2k_poses.npz"), src=hit.astype(np.int32), end1=gp[:, 12:24].copy())
+    for tol_t in (1e-3, 1e-4, 1e-5, 1e-6):
+        r = R.solve_batch(bunny, bunny, gp, tol_d=1e-4, tol_t=tol_t, threads=THREADS)
+        save_compact(f"ref_bunny_grazing_2k_tol{tol_t:g}.npz", r, {"fn": "grazing_of", "src": "ref_bunny_approach_10k", "poses": "bunny_grazing_2k_poses"},
+                     gp, 1e-4, tol_t)
+    idx = np.load(os.path.join(HERE, "heavy_indices.npy"))
+    tris, vi = meshes.torus_knot(512, 32)
+    knot = R.model(tris, vi)
+    batch = workloads.approach_batch(1000000, 20260002, radius=workloads.KNOT_RADIUS)
+    hp = np.ascontiguousarray(batch[idx])
+    r = R.solve_batch(knot, knot, hp, threads=THREADS)
+    save_results("ref_knot_512x32_heavy.npz", r, hp, 1e-4, 1e-4, {"batch_index": idx.astype(np.int32)})
+
+
 def main():
     oracle.build_oracle()
     R = oracle.ref()
+    if "--only-big" in sys.argv:
+        m = np.load(os.path.join(HERE, "bunny_mesh.npz"))
+        big_fixtures(R, R.model(m["verts"][m["vidx"]].reshape(-1, 9).copy(), m["vidx"]))
+        return
     if "--only-bunny-grazing" in sys.argv:
         m = np.load(os.path.join(HERE, "bunny_mesh.npz"))
         bunny_grazing_fixture(R, R.model(m["verts"][m["vidx"]].reshape(-1, 9).copy(), m["vidx"]))

@@ -116,14 +116,15 @@ def test_port_vs_reference_fresh_batch(bunny_tris):
 def test_port_matches_golden(case, ma, mb, golden, bvhs):
     """The port reproduces the reference's committed outputs bit for bit (a slice, to stay fast)."""
     g = golden(case)
-    n = min(160, len(g["toc"]))
+    n = min(160 if "heavy" not in case else 24, len(g["toc"]))  # (a heavy query costs the port ~0.15 s)
     sl = slice(0, n)
     out = oracle.port().solve_batch(bvhs(ma), bvhs(mb), g["poses"][sl],
                                     g["seed_a"][sl] if "seed_a" in g else None,
                                     g["seed_b"][sl] if "seed_b" in g else None,
                                     float(g["tol_d"]), float(g["tol_t"]), threads=8)
     for k in ("collisionfree", "numCA", "num_bv_tests", "num_tri_tests", "toc", "distance", "mint", "pose_toc"):
-        assert np.array_equal(out[k], g[k][sl]), (case, k)
+        if k in g:  # (the compact fixtures carry no pose_toc)
+            assert np.array_equal(out[k], g[k][sl]), (case, k)
     upd = (out["p1"] != 0).any(1)  # p1/p2 are only defined once a leaf updated them
     assert np.array_equal(np.concatenate([out["p1"], out["p2"]], 1)[upd], g["p1p2"][sl][upd])
     if "last_tri" in g:  # demo-mode fixtures: the traversal's o->last_tri side effect and the seed chain it feeds
