@@ -35,6 +35,13 @@
 #pragma once
 #include "c2a_solve.cuh"
 
+// The counters of c2a_b200_wide_stats (cycles per phase, rounds, tests) cost ~15 % of the kernel's time and skew what
+// they measure (clock reads and atomics between the passes), so they are compiled out of the product build;
+// scripts/build_variant.py <name> -DC2A_WIDE_STATS=1 makes a library with them.
+#ifndef C2A_WIDE_STATS
+#define C2A_WIDE_STATS 0
+#endif
+
 namespace c2a {
 
 constexpr int WIDE_WPB = 4;                 // warps per block
@@ -120,7 +127,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
   double *const recs = args.recs + (size_t)gw * args.rec_cap * 4;
   double *const leafout = args.leafout + (size_t)gw * WIDE_UL * WIDE_LEAFOUT_DOUBLES;
 
-  if (args.stats && threadIdx.x == 0) atomicMin(args.stats + WS_T_FIRST, global_ns());
+  if ((C2A_WIDE_STATS && args.stats) && threadIdx.x == 0) atomicMin(args.stats + WS_T_FIRST, global_ns());
   while (true)
   {
     // ---- claim a handed-over query
@@ -142,13 +149,13 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
     const double *rec = args.motions + (size_t)(2 * MOTION_DOUBLES) * q;
     const int seedA = seed_or_zero(args.seedA, q, A.n_tris), seedB = seed_or_zero(args.seedB, q, B.n_tris);
     double dist = 0;
-    if (args.stats && lane == 0) atomicAdd(args.stats + WS_QUERIES, 1ull);
+    if ((C2A_WIDE_STATS && args.stats) && lane == 0) atomicAdd(args.stats + WS_QUERIES, 1ull);
 
     while (true)
     {
       // ================================================================ one CA step =========
       // C2A_TimeOfContactStep, C2A.cpp:1791-1894 (lane 0; the constants go to shared memory)
-      const long long t_setup = args.stats ? clock64() : 0;
+      const long long t_setup = (C2A_WIDE_STATS && args.stats) ? clock64() : 0;
       int root_leaf = 0;
       if (lane == 0)
       {
@@ -203,7 +210,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
       if (mint_prev <= 0.005 || seed_dist <= 0.5 || numCA > 5) { abs_err = 0; rel_err = 0; }
       else { abs_err = 1e+30; rel_err = (numCA <= 2) ? 3 : 0.5; }
       const bool exact = abs_err == 0 && rel_err == 0;
-      if (args.stats && lane == 0) { atomicAdd(args.stats + WS_STEPS, 1ull); atomicAdd(args.stats + WS_CYC_SETUP, (unsigned long long)(clock64() - t_setup)); }
+      if ((C2A_WIDE_STATS && args.stats) && lane == 0) { atomicAdd(args.stats + WS_STEPS, 1ull); atomicAdd(args.stats + WS_CYC_SETUP, (unsigned long long)(clock64() - t_setup)); }
 
       // ---- traversal.  seq = false: wide rounds with records, events and fold; seq = true: one pair per round with
       // direct bookkeeping (non-exact steps, and the redo after an anomaly / a full arena)
@@ -232,7 +239,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
 
         while (sp > 0 || npl > 0)
         {
-          const long long t_pass = args.stats ? clock64() : 0;
+          const long long t_pass = (C2A_WIDE_STATS && args.stats) ? clock64() : 0;
           bool did_leaf = false;
           unsigned long long top_key = ~0ull;   // key of the new top of the stack if this round pushed
           bool top_known = false;
@@ -346,7 +353,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
             if (lane + 32 < rest) { pl_key[lane + 32] = k1; pl_mpar[lane + 32] = a1; pl_val[lane + 32] = v1; pl_b1[lane + 32] = x1; pl_b2[lane + 32] = y1; }
             npl = rest;
             __syncwarp();
-            if (args.stats && lane == 0)
+            if ((C2A_WIDE_STATS && args.stats) && lane == 0)
             {
               atomicAdd(args.stats + WS_LEAF_PASSES, 1ull); atomicAdd(args.stats + WS_LEAVES, (unsigned long long)__popc(em));
               atomicAdd(args.stats + WS_CYC_LEAF, (unsigned long long)(clock64() - t_pass));
@@ -567,7 +574,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
               }
               __syncwarp();
             }
-            if (args.stats && lane == 0)
+            if ((C2A_WIDE_STATS && args.stats) && lane == 0)
             {
               atomicAdd(args.stats + WS_ROUNDS, 1ull); atomicAdd(args.stats + WS_TESTS, (unsigned long long)(2 * npairs));
               atomicAdd(args.stats + WS_CYC_EXPAND, (unsigned long long)(clock64() - t_pass));
@@ -577,7 +584,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
 
           // ---------------------------------------------------------------- resolve events
           // everything that precedes F (the top of the stack, the waiting leaf pairs) has been evaluated
-          const long long t_res = args.stats ? clock64() : 0;
+          const long long t_res = (C2A_WIDE_STATS && args.stats) ? clock64() : 0;
           if (ulm0 | ulm1 | ulm2 | ulm3)
           {
             unsigned long long F = ~0ull;
@@ -632,12 +639,12 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
             }
           }
           __syncwarp();
-          if (args.stats && lane == 0) atomicAdd(args.stats + WS_CYC_RESOLVE, (unsigned long long)(clock64() - t_res));
+          if ((C2A_WIDE_STATS && args.stats) && lane == 0) atomicAdd(args.stats + WS_CYC_RESOLVE, (unsigned long long)(clock64() - t_res));
           if (redo) break;
         }
         if (redo)
         {
-          if (args.stats && lane == 0) atomicAdd(args.stats + WS_REDO, 1ull);
+          if ((C2A_WIDE_STATS && args.stats) && lane == 0) atomicAdd(args.stats + WS_REDO, 1ull);
           seq = true;
           __syncwarp();
           // the root entry was consumed: rewrite its M slot is not needed (entry 0 is intact: pops do not erase), but
@@ -668,12 +675,12 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
         if (seq)
         {
           step_dist = Dw;
-          if (args.stats && lane == 0) atomicAdd(args.stats + WS_SEQ_STEPS, 1ull);
+          if ((C2A_WIDE_STATS && args.stats) && lane == 0) atomicAdd(args.stats + WS_SEQ_STEPS, 1ull);
           break;
         }
 
         // ------------------------------------------------------------------ FOLD
-        const long long t_fold = args.stats ? clock64() : 0;
+        const long long t_fold = (C2A_WIDE_STATS && args.stats) ? clock64() : 0;
         {
           int f_nbv = 0, f_ntri = root_leaf ? 1 : 0;
           double f_mint = step_mint;
@@ -713,7 +720,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
           f_ntri -= root_leaf ? 31 : 0;  // (the root leaf was counted by every lane)
           step_nbv = f_nbv; step_ntri = f_ntri; step_mint = f_mint; step_dist = Dw;
         }
-        if (args.stats && lane == 0)
+        if ((C2A_WIDE_STATS && args.stats) && lane == 0)
         {
           atomicAdd(args.stats + WS_EVENTS, (unsigned long long)nev);
           atomicAdd(args.stats + WS_CYC_FOLD, (unsigned long long)(clock64() - t_fold));
@@ -791,7 +798,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
       }
     }
   }
-  if (args.stats && threadIdx.x == 0) atomicMax(args.stats + WS_T_LAST, global_ns());
+  if ((C2A_WIDE_STATS && args.stats) && threadIdx.x == 0) atomicMax(args.stats + WS_T_LAST, global_ns());
 }
 
 }  // namespace c2a
