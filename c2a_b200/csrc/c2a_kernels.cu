@@ -39,6 +39,22 @@ static int fail(int code, const std::string &msg)
     if (e_ != cudaSuccess) return fail(C2A_B200_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
+// Every entry runs on its models' device and puts the caller's current device back when it returns.
+struct DeviceGuard
+{
+  int prev = -1;
+  cudaError_t err;
+  explicit DeviceGuard(int device)
+  {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    err = cudaSetDevice(device);
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(dev)                                                                                           \
+  DeviceGuard device_guard_(dev);                                                                                \
+  if (device_guard_.err != cudaSuccess) return fail(C2A_B200_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(device_guard_.err))
+
 }  // namespace c2a
 
 struct c2a_b200_model
@@ -203,7 +219,7 @@ int c2a_b200_model_upload(const c2a_b200_bvh *bvh, int32_t device, c2a_b200_mode
   for (int i = 0; i < n; i++) memcpy(&rloc[(size_t)i * RLOC_STRIDE], bvh->R_loc + 9 * (size_t)i, 9 * sizeof(double));
   for (int i = 0; i < nt; i++) memcpy(&tris[(size_t)i * TRI_STRIDE], bvh->tris + 9 * (size_t)i, 9 * sizeof(double));
 
-  CUDA_TRY(cudaSetDevice(device));
+  ON_DEVICE(device);
   c2a_b200_model *m = new c2a_b200_model();
   m->device = device; m->n_nodes = n; m->n_tris = nt; m->depth = depth;
   m->root_ang_radius = bvh->ang_radius[0];
@@ -230,7 +246,7 @@ int c2a_b200_model_upload(const c2a_b200_bvh *bvh, int32_t device, c2a_b200_mode
 int c2a_b200_model_free(c2a_b200_model *m)
 {
   if (!m) return C2A_B200_OK;
-  cudaSetDevice(m->device);
+  DeviceGuard device_guard_(m->device);
   cudaFree(m->geom); cudaFree(m->rloc); cudaFree(m->meta); cudaFree(m->tris); cudaFree(m->tri_vidx);
   delete m;
   return C2A_B200_OK;
@@ -313,6 +329,8 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   const long long warps = blocks * WARPS_PER_BLOCK;
   long long max_slots = (n + warps - 1) / warps;
   if (max_slots > Q) max_slots = Q;
+  if (const long long cap = env_ll("C2A_B200_MAX_SLOTS", 0))  // development aid
+    if (cap > 0 && max_slots > cap) max_slots = cap;
   if (max_slots < 1) max_slots = 1;
   args.max_slots = (int)max_slots;
   // traversal stacks: one per query slot, depth(A)+depth(B)+2 entries of 128 B
@@ -468,7 +486,7 @@ int c2a_b200_contacts_batch(const c2a_b200_model *a, const c2a_b200_model *b, co
   if (contacts && max_contacts <= 0) return fail(C2A_B200_ERR_ARG, "contacts requested with max_contacts <= 0");
   if (a->device != b->device) return fail(C2A_B200_ERR_DEVICE, "models live on different devices");
   if (n == 0) return C2A_B200_OK;
-  CUDA_TRY(cudaSetDevice(a->device));
+  ON_DEVICE(a->device);
   const size_t N = (size_t)n, cbytes = contacts ? N * (size_t)max_contacts * sizeof(c2a_b200_contact) : 0;
   char *arena = nullptr;
   const size_t o_thr = N * 192, o_nc = o_thr + ((N * 8 + 255) & ~(size_t)255), o_cnt = o_nc + ((N * 4 + 255) & ~(size_t)255),
@@ -502,7 +520,7 @@ int c2a_b200_distance_batch(const c2a_b200_model *a, const c2a_b200_model *b, co
   if (n == 0) return C2A_B200_OK;
   if (int rc = check_seeds(seed_a, n, a->n_tris, "seed_a")) return rc;
   if (int rc = check_seeds(seed_b, n, b->n_tris, "seed_b")) return rc;
-  CUDA_TRY(cudaSetDevice(a->device));
+  ON_DEVICE(a->device);
   const size_t N = (size_t)n;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
@@ -572,7 +590,7 @@ int c2a_b200_solve_batch_device(const c2a_b200_model *a, const c2a_b200_model *b
   int rc = check_pair(a, b, n, poses_dev, out_dev);
   if (rc) return rc;
   if (n == 0) return C2A_B200_OK;
-  CUDA_TRY(cudaSetDevice(a->device));
+  ON_DEVICE(a->device);
   cudaStream_t stream = (cudaStream_t)cuda_stream;
   unsigned long long *counter = nullptr;
   CUDA_TRY(cudaMallocAsync(&counter, sizeof(unsigned long long), stream));
@@ -642,7 +660,7 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
   if (!gather && ((rc = check_seeds(seed_a, n, a->n_tris, "seed_a")) || (rc = check_seeds(seed_b, n, b->n_tris, "seed_b")))) return rc;
   const bool want_contacts = !step_in && (out->num_contact || out->contacts);
   if (want_contacts && out->contacts && out->max_contacts <= 0) return fail(C2A_B200_ERR_ARG, "contacts requested with max_contacts <= 0");
-  CUDA_TRY(cudaSetDevice(a->device));
+  ON_DEVICE(a->device);
   const double t_begin = now_s();
   cudaStream_t stream;
   CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -795,7 +813,8 @@ int c2a_b200_solve_batch_multi(const c2a_b200_model *const *a, const c2a_b200_mo
   const int D = n_devices;
   const double t0 = now_s();
   // host half of the motion model once, on all cores; the claim order over the whole batch
-  std::vector<double> motions(N * 48);
+  static thread_local std::vector<double> motions;   // grow-only: a fresh 384 MB vector costs 0.1 s of page faults per call
+  if (motions.size() < N * 48) motions.resize(N * 48);
   motions_from_poses_mt(poses, n, motions.data(), 0);
   std::vector<int32_t> order(N);
   if (n >= 4096) schedule_order(motions.data(), n, a[0]->root_ang_radius, b[0]->root_ang_radius, order.data());
@@ -889,7 +908,7 @@ int c2a_b200_solve_pairs(const c2a_b200_model *const *models, int32_t n_models, 
       int rc = check_pair(models[g / n_models], models[g % n_models], n, poses, out);
       if (rc) return rc;
     }
-  CUDA_TRY(cudaSetDevice(models[0]->device));
+  ON_DEVICE(models[0]->device);
   cudaStream_t stream;
   CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
 
@@ -1033,7 +1052,7 @@ int c2a_b200_broadphase(const double *c0, const double *c1, const double *radius
     return fail(C2A_B200_ERR_ARG, "NULL argument");
   *n_pairs = 0;
   if (n < 2) return C2A_B200_OK;
-  CUDA_TRY(cudaSetDevice(device));
+  ON_DEVICE(device);
   const size_t N = (size_t)n, o_c1 = N * 24, o_r = 2 * N * 24, o_cnt = o_r + N * 8, o_pairs = o_cnt + 8;
   char *arena = nullptr;
   CUDA_TRY(cudaMalloc(&arena, o_pairs + (size_t)max_pairs * 8));
@@ -1258,7 +1277,7 @@ int c2a_b200_kernel_times(double *out3)
 {
   if (!out3) return fail(C2A_B200_ERR_ARG, "NULL argument");
   if (!g_kev.recorded) return fail(C2A_B200_ERR_ARG, "no batch launch on this thread yet");
-  CUDA_TRY(cudaSetDevice(g_kev.device));
+  ON_DEVICE(g_kev.device);
   CUDA_TRY(cudaEventSynchronize(g_kev.e[3]));
   for (int i = 0; i < 3; i++)
   {

@@ -256,21 +256,6 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
               const double M = mpar > val ? mpar : val;
               go = seq ? true : (M < Dw);
             }
-            // slot in the open-leaf list for every evaluated leaf
-            const unsigned em = __ballot_sync(FULL, go);
-            const int nfree = 128 - (__popc(ulm0) + __popc(ulm1) + __popc(ulm2) + __popc(ulm3));
-            if (!seq && __popc(em) > nfree) { redo = true; break; }
-            int slot = 0;
-            if (go && !seq)
-            {
-              int k = __popc(em & ((1u << lane) - 1u));
-              const unsigned f0 = ~ulm0, f1 = ~ulm1, f2 = ~ulm2, f3 = ~ulm3;
-              const int n0 = __popc(f0), n1 = __popc(f1), n2 = __popc(f2);
-              if (k < n0) slot = nth_bit32(f0, k);
-              else if (k < n0 + n1) slot = 32 + nth_bit32(f1, k - n0);
-              else if (k < n0 + n1 + n2) slot = 64 + nth_bit32(f2, k - n0 - n1);
-              else slot = 96 + nth_bit32(f3, k - n0 - n1 - n2);
-            }
             double dTri = 0, leaf_mt = 0, p[3] = {0, 0, 0}, qq[3] = {0, 0, 0};
             int ta = 0, tb = 0;
             if (go)
@@ -306,6 +291,25 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
               if (leaf_mt < 0.0) leaf_mt = 0.0;
             }
             __syncwarp();
+            // Only a leaf with dTri <= Dw can still lower the distance (Dw never grows), whatever the order the events
+            // are resolved in: the others need no slot in the open-leaf list (their triangle test is counted from their
+            // record in the fold)
+            const unsigned em = __ballot_sync(FULL, go);
+            const bool keep = go && !seq && dTri <= Dw;
+            const unsigned km = __ballot_sync(FULL, keep);
+            const int nfree = 128 - (__popc(ulm0) + __popc(ulm1) + __popc(ulm2) + __popc(ulm3));
+            if (!seq && __popc(km) > nfree) { redo = true; break; }
+            int slot = 0;
+            if (keep)
+            {
+              int k = __popc(km & ((1u << lane) - 1u));
+              const unsigned f0 = ~ulm0, f1 = ~ulm1, f2 = ~ulm2, f3 = ~ulm3;
+              const int n0 = __popc(f0), n1 = __popc(f1), n2 = __popc(f2);
+              if (k < n0) slot = nth_bit32(f0, k);
+              else if (k < n0 + n1) slot = 32 + nth_bit32(f1, k - n0);
+              else if (k < n0 + n1 + n2) slot = 64 + nth_bit32(f2, k - n0 - n1);
+              else slot = 96 + nth_bit32(f3, k - n0 - n1 - n2);
+            }
             if (seq)
             {
               // direct bookkeeping: the single leaf (lane 0) is applied at once
@@ -322,7 +326,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
                 for (int i = 0; i < 3; i++) { best_p[i] = __shfl_sync(FULL, p[i], 0); best_q[i] = __shfl_sync(FULL, qq[i], 0); }
               }
             }
-            else if (go)
+            else if (keep)
             {
               ul_key[slot] = key; ul_mpar[slot] = mpar; ul_val[slot] = val; ul_dtri[slot] = dTri;
               double2 *lo = reinterpret_cast<double2 *>(leafout + (size_t)slot * WIDE_LEAFOUT_DOUBLES);
@@ -332,11 +336,11 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
             if (!seq)
             {
               // mark the slots taken (uniform)
-              const unsigned s0 = __ballot_sync(FULL, go && slot < 32), s1 = __ballot_sync(FULL, go && slot >= 32 && slot < 64);
-              const unsigned s2 = __ballot_sync(FULL, go && slot >= 64 && slot < 96), s3 = __ballot_sync(FULL, go && slot >= 96);
+              const unsigned s0 = __ballot_sync(FULL, keep && slot < 32), s1 = __ballot_sync(FULL, keep && slot >= 32 && slot < 64);
+              const unsigned s2 = __ballot_sync(FULL, keep && slot >= 64 && slot < 96), s3 = __ballot_sync(FULL, keep && slot >= 96);
               // (ballots give lanes, not slots: rebuild the slot masks by OR-reduction)
-              unsigned m0 = (go && slot < 32) ? (1u << slot) : 0u, m1 = (go && slot >= 32 && slot < 64) ? (1u << (slot - 32)) : 0u;
-              unsigned m2 = (go && slot >= 64 && slot < 96) ? (1u << (slot - 64)) : 0u, m3 = (go && slot >= 96) ? (1u << (slot - 96)) : 0u;
+              unsigned m0 = (keep && slot < 32) ? (1u << slot) : 0u, m1 = (keep && slot >= 32 && slot < 64) ? (1u << (slot - 32)) : 0u;
+              unsigned m2 = (keep && slot >= 64 && slot < 96) ? (1u << (slot - 64)) : 0u, m3 = (keep && slot >= 96) ? (1u << (slot - 96)) : 0u;
               if (s0) m0 = __reduce_or_sync(FULL, m0); else m0 = 0;
               if (s1) m1 = __reduce_or_sync(FULL, m1); else m1 = 0;
               if (s2) m2 = __reduce_or_sync(FULL, m2); else m2 = 0;
@@ -597,12 +601,16 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
               k = warp_min_u64(k);
               F = k < F ? k : F;
             }
-            // my open leaves (slots lane, lane + 32, ...) below F
+            // my open leaves (slots lane, lane + 32, ...): those that can no longer lower the distance under the current Dw
+            // are dropped whatever their position (Dw never grows); of the others, the ones below F are candidates
             unsigned long long k0 = ~0ull, k1 = ~0ull, k2 = ~0ull, k3 = ~0ull;
-            if ((ulm0 >> lane) & 1u) { const unsigned long long k = ul_key[lane]; if (k < F) k0 = k; }
-            if ((ulm1 >> lane) & 1u) { const unsigned long long k = ul_key[32 + lane]; if (k < F) k1 = k; }
-            if ((ulm2 >> lane) & 1u) { const unsigned long long k = ul_key[64 + lane]; if (k < F) k2 = k; }
-            if ((ulm3 >> lane) & 1u) { const unsigned long long k = ul_key[96 + lane]; if (k < F) k3 = k; }
+            bool dead0 = false, dead1 = false, dead2 = false, dead3 = false;
+            if ((ulm0 >> lane) & 1u) { const double m_ = ul_mpar[lane], v_ = ul_val[lane]; dead0 = !((m_ > v_ ? m_ : v_) < Dw && ul_dtri[lane] <= Dw); if (!dead0) { const unsigned long long k = ul_key[lane]; if (k < F) k0 = k; } }
+            if ((ulm1 >> lane) & 1u) { const double m_ = ul_mpar[32 + lane], v_ = ul_val[32 + lane]; dead1 = !((m_ > v_ ? m_ : v_) < Dw && ul_dtri[32 + lane] <= Dw); if (!dead1) { const unsigned long long k = ul_key[32 + lane]; if (k < F) k1 = k; } }
+            if ((ulm2 >> lane) & 1u) { const double m_ = ul_mpar[64 + lane], v_ = ul_val[64 + lane]; dead2 = !((m_ > v_ ? m_ : v_) < Dw && ul_dtri[64 + lane] <= Dw); if (!dead2) { const unsigned long long k = ul_key[64 + lane]; if (k < F) k2 = k; } }
+            if ((ulm3 >> lane) & 1u) { const double m_ = ul_mpar[96 + lane], v_ = ul_val[96 + lane]; dead3 = !((m_ > v_ ? m_ : v_) < Dw && ul_dtri[96 + lane] <= Dw); if (!dead3) { const unsigned long long k = ul_key[96 + lane]; if (k < F) k3 = k; } }
+            ulm0 &= ~__ballot_sync(FULL, dead0); ulm1 &= ~__ballot_sync(FULL, dead1);
+            ulm2 &= ~__ballot_sync(FULL, dead2); ulm3 &= ~__ballot_sync(FULL, dead3);
             while (true)
             {
               // the smallest key among them: two hardware min-reductions (high, then low word)

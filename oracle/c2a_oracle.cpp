@@ -596,7 +596,8 @@ static thread_local std::vector<uint64_t> *g_visits = nullptr;  // non-NULL: toc
 static thread_local orc_spec_stats *g_spec = nullptr;  // non-NULL: exact-mode steps run the speculative split (design study below)
 static thread_local double g_spec_prev = -1;
 static thread_local orc_replay_stats *g_rp = nullptr;  // non-NULL: every CA step is replayed over the previous step's visit list
-static thread_local orc_wide_stats *g_wide = nullptr;  // non-NULL: exact-mode CA steps run as sequential prefix + level-synchronous wide phase
+static thread_local orc_wide_stats *g_wide = nullptr;
+static thread_local double *g_probe = nullptr; static thread_local int g_probe_step = 0;  // design study: CA-loop state when numCA reaches g_probe_step  // non-NULL: exact-mode CA steps run as sequential prefix + level-synchronous wide phase
 namespace {
 struct Step;
 struct RpEntry;
@@ -1591,6 +1592,7 @@ extern "C" void orc_solve(const orc_bvh *A, const orc_bvh *B, const double poses
     if (lamda >= 1.0) { collisionfree = 1; toc = 0; done_free = true; break; }
     lastLamda = lamda;
     numCA++;
+    if (g_probe && numCA == g_probe_step) { g_probe[0] = lamda; g_probe[1] = dist; g_probe[2] = mint; g_probe[3] = st.num_bv_tests; g_probe[4] = st.num_tri_tests; }
     orc_motion_integrate(&m1, lamda, 0);
     orc_motion_integrate(&m2, lamda, 0);
     st.upbound = 1.0 - lamda;
@@ -1956,6 +1958,29 @@ extern "C" void orc_solve_wide(const orc_bvh *A, const orc_bvh *B, const double 
   g_wide = stats;
   orc_solve(A, B, poses, seedA, seedB, tol_d, tol_t, out);
   g_wide = nullptr;
+}
+
+// Design study entry: orc_solve that also reports the CA-loop state at the moment numCA reaches `step` (lamda, distance, mint,
+// BV and triangle tests so far; zeros if the query ends earlier): how well does the state after a few cheap steps predict
+// the cost of the whole query?
+extern "C" void orc_solve_probe(const orc_bvh *A, const orc_bvh *B, const double *poses, int64_t n, double tol_d, double tol_t,
+                                int32_t step, orc_result *out, double *probe5, int32_t n_threads)
+{
+  std::atomic<int64_t> next(0);
+  auto work = [&](int) {
+    while (true)
+    {
+      const int64_t i = next.fetch_add(1);
+      if (i >= n) break;
+      for (int k = 0; k < 5; k++) probe5[5 * i + k] = 0;
+      g_probe = probe5 + 5 * i; g_probe_step = step;
+      orc_solve(A, B, poses + 48 * i, 0, 0, tol_d, tol_t, &out[i]);
+      g_probe = nullptr;
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 0; t < (n_threads < 1 ? 1 : n_threads); t++) th.emplace_back(work, t);
+  for (auto &t : th) t.join();
 }
 
 // Design study entry: orc_solve with every CA step replayed over the previous step's visit list (see replay_step).
