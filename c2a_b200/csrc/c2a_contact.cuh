@@ -26,9 +26,11 @@ struct ContactArgs
   int *num_contact;             // [n]
   c2a_b200_contact *contacts;   // [n][max_contacts] or NULL
   unsigned long long *counter;
+  double *gstack;               // GS = true: [entries][13][threads] traversal stacks in global memory
 };
 
-constexpr int CONTACT_STACK = 96;  // >= depth(A)+depth(B)+2, validated on the host
+constexpr int CONTACT_STACK = 96;  // local-memory stack; deeper hierarchies run the GS = true instance
+constexpr int CONTACT_ENTRY = 13;  // R(9) T(3) ids
 
 C2A_DEV void feature_ids(int out[3], int type, int fid, const int *v)
 {
@@ -39,10 +41,13 @@ C2A_DEV void feature_ids(int out[3], int type, int fid, const int *v)
   else if (type == 2) { out[0] = v[0]; out[1] = v[1]; out[2] = v[2]; }
 }
 
+template <bool GS>
 __global__ void __launch_bounds__(128) c2a_contact_kernel(const ContactArgs args)
 {
   const DevModel &A = args.A, &B = args.B;
-  double stk[CONTACT_STACK * 13];  // R(9) T(3) ids
+  double stk_local[GS ? 1 : CONTACT_STACK * CONTACT_ENTRY];
+  const size_t gstride = (size_t)gridDim.x * blockDim.x, gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+#define STK(e, f) (*(GS ? (args.gstack + ((size_t)(e) * CONTACT_ENTRY + (f)) * gstride + gtid) : (stk_local + (e) * CONTACT_ENTRY + (f))))
   while (true)
   {
     const long long q = (long long)atomicAdd(args.counter, 1ull);
@@ -68,20 +73,20 @@ __global__ void __launch_bounds__(128) c2a_contact_kernel(const ContactArgs args
       mt_v(T, g1, Tt);
       int sp = 0;
       {
-        double *e = stk;
 #pragma unroll
-        for (int i = 0; i < 9; i++) e[i] = R[i];
-        e[9] = T[0]; e[10] = T[1]; e[11] = T[2]; e[12] = __hiloint2double(0, 0);
+        for (int i = 0; i < 9; i++) STK(0, i) = R[i];
+        STK(0, 9) = T[0]; STK(0, 10) = T[1]; STK(0, 11) = T[2]; STK(0, 12) = __hiloint2double(0, 0);
         sp = 1;
       }
       while (sp > 0)
       {
-        const double *e = stk + (sp - 1) * 13;
+        const int ei = sp - 1;
         sp--;
 #pragma unroll
-        for (int i = 0; i < 9; i++) R[i] = e[i];
-        T[0] = e[9]; T[1] = e[10]; T[2] = e[11];
-        const int b1 = __double2hiint(e[12]), b2 = __double2loint(e[12]);
+        for (int i = 0; i < 9; i++) R[i] = STK(ei, i);
+        T[0] = STK(ei, 9); T[1] = STK(ei, 10); T[2] = STK(ei, 11);
+        const double e_ids = STK(ei, 12);
+        const int b1 = __double2hiint(e_ids), b2 = __double2loint(e_ids);
         const NodeMeta ma = A.meta[b1], mb = B.meta[b2];
         const bool l1 = ma.first_child < 0, l2 = mb.first_child < 0;
         if (l1 && l2)
@@ -153,12 +158,11 @@ __global__ void __launch_bounds__(128) c2a_contact_kernel(const ContactArgs args
           const bool push_c = (k == 0) ? !c_first : c_first;  // k = 0: the one visited second
           if (push_c ? vc : va)
           {
-            double *o = stk + sp * 13;
             const double *Rs = push_c ? Rc : Ra, *Ts = push_c ? Tc : Ta;
 #pragma unroll
-            for (int i = 0; i < 9; i++) o[i] = Rs[i];
-            o[9] = Ts[0]; o[10] = Ts[1]; o[11] = Ts[2];
-            o[12] = push_c ? __hiloint2double(c1, c2) : __hiloint2double(a1, a2);
+            for (int i = 0; i < 9; i++) STK(sp, i) = Rs[i];
+            STK(sp, 9) = Ts[0]; STK(sp, 10) = Ts[1]; STK(sp, 11) = Ts[2];
+            STK(sp, 12) = push_c ? __hiloint2double(c1, c2) : __hiloint2double(a1, a2);
             sp++;
           }
         }
@@ -166,6 +170,7 @@ __global__ void __launch_bounds__(128) c2a_contact_kernel(const ContactArgs args
     }
     if (args.num_contact) args.num_contact[q] = count;
   }
+#undef STK
 }
 
 }  // namespace c2a

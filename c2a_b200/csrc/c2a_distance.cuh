@@ -21,16 +21,20 @@ struct DistanceArgs
   double *p1p2;               // [n][6] or NULL: closest points, each in its own model's frame
   int *tri_pair;              // [n][2] or NULL: closest triangle pair, builder order (o->last_tri coming out)
   int *num_bv_tests, *num_tri_tests;  // [n] or NULL
+  double *gstack;             // GS = true: [entries][DIST_ENTRY][threads] traversal stacks in global memory
 };
 
-constexpr int DIST_STACK = 96;  // >= depth(A)+depth(B)+2, validated on the host
+constexpr int DIST_STACK = 96;  // local-memory stack; deeper hierarchies run the GS = true instance
 constexpr int DIST_ENTRY = 14;  // R(9) T(3) ids d
 
+template <bool GS>
 __global__ void __launch_bounds__(128) c2a_distance_kernel(const DistanceArgs args)
 {
   const DevModel &A = args.A, &B = args.B;
-  double stk[DIST_STACK * DIST_ENTRY];
+  double stk_local[GS ? 1 : DIST_STACK * DIST_ENTRY];
   const long long stride = (long long)gridDim.x * blockDim.x;
+  const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+#define STK(e, f) (*(GS ? (args.gstack + ((size_t)(e) * DIST_ENTRY + (f)) * (size_t)stride + gtid) : (stk_local + (e) * DIST_ENTRY + (f))))
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < args.n; q += stride)
   {
     const double *pose = args.poses + 24 * q;
@@ -54,24 +58,24 @@ __global__ void __launch_bounds__(128) c2a_distance_kernel(const DistanceArgs ar
     mt_v(T, g1, Tt);
     int nbv = 0, ntri = 0, sp = 0;
     {
-      double *e = stk;
 #pragma unroll
-      for (int i = 0; i < 9; i++) e[i] = R[i];
-      e[9] = T[0]; e[10] = T[1]; e[11] = T[2]; e[12] = __hiloint2double(0, 0);
-      e[13] = -1.0;  // flag: the root pair is visited unconditionally
+      for (int i = 0; i < 9; i++) STK(0, i) = R[i];
+      STK(0, 9) = T[0]; STK(0, 10) = T[1]; STK(0, 11) = T[2]; STK(0, 12) = __hiloint2double(0, 0);
+      STK(0, 13) = -1.0;  // flag: the root pair is visited unconditionally
       sp = 1;
     }
     while (sp > 0)
     {
-      const double *e = stk + (sp - 1) * DIST_ENTRY;
+      const int ei = sp - 1;
       sp--;
-      const double ed = e[13];
+      const double ed = STK(ei, 13);
       // the descend test, evaluated when the reference would reach this child (:589-613)
       if (ed >= 0.0 && !((ed < (dist - args.abs_err)) || (ed * (1 + args.rel_err) < dist))) continue;
 #pragma unroll
-      for (int i = 0; i < 9; i++) R[i] = e[i];
-      T[0] = e[9]; T[1] = e[10]; T[2] = e[11];
-      const int b1 = __double2hiint(e[12]), b2 = __double2loint(e[12]);
+      for (int i = 0; i < 9; i++) R[i] = STK(ei, i);
+      T[0] = STK(ei, 9); T[1] = STK(ei, 10); T[2] = STK(ei, 11);
+      const double e_ids = STK(ei, 12);
+      const int b1 = __double2hiint(e_ids), b2 = __double2loint(e_ids);
       const NodeMeta ma = A.meta[b1], mb = B.meta[b2];
       const bool l1 = ma.first_child < 0, l2 = mb.first_child < 0;
       if (l1 && l2)
@@ -124,11 +128,10 @@ __global__ void __launch_bounds__(128) c2a_distance_kernel(const DistanceArgs ar
       for (int k = 0; k < 2; k++)
       {
         const int c = (k == 0) ? (c_first ? 0 : 1) : (c_first ? 1 : 0);  // the one visited second is pushed first
-        double *o = stk + sp * DIST_ENTRY;
 #pragma unroll
-        for (int i = 0; i < 9; i++) o[i] = Rch[c][i];
-        o[9] = Tch[c][0]; o[10] = Tch[c][1]; o[11] = Tch[c][2];
-        o[12] = ids[c]; o[13] = dch[c];
+        for (int i = 0; i < 9; i++) STK(sp, i) = Rch[c][i];
+        STK(sp, 9) = Tch[c][0]; STK(sp, 10) = Tch[c][1]; STK(sp, 11) = Tch[c][2];
+        STK(sp, 12) = ids[c]; STK(sp, 13) = dch[c];
         sp++;
       }
     }
@@ -146,6 +149,7 @@ __global__ void __launch_bounds__(128) c2a_distance_kernel(const DistanceArgs ar
     if (args.num_bv_tests) args.num_bv_tests[q] = nbv;
     if (args.num_tri_tests) args.num_tri_tests[q] = ntri;
   }
+#undef STK
 }
 
 }  // namespace c2a

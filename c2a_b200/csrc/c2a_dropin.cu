@@ -71,14 +71,39 @@ C2A_Model::C2A_Model()
 }
 C2A_Model::~C2A_Model()
 {
+  for (size_t i = 0; i < replicas_.size(); i++) c2a_b200_model_free(replicas_[i].second);
   if (gpu) c2a_b200_model_free(gpu);
   if (host_bvh) c2a_b200_bvh_free(host_bvh);
+}
+int C2A_Model::ReplicateTo(int other_device)
+{
+  if (build_state != C2A_BUILD_STATE_PROCESSED || !host_bvh) return PQP_ERR_UNPROCESSED_MODEL;
+  if (OnDevice(other_device)) return PQP_OK;
+  c2a_b200_bvh view;
+  c2a_b200_bvh_view(host_bvh, &view, 0, 0);
+  c2a_b200_model *m = 0;
+  if (c2a_b200_model_upload(&view, other_device, &m))
+  {
+    fprintf(stderr, "c2a_b200: model upload failed: %s\n", c2a_b200_last_error());
+    return PQP_ERR_MODEL_OUT_OF_MEMORY;
+  }
+  replicas_.push_back(std::make_pair(other_device, m));
+  return PQP_OK;
+}
+c2a_b200_model *C2A_Model::OnDevice(int d) const
+{
+  if (d == device) return gpu;
+  for (size_t i = 0; i < replicas_.size(); i++)
+    if (replicas_[i].first == d) return replicas_[i].second;
+  return 0;
 }
 int C2A_Model::BeginModel(int n)
 {
   const bool was_empty = build_state == C2A_BUILD_STATE_EMPTY;
   if (!was_empty)
   {
+    for (size_t i = 0; i < replicas_.size(); i++) c2a_b200_model_free(replicas_[i].second);
+    replicas_.clear();
     if (gpu) { c2a_b200_model_free(gpu); gpu = 0; }
     if (host_bvh) { c2a_b200_bvh_free(host_bvh); host_bvh = 0; }
     storage_.clear();
@@ -430,6 +455,44 @@ PQP_REAL C2A_QueryContact(CInterpMotion *objmotion1, CInterpMotion *objmotion2, 
   return 0;
 }
 
+// C2A/src/C2A.cpp:1969-1985: the contact pass at explicit poses; unlike C2A_QueryContact it clears the list first
+PQP_REAL C2A_QueryContactOnly(C2A_TimeOfContactResult *res, PQP_REAL R1[3][3], PQP_REAL T1[3], C2A_Model *o1, PQP_REAL R2[3][3],
+                              PQP_REAL T2[3], C2A_Model *o2, double threshold)
+{
+  res->cont_l.clear();
+  res->num_contact = 0;
+  res->UpboundTOC = 1;
+  if (!o1 || !o2 || !o1->gpu || !o2->gpu) return PQP_OK;
+  double poses[24];
+  for (int i = 0; i < 3; i++)
+  {
+    for (int j = 0; j < 3; j++) { poses[3 * i + j] = R1[i][j]; poses[12 + 3 * i + j] = R2[i][j]; }
+    poses[9 + i] = T1[i]; poses[21 + i] = T2[i];
+  }
+  int cap = 256;
+  std::vector<c2a_b200_contact> recs(cap);
+  int32_t n = 0;
+  int rc = c2a_b200_contacts_batch(o1->gpu, o2->gpu, poses, &threshold, 1, cap, &n, recs.data());
+  if (rc == 0 && n > cap)
+  {
+    recs.resize(n);
+    rc = c2a_b200_contacts_batch(o1->gpu, o2->gpu, poses, &threshold, 1, n, &n, recs.data());
+  }
+  if (rc != 0) { fprintf(stderr, "c2a_b200: %s\n", c2a_b200_last_error()); return PQP_OK; }
+  for (int i = 0; i < n; i++)
+  {
+    const c2a_b200_contact &c = recs[i];
+    ContactF f;
+    f.FeatureType_A = c.type_a; f.FeatureType_B = c.type_b;
+    for (int k = 0; k < 3; k++) { f.FeatureID_A[k] = c.fid_a[k]; f.FeatureID_B[k] = c.fid_b[k]; f.P_A[k] = c.pa[k]; f.P_B[k] = c.pb[k]; }
+    f.TriangleID_A = c.tri_a; f.TriangleID_B = c.tri_b;
+    f.Distance = c.dist;
+    res->cont_l.push_front(f);
+  }
+  res->num_contact = n;
+  return PQP_OK;
+}
+
 // C2A/src/C2A.cpp:1778-1931 (rotational branch)
 int C2A_TimeOfContactStep(CInterpMotion *objmotion1, CInterpMotion *objmotion2, C2A_TimeOfContactResult *res,
                           PQP_REAL R1[3][3], PQP_REAL T1[3], C2A_Model *o1, PQP_REAL R2[3][3], PQP_REAL T2[3],
@@ -511,10 +574,10 @@ C2A_Result C2A_Solve(Transform *trans00, Transform *trans01, C2A_Model *obj1_tes
   return TOCFound;
 }
 
-int C2A_SolveBatch(int n, const Transform *trans00, const Transform *trans01, C2A_Model *obj1_tested,
-                   const Transform *trans10, const Transform *trans11, C2A_Model *obj2_tested,
-                   const int *seed_tri_a, const int *seed_tri_b, bool *collisionfree, PQP_REAL *time_of_contact,
-                   PQP_REAL *distance, int *number_of_iteration, Transform *trans0, Transform *trans1)
+static int solve_batch_common(const int *devices, int n_devices, int n, const Transform *trans00, const Transform *trans01,
+                              C2A_Model *obj1_tested, const Transform *trans10, const Transform *trans11, C2A_Model *obj2_tested,
+                              const int *seed_tri_a, const int *seed_tri_b, bool *collisionfree, PQP_REAL *time_of_contact,
+                              PQP_REAL *distance, int *number_of_iteration, Transform *trans0, Transform *trans1)
 {
   if (n < 0 || !obj1_tested || !obj2_tested || !obj1_tested->gpu || !obj2_tested->gpu) return C2A_B200_ERR_ARG;
   if (n == 0) return PQP_OK;
@@ -530,8 +593,19 @@ int C2A_SolveBatch(int n, const Transform *trans00, const Transform *trans01, C2
   out.status = status.data(); out.collisionfree = cf.data(); out.num_ca = nca.data();
   out.toc = time_of_contact; out.distance = distance;
   if (!pose_toc.empty()) out.pose_toc = pose_toc.data();
-  const int rc = c2a_b200_solve_batch(obj1_tested->gpu, obj2_tested->gpu, poses.data(), seed_tri_a, seed_tri_b, n, 0.0001,
-                                      0.0001, &out);
+  int rc;
+  if (!devices)
+    rc = c2a_b200_solve_batch(obj1_tested->gpu, obj2_tested->gpu, poses.data(), seed_tri_a, seed_tri_b, n, 0.0001, 0.0001, &out);
+  else
+  {
+    std::vector<const c2a_b200_model *> a(n_devices), b(n_devices);
+    for (int d = 0; d < n_devices; d++)
+    {
+      a[d] = obj1_tested->OnDevice(devices[d]); b[d] = obj2_tested->OnDevice(devices[d]);
+      if (!a[d] || !b[d]) return C2A_B200_ERR_DEVICE;  // no replica there: C2A_Model::ReplicateTo first
+    }
+    rc = c2a_b200_solve_batch_multi(a.data(), b.data(), n_devices, poses.data(), seed_tri_a, seed_tri_b, n, 0.0001, 0.0001, &out);
+  }
   if (rc) return rc;
   for (int i = 0; i < n; i++)
   {
@@ -545,4 +619,23 @@ int C2A_SolveBatch(int n, const Transform *trans00, const Transform *trans01, C2
     }
   }
   return PQP_OK;
+}
+
+int C2A_SolveBatch(int n, const Transform *trans00, const Transform *trans01, C2A_Model *obj1_tested,
+                   const Transform *trans10, const Transform *trans11, C2A_Model *obj2_tested,
+                   const int *seed_tri_a, const int *seed_tri_b, bool *collisionfree, PQP_REAL *time_of_contact,
+                   PQP_REAL *distance, int *number_of_iteration, Transform *trans0, Transform *trans1)
+{
+  return solve_batch_common(0, 0, n, trans00, trans01, obj1_tested, trans10, trans11, obj2_tested, seed_tri_a, seed_tri_b, collisionfree,
+                            time_of_contact, distance, number_of_iteration, trans0, trans1);
+}
+
+int C2A_SolveBatchMulti(const int *devices, int n_devices, int n, const Transform *trans00, const Transform *trans01,
+                        C2A_Model *obj1_tested, const Transform *trans10, const Transform *trans11, C2A_Model *obj2_tested,
+                        const int *seed_tri_a, const int *seed_tri_b, bool *collisionfree, PQP_REAL *time_of_contact,
+                        PQP_REAL *distance, int *number_of_iteration, Transform *trans0, Transform *trans1)
+{
+  if (!devices || n_devices <= 0) return C2A_B200_ERR_ARG;
+  return solve_batch_common(devices, n_devices, n, trans00, trans01, obj1_tested, trans10, trans11, obj2_tested, seed_tri_a, seed_tri_b,
+                            collisionfree, time_of_contact, distance, number_of_iteration, trans0, trans1);
 }

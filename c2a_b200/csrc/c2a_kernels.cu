@@ -48,6 +48,7 @@ struct DeviceGuard
   {
     if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
     err = cudaSetDevice(device);
+    if (err != cudaSuccess) cudaGetLastError();  // (not sticky: do not leave it for the next launch check to trip over)
   }
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
@@ -415,12 +416,19 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
     // query has rotation return at once, so a batch without such queries pays one near-empty launch.
     TransArgs t;
     t.A = args.A; t.B = args.B; t.motions = poses; t.seedA = sa; t.seedB = sb; t.n = n; t.tol_d = tol_d;
-    t.out = *out; t.order = order;
-    t.too_deep = (a->depth + b->depth + 2 > TRANS_STACK) ? 1 : 0;
+    t.out = *out; t.order = order; t.gstack = nullptr;
     long long tb = (long long)sms * 8;
     const long long tneed = (n + 127) / 128;
     if (tb > tneed) tb = tneed;
-    c2a_translation_kernel<<<(unsigned)tb, 128, 0, stream>>>(t);
+    if (args.stack_entries <= TRANS_STACK) c2a_translation_kernel<false><<<(unsigned)tb, 128, 0, stream>>>(t);
+    else
+    {
+      // hierarchies deeper than the local-memory stack: the same kernel with its stacks in global memory, on a small grid
+      if (tb > 16) tb = 16;
+      CUDA_TRY(cudaMallocAsync(&t.gstack, (size_t)tb * 128 * args.stack_entries * TRANS_ENTRY * sizeof(double), stream));
+      c2a_translation_kernel<true><<<(unsigned)tb, 128, 0, stream>>>(t);
+      cudaFreeAsync(t.gstack, stream);
+    }
     g_launches.fetch_add(1);
     le = cudaGetLastError();
     if (le != cudaSuccess) return fail(C2A_B200_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(le));
@@ -434,7 +442,6 @@ static int launch_contacts(const c2a_b200_model *a, const c2a_b200_model *b, con
                            const double *distance, const int *collisionfree, const int *status, int64_t n, int max_contacts,
                            int *num_contact, c2a_b200_contact *contacts, unsigned long long *counter, cudaStream_t stream)
 {
-  if (a->depth + b->depth + 2 > CONTACT_STACK) return fail(C2A_B200_ERR_DEPTH, "BVH depths exceed the contact-pass stack");
   ContactArgs args;
   args.A = DevModel{a->geom, a->rloc, a->meta, a->tris, a->n_nodes, a->n_tris};
   args.B = DevModel{b->geom, b->rloc, b->meta, b->tris, b->n_nodes, b->n_tris};
@@ -449,7 +456,17 @@ static int launch_contacts(const c2a_b200_model *a, const c2a_b200_model *b, con
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
   CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
-  c2a_contact_kernel<<<(unsigned)blocks, 128, 0, stream>>>(args);
+  args.gstack = nullptr;
+  const int entries = a->depth + b->depth + 2;
+  if (entries <= CONTACT_STACK) c2a_contact_kernel<false><<<(unsigned)blocks, 128, 0, stream>>>(args);
+  else
+  {
+    // hierarchies deeper than the local-memory stack: stacks in global memory, small grid
+    if (blocks > 16) blocks = 16;
+    CUDA_TRY(cudaMallocAsync(&args.gstack, (size_t)blocks * 128 * entries * CONTACT_ENTRY * sizeof(double), stream));
+    c2a_contact_kernel<true><<<(unsigned)blocks, 128, 0, stream>>>(args);
+    cudaFreeAsync(args.gstack, stream);
+  }
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return C2A_B200_OK;
@@ -516,7 +533,6 @@ int c2a_b200_distance_batch(const c2a_b200_model *a, const c2a_b200_model *b, co
 {
   if (!a || !b || n < 0 || (n > 0 && (!poses24 || !distance))) return fail(C2A_B200_ERR_ARG, "NULL argument");
   if (a->device != b->device) return fail(C2A_B200_ERR_DEVICE, "models live on different devices");
-  if (a->depth + b->depth + 2 > DIST_STACK) return fail(C2A_B200_ERR_DEPTH, "BVH depths exceed the distance query's stack");
   if (n == 0) return C2A_B200_OK;
   if (int rc = check_seeds(seed_a, n, a->n_tris, "seed_a")) return rc;
   if (int rc = check_seeds(seed_b, n, b->n_tris, "seed_b")) return rc;
@@ -552,10 +568,19 @@ int c2a_b200_distance_batch(const c2a_b200_model *a, const c2a_b200_model *b, co
     long long blocks = (long long)sms * 8;
     const long long need = (n + 127) / 128;
     if (blocks > need) blocks = need;
-    c2a_distance_kernel<<<(unsigned)blocks, 128>>>(args);
+    args.gstack = nullptr;
+    const int entries = a->depth + b->depth + 2;
+    if (entries <= DIST_STACK) c2a_distance_kernel<false><<<(unsigned)blocks, 128>>>(args);
+    else
+    {
+      if (blocks > 16) blocks = 16;
+      STEP(cudaMalloc(&args.gstack, (size_t)blocks * 128 * entries * DIST_ENTRY * sizeof(double)));
+      if (rc == C2A_B200_OK) c2a_distance_kernel<true><<<(unsigned)blocks, 128>>>(args);
+    }
     g_launches.fetch_add(1);
     STEP(cudaGetLastError());
     STEP(cudaDeviceSynchronize());
+    if (args.gstack) cudaFree(args.gstack);
   }
   STEP(cudaMemcpy(distance, arena + o_d, N * 8, cudaMemcpyDeviceToHost));
   if (p1p2) STEP(cudaMemcpy(p1p2, arena + o_pp, N * 48, cudaMemcpyDeviceToHost));

@@ -33,10 +33,10 @@ struct TransArgs
   double tol_d;
   c2a_b200_results out;
   const int *order;  // optional [n]: the batch is the queries order[0..n) (heterogeneous batches), NULL = 0..n-1
-  int too_deep;      // depth(A)+depth(B)+2 > TRANS_STACK: translation-only queries are reported, not solved
+  double *gstack;    // GS = true: [entries][TRANS_ENTRY][threads] traversal stacks in global memory (hierarchies deeper than TRANS_STACK)
 };
 
-constexpr int TRANS_STACK = 96;           // >= depth(A)+depth(B)+2, validated on the host
+constexpr int TRANS_STACK = 96;           // local-memory stack; deeper hierarchies (depth(A)+depth(B)+2 > 96) run the GS = true instance
 constexpr int TRANS_ENTRY = 15;           // R(9) T(3) ids mint_child d_child
 constexpr double SECURITY_RATIO = 0.1;    // GMP_CCD_SECURITY_DISTANCE_RATIO, InterpMotion.cpp:289
 
@@ -142,21 +142,21 @@ C2A_DEV bool ca_on_triangles(const Motion &m1, double delta, const double r1[9],
   return false;
 }
 
+// GS: the per-thread stack lives in global memory, entry-major and thread-interleaved (what local memory does, without its
+// size limit) -- only used for hierarchies deeper than TRANS_STACK
+template <bool GS>
 __global__ void __launch_bounds__(128) c2a_translation_kernel(const TransArgs args)
 {
   const DevModel &A = args.A, &B = args.B;
-  double stk[TRANS_STACK * TRANS_ENTRY];
+  double stk_local[GS ? 1 : TRANS_STACK * TRANS_ENTRY];
   const long long stride = (long long)gridDim.x * blockDim.x;
+  const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+#define STK(e, f) (*(GS ? (args.gstack + ((size_t)(e) * TRANS_ENTRY + (f)) * (size_t)stride + gtid) : (stk_local + (e) * TRANS_ENTRY + (f))))
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < args.n; k += stride)
   {
     const long long q = args.order ? (long long)__ldg(args.order + k) : k;
     const double *rec = args.motions + (size_t)(2 * MOTION_DOUBLES) * q;
     if (!(__ldg(rec + 18) < 1e-8 && __ldg(rec + MOTION_DOUBLES + 18) < 1e-8)) continue;  // C2A.cpp:2391-2395
-    if (args.too_deep)
-    {
-      if (args.out.status) args.out.status[q] = C2A_B200_QUERY_TRANSLATION_ONLY;
-      continue;
-    }
     Motion m1;
     motion_load(m1, rec);
     const double dl = __ldg(rec + 23);
@@ -192,24 +192,24 @@ __global__ void __launch_bounds__(128) c2a_translation_kernel(const TransArgs ar
 
     int nbv = 0, ntri = 0, sp = 0;
     {
-      double *e = stk;
 #pragma unroll
-      for (int i = 0; i < 9; i++) e[i] = R[i];
-      e[9] = T[0]; e[10] = T[1]; e[11] = T[2]; e[12] = __hiloint2double(0, 0);
-      e[13] = -1.0; e[14] = -1.0;  // the root pair is visited unconditionally (res->mint, res->distance are >= 0)
+      for (int i = 0; i < 9; i++) STK(0, i) = R[i];
+      STK(0, 9) = T[0]; STK(0, 10) = T[1]; STK(0, 11) = T[2]; STK(0, 12) = __hiloint2double(0, 0);
+      STK(0, 13) = -1.0; STK(0, 14) = -1.0;  // the root pair is visited unconditionally (res->mint, res->distance are >= 0)
       sp = 1;
     }
     while (sp > 0)
     {
-      const double *e = stk + (sp - 1) * TRANS_ENTRY;
+      const int ei = sp - 1;
       sp--;
-      const double e_mt = e[13], e_d = e[14];
+      const double e_mt = STK(ei, 13), e_d = STK(ei, 14);
       // :1481-1515, evaluated with the state at the moment the reference would reach this child
       if (!(e_mt < res_mint && ((e_d < (res_dist - 0.0)) || (e_d * (1 + 0.0) < res_dist)))) continue;
 #pragma unroll
-      for (int i = 0; i < 9; i++) R[i] = e[i];
-      T[0] = e[9]; T[1] = e[10]; T[2] = e[11];
-      const int b1 = __double2hiint(e[12]), b2 = __double2loint(e[12]);
+      for (int i = 0; i < 9; i++) R[i] = STK(ei, i);
+      T[0] = STK(ei, 9); T[1] = STK(ei, 10); T[2] = STK(ei, 11);
+      const double e_ids = STK(ei, 12);
+      const int b1 = __double2hiint(e_ids), b2 = __double2loint(e_ids);
       const NodeMeta ma = A.meta[b1], mb = B.meta[b2];
       const bool l1 = ma.first_child < 0, l2 = mb.first_child < 0;
       if (l1 && l2)
@@ -260,12 +260,11 @@ __global__ void __launch_bounds__(128) c2a_translation_kernel(const TransArgs ar
       for (int k = 0; k < 2; k++)
       {
         const int c = (k == 0) ? (c_first ? 0 : 1) : (c_first ? 1 : 0);
-        double *o = stk + sp * TRANS_ENTRY;
 #pragma unroll
-        for (int i = 0; i < 9; i++) o[i] = Rch[c][i];
-        o[9] = Tch[c][0]; o[10] = Tch[c][1]; o[11] = Tch[c][2];
-        o[12] = ids[c];
-        o[13] = mt_ac[c]; o[14] = d_ac[c];
+        for (int i = 0; i < 9; i++) STK(sp, i) = Rch[c][i];
+        STK(sp, 9) = Tch[c][0]; STK(sp, 10) = Tch[c][1]; STK(sp, 11) = Tch[c][2];
+        STK(sp, 12) = ids[c];
+        STK(sp, 13) = mt_ac[c]; STK(sp, 14) = d_ac[c];
         sp++;
       }
     }
@@ -311,6 +310,7 @@ __global__ void __launch_bounds__(128) c2a_translation_kernel(const TransArgs ar
       for (int i = 0; i < 3; i++) { o.pose_toc[24 * q + 9 + i] = Ta[i]; o.pose_toc[24 * q + 21 + i] = Tb[i]; }
     }
   }
+#undef STK
 }
 
 }  // namespace c2a

@@ -540,9 +540,11 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
               if (have)
               {
                 ckey = (key & ~0xffull) | ((unsigned long long)j << (63 - depth)) | (unsigned long long)(depth + 1) | (my_leafpair ? 0x80ull : 0ull);
+                // (streaming stores: a record is written once and read once, by the fold; 5 GB of record arenas must not
+                // push the stacks and the models out of L2)
                 double2 *rr = reinterpret_cast<double2 *>(recs + (size_t)(nrec + lane) * 4);
-                rr[0] = make_double2(__longlong_as_double((long long)ckey), Mpar);
-                rr[1] = make_double2(val, mt);
+                __stcs(rr, make_double2(__longlong_as_double((long long)ckey), Mpar));
+                __stcs(rr + 1, make_double2(val, mt));
               }
               nrec += 2 * npairs;
               const bool pass = have && val < Dw;   // (the popped pair's M < Dw already)
@@ -697,11 +699,11 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
           const int nr = nrnd < WIDE_RND ? nrnd : WIDE_RND;
           int rc = 0;
           double2 n0 = make_double2(0, 0), n1 = make_double2(0, 0);
-          if (lane < nrec) { n0 = __ldcg(reinterpret_cast<const double2 *>(recs + (size_t)lane * 4)); n1 = __ldcg(reinterpret_cast<const double2 *>(recs + (size_t)lane * 4) + 1); }
+          if (lane < nrec) { n0 = __ldcs(reinterpret_cast<const double2 *>(recs + (size_t)lane * 4)); n1 = __ldcs(reinterpret_cast<const double2 *>(recs + (size_t)lane * 4) + 1); }
           for (int i = lane; i < nrec; i += 32)
           {
             const double2 r0 = n0, r1 = n1;
-            if (i + 32 < nrec) { n0 = __ldcg(reinterpret_cast<const double2 *>(recs + (size_t)(i + 32) * 4)); n1 = __ldcg(reinterpret_cast<const double2 *>(recs + (size_t)(i + 32) * 4) + 1); }
+            if (i + 32 < nrec) { n0 = __ldcs(reinterpret_cast<const double2 *>(recs + (size_t)(i + 32) * 4)); n1 = __ldcs(reinterpret_cast<const double2 *>(recs + (size_t)(i + 32) * 4) + 1); }
             while (rc + 1 < nr && rnd_tab[rc + 1].x <= i) rc++;
             const unsigned long long key = (unsigned long long)__double_as_longlong(r0.x);
             const int depth = (int)(key & 0x3full);

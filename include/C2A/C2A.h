@@ -23,6 +23,7 @@
 #define C2A_B200_DROPIN_C2A_H
 
 #include <list>
+#include <utility>
 #include <vector>
 
 typedef double PQP_REAL;
@@ -150,7 +151,12 @@ public:
   int device;                   // GPU the model is uploaded to (set before EndModel; default 0)
   c2a_b200_model *gpu;          // device-resident hierarchy
   c2a_b200_host_bvh *host_bvh;  // host copy of the flattened hierarchy
+  // Replica of the built hierarchy on another GPU of the box (for C2A_SolveBatchMulti); idempotent per device.
+  // Returns PQP_OK, PQP_ERR_UNPROCESSED_MODEL before EndModel(), PQP_ERR_MODEL_OUT_OF_MEMORY if the upload fails.
+  int ReplicateTo(int other_device);
+  c2a_b200_model *OnDevice(int d) const;  // the replica on device d (the model itself for d == device), or 0
 private:
+  std::vector<std::pair<int, c2a_b200_model *> > replicas_;
   std::vector<C2A_Tri> storage_;
   C2A_Model(const C2A_Model &);
   C2A_Model &operator=(const C2A_Model &);
@@ -280,6 +286,10 @@ PQP_REAL C2A_QueryTimeOfContact(CInterpMotion *objmotion1, CInterpMotion *objmot
 PQP_REAL C2A_QueryContact(CInterpMotion *objmotion1, CInterpMotion *objmotion2, C2A_TimeOfContactResult *res, C2A_Model *o1,
                           C2A_Model *o2, double threshold);
 
+// C2A/C2A.h:292, C2A/src/C2A.cpp:1969-1985: the contact pass at explicit poses (clears res->cont_l first)
+PQP_REAL C2A_QueryContactOnly(C2A_TimeOfContactResult *res, PQP_REAL R1[3][3], PQP_REAL T1[3], C2A_Model *o1, PQP_REAL R2[3][3],
+                              PQP_REAL T2[3], C2A_Model *o2, double threshold);
+
 int C2A_TimeOfContactStep(CInterpMotion *objmotion1, CInterpMotion *objmotion2, C2A_TimeOfContactResult *res,
                           PQP_REAL R1[3][3], PQP_REAL T1[3], C2A_Model *o1, PQP_REAL R2[3][3], PQP_REAL T2[3],
                           C2A_Model *o2, PQP_REAL tolerance_t, PQP_REAL tolerance_d);
@@ -293,5 +303,13 @@ int C2A_SolveBatch(int n, const Transform *trans00, const Transform *trans01, C2
                    const Transform *trans10, const Transform *trans11, C2A_Model *obj2_tested,
                    const int *seed_tri_a, const int *seed_tri_b, bool *collisionfree, PQP_REAL *time_of_contact,
                    PQP_REAL *distance, int *number_of_iteration, Transform *trans0, Transform *trans1);
+
+// The same batch sharded over several GPUs of the box (c2a_b200_solve_batch_multi): devices[0..n_devices) are distinct
+// CUDA devices on each of which both models have a replica (the device they were built for, or C2A_Model::ReplicateTo).
+// Results are identical to C2A_SolveBatch's.
+int C2A_SolveBatchMulti(const int *devices, int n_devices, int n, const Transform *trans00, const Transform *trans01,
+                        C2A_Model *obj1_tested, const Transform *trans10, const Transform *trans11, C2A_Model *obj2_tested,
+                        const int *seed_tri_a, const int *seed_tri_b, bool *collisionfree, PQP_REAL *time_of_contact,
+                        PQP_REAL *distance, int *number_of_iteration, Transform *trans0, Transform *trans1);
 
 #endif

@@ -24,16 +24,14 @@ extern "C" {
 #define C2A_B200_OK 0
 #define C2A_B200_ERR_ARG (-1)         /* null pointer, bad size, malformed BVH */
 #define C2A_B200_ERR_CUDA (-2)        /* CUDA runtime error (including: no device) */
-#define C2A_B200_ERR_DEPTH (-3)       /* depth(A)+depth(B) exceeds the traversal stack */
+#define C2A_B200_ERR_DEPTH (-3)       /* depth(A)+depth(B)+2 > 512: beyond what the batched CCD kernel allocates per query slot */
 #define C2A_B200_ERR_DEVICE (-4)      /* models live on different devices */
 
 /* per-query status written to c2a_b200_results.status */
 #define C2A_B200_QUERY_OK 0
-#define C2A_B200_QUERY_TRANSLATION_ONLY 1 /* a translation-only query (both angular speeds < 1e-8, the reference's
-                                             branch at C2A/src/C2A.cpp:2391-2395) on hierarchies with
-                                             depth(A)+depth(B)+2 > 96, deeper than that branch's traversal stack:
-                                             reported, outputs not written.  Otherwise such queries are solved
-                                             like any other (status 0; they are the ones with num_ca == 0) */
+#define C2A_B200_QUERY_TRANSLATION_ONLY 1 /* (round 1 only: translation-only queries on hierarchies deeper than that branch's
+                                             local stack.  No longer reported: deep hierarchies run with their stacks in
+                                             global memory, so every query of a batch ends with status 0) */
 
 /* Flattened RSS bounding-volume hierarchy of one C2A_Model after EndModel(): the hot fields of
  * C2A_BV (C2A/C2A_BV.h:33-77 on top of PQP's BV) and the triangles (PQP Tri p1,p2,p3) in the

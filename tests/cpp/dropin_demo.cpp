@@ -89,6 +89,45 @@ int main(int argc, char **argv)
     if (cf[f] != (free_single[f] != 0) || tocs[f] != toc_single[f] || dists[f] != dist_single[f] || its[f] != it_single[f]) batch_bad++;
   printf("BATCH_MISMATCH %d\n", batch_bad);
 
+  // the multi-device entry over the device(s) the models live on must agree as well (a box with more GPUs gets replicas)
+  {
+    int devs[2] = {object1_tested->device, object1_tested->device + 1};
+    int nd = 1;
+    if (object1_tested->ReplicateTo(devs[1]) == PQP_OK && object2_tested->ReplicateTo(devs[1]) == PQP_OK) nd = 2;
+    std::vector<double> tocs2(nframes), dists2(nframes);
+    std::vector<int> its2(nframes);
+    bool *cf2 = new bool[nframes];
+    if (C2A_SolveBatchMulti(devs, nd, nframes, t00.data(), t01.data(), object1_tested, t10.data(), t11.data(), object2_tested, seed_a.data(),
+                            seed_b.data(), cf2, tocs2.data(), dists2.data(), its2.data(), 0, 0) != PQP_OK) return 11;
+    int multi_bad = 0;
+    for (int f = 0; f < nframes; f++)
+      if (cf2[f] != cf[f] || tocs2[f] != tocs[f] || dists2[f] != dists[f] || its2[f] != its[f]) multi_bad++;
+    printf("MULTI_MISMATCH %d devices %d\n", multi_bad, nd);
+    delete[] cf2;
+  }
+
+  // C2A_QueryContactOnly at the first frames' start poses against C2A_QueryContact on motions standing at those poses
+  {
+    int only_bad = 0;
+    for (int f = 0; f < nframes && f < 12; f++)
+    {
+      PQP_REAL R1[3][3], T1[3], R2[3][3], T2[3];
+      t00[f].Rotation().Get_Value(R1); t00[f].Translation().Get_Value(T1);
+      t10[f].Rotation().Get_Value(R2); t10[f].Translation().Get_Value(T2);
+      CInterpMotion_Linear m1(R1, T1, R1, T1), m2(R2, T2, R2, T2);
+      C2A_TimeOfContactResult ra, rb;
+      const double thr = 25.0;
+      C2A_QueryContact(&m1, &m2, &ra, object1_tested, object2_tested, thr);
+      rb.cont_l.push_front(ContactF());  // must be cleared by the call
+      C2A_QueryContactOnly(&rb, R1, T1, object1_tested, R2, T2, object2_tested, thr);
+      if (ra.num_contact != rb.num_contact || ra.cont_l.size() != rb.cont_l.size()) { only_bad++; continue; }
+      std::list<ContactF>::iterator ia = ra.cont_l.begin(), ib = rb.cont_l.begin();
+      for (; ia != ra.cont_l.end(); ++ia, ++ib)
+        if (ia->TriangleID_A != ib->TriangleID_A || ia->TriangleID_B != ib->TriangleID_B || ia->Distance != ib->Distance) { only_bad++; break; }
+    }
+    printf("CONTACTONLY_MISMATCH %d\n", only_bad);
+  }
+
   // Drive the CA loop from the host with C2A_TimeOfContactStep, the way C2A_QueryTimeOfContact does
   // (C2A/src/C2A.cpp:2005-2143), and compare with the one-call result.
   int step_bad = 0;

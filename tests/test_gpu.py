@@ -350,3 +350,56 @@ def test_contact_pass_matches_reference(models, golden):
     for j, i in enumerate(hits[:40]):
         for a, c in zip(lists[i], recs[j][:num[j]][::-1]):
             assert contacts_equal(a, c), i
+
+
+def skinny_mesh(n=50, ratio=64.0):
+    """Triangles whose positions and sizes grow geometrically with a ratio larger than their number: the builder's mean
+    split peels off one triangle per level, so the hierarchy is a chain of depth n - 1."""
+    tris = []
+    for i in range(n):
+        x = ratio ** i * 1e-40
+        s = 0.3 * x
+        tris.append([x, 0, 0, x + s, 0.1 * s, 0, x, s, 0.05 * s])
+    return np.array(tris)
+
+
+def test_deep_hierarchies_run_on_global_memory_stacks():
+    """depth(A) + depth(B) + 2 = 100 > 96: deeper than the local-memory stacks of the translation-only, contact and
+    distance kernels, and than the 56 key levels of the wide kernel.  Round 1 returned a status / ERR_DEPTH there; now
+    the same kernels run with their stacks in global memory (and the wide kernel one pair per round) -- checked
+    bit for bit against the oracle port, which recurses without a depth limit."""
+    tris = skinny_mesh()
+    bvh = api.build_bvh(tris)
+    assert 2 * bvh["depth"] + 2 > 96
+    m = api.Model(bvh, 0)
+    rad = float(np.linalg.norm(bvh["tris"].reshape(-1, 3), axis=1).max())
+    P = oracle.port()
+    # rotational queries (main kernel; the ones past their fifth CA step finish in the wide kernel)
+    poses = workloads.approach_batch(300, 7, radius=rad)
+    ref = P.solve_batch(bvh, bvh, poses, threads=8)
+    got = api.solve_batch(m, m, poses)
+    assert (got["status"] == 0).all()
+    for a, b in FIELDS:
+        assert np.array_equal(got[a], ref[b]), a
+    assert (ref["numCA"] > 6).sum() >= 3
+    # translation-only queries
+    tp = workloads.translation_batch(120, 8, radius=rad, move_b=True)
+    ref = P.solve_batch(bvh, bvh, tp, threads=1)
+    got = api.solve_batch(m, m, tp)
+    assert (got["status"] == 0).all() and (ref["numCA"] == 0).all()
+    for a, b in FIELDS:
+        assert np.array_equal(got[a], ref[b]), a
+    assert np.array_equal(got["last_tri"], np.stack([ref["last_tri_a"], ref["last_tri_b"]], 1))
+    # discrete distance and the contact pass
+    sp = workloads.static_pose_batch(100, 9, radius=rad)
+    rd = P.distance(bvh, bvh, sp)
+    gd = api.distance_batch(m, m, sp)
+    assert np.array_equal(gd["distance"], rd["distance"]) and np.array_equal(gd["num_bv_tests"], rd["num_bv_tests"])
+    assert np.array_equal(gd["tri_pair"], np.stack([rd["tri_a"], rd["tri_b"]], 1))
+    thr = np.full(len(sp), 0.05 * rad)
+    num, recs = api.contacts_batch(m, m, sp, thr, max_contacts=64)
+    for i in range(len(sp)):
+        n_ref, r_ref = P.contacts(bvh, bvh, sp[i, :12], sp[i, 12:], thr[i], max_out=64)
+        assert num[i] == n_ref, i
+        k = min(n_ref, 64)
+        assert np.array_equal(recs[i][:k]["tri_a"], r_ref["tri_a"][:k]) and np.array_equal(recs[i][:k]["dist"], r_ref["dist"][:k]), i

@@ -63,6 +63,8 @@ def test_cpp_dropin_matches_reference_fixture(tmp_path, golden):
         if not g["collisionfree"][i]:
             assert [float.fromhex(x) for x in r[12:21]] == list(g["pose_toc"][i][:9])
     assert "BATCH_MISMATCH 0" in out.stdout
+    assert "MULTI_MISMATCH 0" in out.stdout       # C2A_SolveBatchMulti (one device here, two on a multi-GPU box)
+    assert "CONTACTONLY_MISMATCH 0" in out.stdout  # C2A_QueryContactOnly == C2A_QueryContact at the same poses
     assert "STEP_MISMATCH 0" in out.stdout
     trows = [l.split() for l in out.stdout.splitlines() if l.startswith("T ")]
     assert len(trows) == nt
