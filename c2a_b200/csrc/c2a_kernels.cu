@@ -667,6 +667,43 @@ struct PinnedLease
 };
 }  // namespace
 
+// Per host thread and device: a stream, and for small calls a grow-only device arena plus pinned staging memory, kept
+// between calls -- a single C2A_Solve must not pay for a stream, two pool allocations and a dozen small copies.
+namespace {
+struct HostCtx
+{
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  char *dev = nullptr; size_t dev_cap = 0;
+  char *pin = nullptr; size_t pin_cap = 0;
+};
+struct HostCtxSet
+{
+  std::vector<HostCtx> v;
+  ~HostCtxSet()
+  {
+    for (auto &c : v)
+    {
+      DeviceGuard g(c.device);
+      if (g.err != cudaSuccess) continue;
+      if (c.stream) cudaStreamDestroy(c.stream);
+      if (c.dev) cudaFree(c.dev);
+      if (c.pin) cudaFreeHost(c.pin);
+    }
+  }
+};
+thread_local HostCtxSet g_ctx;
+HostCtx *host_ctx(int device)  // the caller has made `device` current
+{
+  for (auto &c : g_ctx.v) if (c.device == device) return &c;
+  HostCtx c; c.device = device;
+  if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  g_ctx.v.push_back(c);
+  return &g_ctx.v.back();
+}
+constexpr size_t SMALL_CALL_BYTES = 8u << 20;  // calls whose device arena is smaller take the persistent-arena path
+}  // namespace
+
 // wall-clock breakdown of the last host-buffer call on this thread (development aid, c2a_b200_testing.h)
 static thread_local double g_host_timing[8];
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -687,8 +724,9 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
   if (want_contacts && out->contacts && out->max_contacts <= 0) return fail(C2A_B200_ERR_ARG, "contacts requested with max_contacts <= 0");
   ON_DEVICE(a->device);
   const double t_begin = now_s();
-  cudaStream_t stream;
-  CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  HostCtx *ctx = host_ctx(a->device);
+  if (!ctx) return fail(C2A_B200_ERR_CUDA, "cudaStreamCreate failed");
+  cudaStream_t stream = ctx->stream;
 
   // one device arena: poses | seeds | outputs | counter
   const size_t N = (size_t)n;
@@ -711,12 +749,28 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
   const size_t o_order = use_order ? take(N * 4) : 0;
   const size_t o_cnt = take(8);
   char *arena = nullptr;
-  cudaError_t e = cudaMallocAsync(&arena, off, stream);
-  if (e != cudaSuccess)
+  cudaError_t e = cudaSuccess;
+  const size_t in_end = (o_sb ? o_sb : (o_sa ? o_sa : o_pose)) + (((o_sb || o_sa) ? N * 4 : N * 48 * 8) + 255 & ~(size_t)255);  // poses | seeds
+  const bool small = off <= SMALL_CALL_BYTES && !want_contacts && !step_in && !use_order;
+  if (small)
   {
-    cudaStreamDestroy(stream);
-    return fail(C2A_B200_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+    // persistent arena and pinned staging (inputs | outputs, same layout as the device arena)
+    if (ctx->dev_cap < off)
+    {
+      if (ctx->dev) cudaFree(ctx->dev);
+      ctx->dev = nullptr; ctx->dev_cap = 0;
+      if ((e = cudaMalloc(&ctx->dev, SMALL_CALL_BYTES)) == cudaSuccess) ctx->dev_cap = SMALL_CALL_BYTES;
+    }
+    if (e == cudaSuccess && ctx->pin_cap < off)
+    {
+      if (ctx->pin) cudaFreeHost(ctx->pin);
+      ctx->pin = nullptr; ctx->pin_cap = 0;
+      if ((e = cudaMallocHost(&ctx->pin, SMALL_CALL_BYTES)) == cudaSuccess) ctx->pin_cap = SMALL_CALL_BYTES;
+    }
+    arena = ctx->dev;
   }
+  else e = cudaMallocAsync(&arena, off, stream);
+  if (e != cudaSuccess) return fail(C2A_B200_ERR_CUDA, std::string("device arena: ") + cudaGetErrorString(e));
   c2a_b200_results d;
   memset(&d, 0, sizeof(d));
   if (out->status || want_contacts) d.status = (int32_t *)(arena + o_status);
@@ -737,8 +791,8 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
   STEP(cudaMemsetAsync(arena + o_pose + ((N * 48 * 8 + 255) & ~(size_t)255), 0, off - (o_pose + ((N * 48 * 8 + 255) & ~(size_t)255)), stream));  // outputs start zeroed
   // motion constants on the host (libm acos), straight into pinned staging memory
   PinnedLease pin;
-  STEP(pin.acquire(N * 48 * 8, a->device));
-  double *staging = (double *)pin.ptr;
+  if (!small) STEP(pin.acquire(N * 48 * 8, a->device));
+  double *staging = small ? (double *)(ctx->pin + o_pose) : (double *)pin.ptr;
   const double t_alloc = now_s();
   if (rc == C2A_B200_OK)
   {
@@ -764,9 +818,23 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
     for (size_t i = 0; i < N; i++) { seeds_g[i] = seed_a ? seed_a[gather[i]] : 0; seeds_g[N + i] = seed_b ? seed_b[gather[i]] : 0; }
     seed_a = seed_a ? seeds_g.data() : nullptr; seed_b = seed_b ? seeds_g.data() + N : nullptr;
   }
-  if (seed_a) STEP(cudaMemcpyAsync(arena + o_sa, seed_a, N * 4, cudaMemcpyHostToDevice, stream));
-  if (seed_b) STEP(cudaMemcpyAsync(arena + o_sb, seed_b, N * 4, cudaMemcpyHostToDevice, stream));
-  if (out->pose_toc) STEP(cudaMemsetAsync(arena + o_pt, 0, N * 192, stream));
+  if (small)
+  {
+    // (the motions went up with the copy above only up to their own end: send the seeds, staged next to them, in one more)
+    if (seed_a) memcpy(ctx->pin + o_sa, seed_a, N * 4);
+    if (seed_b) memcpy(ctx->pin + o_sb, seed_b, N * 4);
+    if (seed_a || seed_b)
+    {
+      const size_t lo = seed_a ? o_sa : o_sb;
+      STEP(cudaMemcpyAsync(arena + lo, ctx->pin + lo, in_end - lo, cudaMemcpyHostToDevice, stream));
+    }
+  }
+  else
+  {
+    if (seed_a) STEP(cudaMemcpyAsync(arena + o_sa, seed_a, N * 4, cudaMemcpyHostToDevice, stream));
+    if (seed_b) STEP(cudaMemcpyAsync(arena + o_sb, seed_b, N * 4, cudaMemcpyHostToDevice, stream));
+  }
+  if (out->pose_toc && !small) STEP(cudaMemsetAsync(arena + o_pt, 0, N * 192, stream));
   if (rc == C2A_B200_OK)
     rc = launch_batch(a, b, (const double *)(arena + o_pose), seed_a ? (const int32_t *)(arena + o_sa) : nullptr,
                       seed_b ? (const int32_t *)(arena + o_sb) : nullptr, n, tol_d, tol_t, &d,
@@ -782,8 +850,18 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
   if (want_contacts && out->num_contact) STEP(cudaMemcpyAsync(out->num_contact, arena + o_nc, N * 4, cudaMemcpyDeviceToHost, stream));
   if (want_contacts && out->contacts)
     STEP(cudaMemcpyAsync(out->contacts, arena + o_ct, N * (size_t)out->max_contacts * sizeof(c2a_b200_contact), cudaMemcpyDeviceToHost, stream));
-#define BACK(field, ofs, bytes) \
-  if (out->field) STEP(cudaMemcpyAsync(out->field, arena + ofs, bytes, cudaMemcpyDeviceToHost, stream));
+#define BACK(field, ofs, bytes)                                                                                          \
+  if (out->field)                                                                                                       \
+  {                                                                                                                     \
+    if (small) { if (rc == C2A_B200_OK) memcpy(out->field, ctx->pin + ofs, bytes); }                                    \
+    else STEP(cudaMemcpyAsync(out->field, arena + ofs, bytes, cudaMemcpyDeviceToHost, stream));                         \
+  }
+  if (small)
+  {
+    // the whole output region in one copy (issued before the wait below would be better still; the kernels dominate)
+    STEP(cudaMemcpyAsync(ctx->pin + in_end, arena + in_end, off - in_end, cudaMemcpyDeviceToHost, stream));
+    STEP(cudaStreamSynchronize(stream));
+  }
   BACK(status, o_status, N * 4) BACK(collisionfree, o_cf, N * 4) BACK(num_ca, o_nca, N * 4)
   BACK(num_bv_tests, o_nbv, N * 4) BACK(num_tri_tests, o_ntri, N * 4) BACK(toc, o_toc, N * 8)
   BACK(distance, o_dist, N * 8) BACK(mint, o_mint, N * 8) BACK(p1p2, o_pp, N * 48) BACK(pose_toc, o_pt, N * 192)
@@ -792,9 +870,11 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
   STEP(cudaStreamSynchronize(stream));
 #undef STEP
   const double t_back = now_s();
-  cudaFreeAsync(arena, stream);
-  cudaStreamSynchronize(stream);
-  cudaStreamDestroy(stream);
+  if (!small)
+  {
+    cudaFreeAsync(arena, stream);
+    cudaStreamSynchronize(stream);
+  }
   const double t_end = now_s();
   g_host_timing[0] = t_alloc - t_begin; g_host_timing[1] = t_motions - t_alloc; g_host_timing[2] = t_order - t_motions;
   g_host_timing[3] = t_launched - t_order; g_host_timing[4] = t_kernel - t_launched; g_host_timing[5] = t_back - t_kernel;
