@@ -303,8 +303,8 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
     {
       CUDA_TRY(cudaFuncSetAttribute(c2a_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BLOCK_SMEM_BYTES));
       CUDA_TRY(cudaFuncSetAttribute(c2a_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIDE_BLOCK_SMEM));
-      // the wide kernel wants L1, not shared memory: two 30 KB blocks per SM
-      cudaFuncSetAttribute(c2a_wide_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)env_ll("C2A_B200_WIDE_CARVEOUT", 29));
+      if (env_ll("C2A_B200_WIDE_CARVEOUT", -1) >= 0)  // development aid (no measurable effect: profiles/experiments/README.md)
+        cudaFuncSetAttribute(c2a_wide_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)env_ll("C2A_B200_WIDE_CARVEOUT", -1));
       cudaMemPool_t pool;
       if (cudaDeviceGetDefaultMemPool(&pool, a->device) == cudaSuccess)
       {
