@@ -920,9 +920,10 @@ int c2a_b200_solve_batch_multi(const c2a_b200_model *const *a, const c2a_b200_mo
   // host half of the motion model once, on all cores; the claim order over the whole batch
   static thread_local std::vector<double> motions;   // grow-only: a fresh 384 MB vector costs 0.1 s of page faults per call
   if (motions.size() < N * 48) motions.resize(N * 48);
-  motions_from_poses_mt(poses, n, motions.data(), 0);
+  double *const motions_ptr = motions.data();  // (the workers below are other threads: they must not name the thread_local)
+  motions_from_poses_mt(poses, n, motions_ptr, 0);
   std::vector<int32_t> order(N);
-  if (n >= 4096) schedule_order(motions.data(), n, a[0]->root_ang_radius, b[0]->root_ang_radius, order.data());
+  if (n >= 4096) schedule_order(motions_ptr, n, a[0]->root_ang_radius, b[0]->root_ang_radius, order.data());
   else for (size_t i = 0; i < N; i++) order[i] = (int32_t)i;
   const double t1 = now_s();
   std::vector<int> rcs(D, 0);
@@ -949,7 +950,7 @@ int c2a_b200_solve_batch_multi(const c2a_b200_model *const *a, const c2a_b200_mo
     if (out->p1p2) { pp.resize(nd * 6); o.p1p2 = pp.data(); }
     if (out->pose_toc) { pt.resize(nd * 24); o.pose_toc = pt.data(); }
     if (out->last_tri) { lt.resize(nd * 2); o.last_tri = lt.data(); }
-    rcs[d] = solve_host(a[d], b[d], nullptr, motions.data(), nullptr, seed_a, seed_b, (int64_t)nd, tol_d, tol_t, &o, idx.data());
+    rcs[d] = solve_host(a[d], b[d], nullptr, motions_ptr, nullptr, seed_a, seed_b, (int64_t)nd, tol_d, tol_t, &o, idx.data());
     if (rcs[d]) { errs[d] = g_err; return; }
     for (size_t k = 0; k < nd; k++)
     {

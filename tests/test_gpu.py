@@ -403,3 +403,31 @@ def test_deep_hierarchies_run_on_global_memory_stacks():
         assert num[i] == n_ref, i
         k = min(n_ref, 64)
         assert np.array_equal(recs[i][:k]["tri_a"], r_ref["tri_a"][:k]) and np.array_equal(recs[i][:k]["dist"], r_ref["dist"][:k]), i
+
+
+def test_multi_device_entry_matches_single_device(models, bvhs, golden):
+    """c2a_b200_solve_batch_multi: the same batch sharded over every GPU of the box (interleaved cost-sorted shards, one
+    host thread + stream per device, results scattered back) gives exactly the single-device results.  With one GPU the
+    entry degenerates to c2a_b200_solve_batch; the argument checks are exercised either way."""
+    g = golden("ref_knot_128x16")
+    n_dev = api.device_count()
+    bvh = bvhs("knot_128x16")
+    reps = [models("knot_128x16")] + [api.Model(bvh, d) for d in range(1, min(n_dev, 4))]
+    rng = np.random.default_rng(4)
+    sa = rng.integers(0, len(bvh["tris"]), len(g["poses"])).astype(np.int32)
+    one = api.solve_batch(reps[0], reps[0], g["poses"], sa, None)
+    many = api.solve_batch_multi(reps, reps, g["poses"], sa, None)
+    for k in one:
+        assert np.array_equal(one[k], many[k], equal_nan=True) if one[k].dtype.kind == "f" else np.array_equal(one[k], many[k]), k
+    # a batch large enough for the claim order to be cost-sorted (>= 4096), on fresh poses
+    poses = workloads.approach_batch(6000, 77, radius=workloads.KNOT_RADIUS)
+    one = api.solve_batch(reps[0], reps[0], poses, fields=("status", "toc", "distance", "num_ca", "num_bv_tests", "pose_toc"))
+    many = api.solve_batch_multi(reps, reps, poses, fields=("status", "toc", "distance", "num_ca", "num_bv_tests", "pose_toc"))
+    for k in one:
+        assert np.array_equal(one[k], many[k]), k
+    with pytest.raises(api.C2AError):   # two shards on one device
+        api.solve_batch_multi([reps[0], reps[0]], [reps[0], reps[0]], poses[:8])
+    with pytest.raises(api.C2AError):   # a seed that is not a triangle of the model
+        api.solve_batch_multi(reps, reps, poses[:8], np.full(8, 10 ** 6, np.int32), None)
+    with pytest.raises(api.C2AError):
+        api.solve_batch(reps[0], reps[0], poses[:8], np.full(8, -1, np.int32), None)
