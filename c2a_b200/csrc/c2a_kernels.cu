@@ -278,6 +278,47 @@ static long long env_ll(const char *name, long long dflt)
 }
 static int64_t g_trace_n = 0;
 
+// Per host thread and device: a lowest-priority side stream for the wide kernel's early launch, with the two events that
+// fork it from and join it to the caller's stream.
+namespace {
+struct SideStream { int device = -1; cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+struct SideStreamSet
+{
+  std::vector<SideStream> v;
+  ~SideStreamSet()
+  {
+    for (auto &c : v)
+    {
+      if (!c.s) continue;
+      int cur = -1;
+      if (cudaGetDevice(&cur) != cudaSuccess || cudaSetDevice(c.device) != cudaSuccess) { cudaGetLastError(); continue; }
+      cudaStreamDestroy(c.s); cudaEventDestroy(c.fork); cudaEventDestroy(c.join);
+      cudaSetDevice(cur);
+    }
+  }
+};
+thread_local SideStreamSet g_side;
+SideStream *side_stream(int device)  // the caller has made `device` current; nullptr: none to be had (no early launch then)
+{
+  for (auto &c : g_side.v) if (c.device == device) return c.s ? &c : nullptr;
+  SideStream c; c.device = device;
+  int least = 0, greatest = 0;
+  if (cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess &&
+      cudaStreamCreateWithPriority(&c.s, cudaStreamNonBlocking, least) == cudaSuccess)
+  {
+    if (cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming) != cudaSuccess)
+    {
+      if (c.fork) cudaEventDestroy(c.fork);
+      cudaStreamDestroy(c.s); c.s = nullptr;
+    }
+  }
+  if (!c.s) cudaGetLastError();
+  g_side.v.push_back(c);
+  return g_side.v.back().s ? &g_side.v.back() : nullptr;
+}
+}  // namespace
+
 // per-device scratch: the claim counter
 static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses, const int32_t *sa,
                         const int32_t *sb, int64_t n, double tol_d, double tol_t, const c2a_b200_results *out,
@@ -353,7 +394,7 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   const int w_stack_cap = (int)std::max<long long>(env_ll("C2A_B200_WIDE_STACK", 4096), args.stack_entries + 64);
   const int w_rec_cap = (int)env_ll("C2A_B200_WIDE_RECS", 131072);
   auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  const size_t spill_bytes = wide ? up((size_t)SPILL_BUCKETS * n * MB_DOUBLES * sizeof(double)) : 0, wctl_bytes = wide ? 256 : 0;
+  const size_t spill_bytes = wide ? up((size_t)SPILL_BUCKETS * n * MB_DOUBLES * sizeof(double)) : 0, wctl_bytes = wide ? up(SPILL_CTL_WORDS * sizeof(unsigned long long)) : 0;
   const size_t wstack_bytes = wide ? up((size_t)wwarps * w_stack_cap * ENTRY_DOUBLES * sizeof(double)) : 0;
   const size_t wrec_bytes = wide ? up((size_t)wwarps * w_rec_cap * 4 * sizeof(double)) : 0;
   const size_t wleaf_bytes = wide ? up((size_t)wwarps * WIDE_UL * WIDE_LEAFOUT_DOUBLES * sizeof(double)) : 0;
@@ -370,8 +411,14 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
     args.spill_count = reinterpret_cast<unsigned long long *>(extra + spill_bytes);
     args.spill_cap = n;
     args.spill_live = (int)env_ll("C2A_B200_SPILL_LIVE", 20);
+    CUDA_TRY(cudaMemsetAsync(extra, 0xff, spill_bytes, stream));   // query index -1 = "record not written yet"
     CUDA_TRY(cudaMemsetAsync(extra + spill_bytes, 0, wctl_bytes, stream));
   }
+  // The wide kernel is launched twice: once beside the main kernel on a side stream (its blocks move in as the main
+  // kernel's blocks retire, so the long chains of the heaviest queries overlap the main kernel's run-out), and once after
+  // it for whatever is left.  Only when the main kernel fills the machine -- smaller launches end too soon to overlap.
+  SideStream *side = nullptr;
+  if (wide && blocks == (long long)sms * per_sm && !getenv("C2A_B200_NO_EARLY_WIDE")) side = side_stream(a->device);
   args.stats = g_stats_dev;
   args.trace = (g_trace_dev && n <= g_trace_n && !step_in) ? g_trace_dev : nullptr;
   CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
@@ -386,6 +433,10 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   const bool kev = g_kev.device == a->device;
   g_kev.recorded = false;
   if (kev) cudaEventRecord(g_kev.e[0], stream);
+  if (side && (cudaEventRecord(side->fork, stream) != cudaSuccess || cudaStreamWaitEvent(side->s, side->fork, 0) != cudaSuccess))
+  {
+    cudaGetLastError(); side = nullptr;
+  }
   c2a_solve_kernel<<<(unsigned)blocks, BLOCK_THREADS, BLOCK_SMEM_BYTES, stream>>>(args);
   if (kev) cudaEventRecord(g_kev.e[1], stream);
   g_launches.fetch_add(1);
@@ -395,7 +446,7 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   {
     WideArgs w;
     w.A = args.A; w.B = args.B; w.motions = poses; w.seedA = sa; w.seedB = sb; w.tol_d = tol_d; w.tol_t = tol_t; w.out = *out;
-    w.items = args.spill_recs; w.n_items = args.spill_count; w.items_cap = n; w.counter = args.spill_count + SPILL_BUCKETS;
+    w.items = args.spill_recs; w.ctl = args.spill_count; w.items_cap = n; w.main_blocks = (unsigned)blocks;
     w.stack = reinterpret_cast<double *>(extra + spill_bytes + wctl_bytes);
     w.recs = reinterpret_cast<double *>(extra + spill_bytes + wctl_bytes + wstack_bytes);
     w.leafout = reinterpret_cast<double *>(extra + spill_bytes + wctl_bytes + wstack_bytes + wrec_bytes);
@@ -403,6 +454,22 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
     w.stack_cap = w_stack_cap; w.rec_cap = w_rec_cap;
     w.window = (int)std::min<long long>(16, std::max<long long>(1, env_ll("C2A_B200_WIDE_WINDOW", 16)));
     w.stats = g_wide_stats_dev; w.trace = args.trace;
+    if (side)
+    {
+      w.early = 1;
+      c2a_wide_kernel<<<(unsigned)wblocks, WIDE_THREADS, WIDE_BLOCK_SMEM, side->s>>>(w);
+      g_launches.fetch_add(1);
+      // the caller's stream goes on only after the side stream's kernel (which also keeps the scratch alive for it)
+      cudaError_t je = cudaGetLastError();
+      if (je == cudaSuccess) je = cudaEventRecord(side->join, side->s);
+      if (je == cudaSuccess) je = cudaStreamWaitEvent(stream, side->join, 0);
+      if (je != cudaSuccess)
+      {
+        cudaStreamSynchronize(side->s);
+        return fail(C2A_B200_ERR_CUDA, std::string("wide kernel, early launch: ") + cudaGetErrorString(je));
+      }
+    }
+    w.early = 0;
     c2a_wide_kernel<<<(unsigned)wblocks, WIDE_THREADS, WIDE_BLOCK_SMEM, stream>>>(w);
     g_launches.fetch_add(1);
     le = cudaGetLastError();

@@ -86,12 +86,14 @@ struct BatchArgs
   // state is 64 bytes: no stack) and the slot retires; the wide kernel, launched next on the stream, finishes it with
   // parallelism inside the traversal.
   double *spill_recs;                 // [SPILL_BUCKETS][spill_cap][MB_DOUBLES]
-  unsigned long long *spill_count;    // [SPILL_BUCKETS]
+  unsigned long long *spill_count;    // control words, SPILL_CTL_*: [0..2] records reserved per list, [4..6] records claimed by
+                                      // the wide kernel, [8] blocks of this kernel that have started, [9] warps that are done
   long long spill_cap;
   int spill_live;
   int max_slots;                      // query slots a warp uses (<= Q): small batches spread over all warps
 };
 constexpr int SPILL_BUCKETS = 3, SPILL_CA_HEAVY = 40, SPILL_CA_MID = 16;
+constexpr int SPILL_CTL_CLAIMED = 4, SPILL_CTL_STARTED = 8, SPILL_CTL_DONE = 9, SPILL_CTL_WORDS = 32;
 constexpr int MB_DOUBLES = 8;  // q, lamda, lastLamda, mint, UpboundTOC, {numCA, nItrs}, {nbv, ntri}, {lastA, lastB}
 
 // Single-step mode (the device side of C2A_TimeOfContactStep, C2A.cpp:1778-1931): per query the caller
@@ -228,6 +230,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
   const DevModel &A = args.A, &B = args.B;
   double *const stack_base = args.stacks + ((size_t)(blockIdx.x * WARPS_PER_BLOCK + warp) * Q) * args.stack_entries * ENTRY_DOUBLES;
   const size_t stack_stride = (size_t)args.stack_entries * ENTRY_DOUBLES;
+  if (args.spill_count && threadIdx.x == 0) atomicAdd(args.spill_count + SPILL_CTL_STARTED, 1ull);
 
 #define SD(f, s) sd[(f) * Q + (s)]
 #define SI(f, s) si[(f) * Q + (s)]
@@ -726,9 +729,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
           if (idx < (unsigned long long)args.spill_cap)
           {
             double *r = args.spill_recs + ((size_t)bucket * args.spill_cap + idx) * MB_DOUBLES;
-            r[0] = __longlong_as_double(q); r[1] = lamda; r[2] = SD(F_LASTL, slot); r[3] = SD(F_MINT, slot); r[4] = SD(F_UPB, slot);
+            r[1] = lamda; r[2] = SD(F_LASTL, slot); r[3] = SD(F_MINT, slot); r[4] = SD(F_UPB, slot);
             r[5] = __hiloint2double(numCA, SI(I_NITRS, slot)); r[6] = __hiloint2double(SI(I_NBV, slot), SI(I_NTRI, slot));
             r[7] = __hiloint2double(SI(I_LASTA, slot), SI(I_LASTB, slot));
+            // the wide kernel may be running beside this one: the query index (pre-set to -1 by the host) goes last and
+            // marks the record as complete
+            __threadfence();
+            *reinterpret_cast<volatile long long *>(r) = q;
             SI(I_STATE, slot) = ST_EXIT;
             q = -1; pending = false; handed_over = true;
           }
@@ -856,6 +863,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
       atomicAdd(args.stats + k, 1ull); atomicAdd(args.stats + k + 1, (unsigned long long)(clock64() - pass_t0));
     }
   }
+  // this warp hands nothing over any more (its records are complete: fence before the count)
+  if (args.spill_count && lane == 0) { __threadfence(); atomicAdd(args.spill_count + SPILL_CTL_DONE, 1ull); }
 #undef SD
 #undef SI
 }

@@ -68,9 +68,10 @@ struct WideArgs
   double tol_d, tol_t;
   c2a_b200_results out;
   const double *items;                  // [SPILL_BUCKETS][items_cap][MB_DOUBLES]: CA-loop state of the queries handed over
-  const unsigned long long *n_items;    // [SPILL_BUCKETS] device-resident counts
+  unsigned long long *ctl;              // the main kernel's control words (SPILL_CTL_*): list lengths, claim counters, progress
   long long items_cap;
-  unsigned long long *counter;          // claim counter
+  int early;                            // launched beside the main kernel (side stream): lists still growing, poll until it is done
+  unsigned main_blocks;                 // grid of the main kernel
   double *stack;                        // [warps][stack_cap][ENTRY_DOUBLES]
   double *recs;                         // [warps][rec_cap][4]
   double *leafout;                      // [warps][WIDE_UL][WIDE_LEAFOUT_DOUBLES]
@@ -127,20 +128,46 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
   double *const recs = args.recs + (size_t)gw * args.rec_cap * 4;
   double *const leafout = args.leafout + (size_t)gw * WIDE_UL * WIDE_LEAFOUT_DOUBLES;
 
+  // The early launch only keeps an SM slot while EVERY block of the main kernel is already on the machine (it waits for
+  // that kernel to finish, so it must never be what stands between one of its blocks and an SM); the launch after the
+  // main kernel picks up whatever this one left.
+  if (args.early && *(volatile unsigned long long *)(args.ctl + SPILL_CTL_STARTED) < (unsigned long long)args.main_blocks) return;
   if ((C2A_WIDE_STATS && args.stats) && threadIdx.x == 0) atomicMin(args.stats + WS_T_FIRST, global_ns());
   while (true)
   {
-    // ---- claim a handed-over query
-    unsigned long long item = 0;
-    if (lane == 0) item = atomicAdd(args.counter, 1ull);
-    item = shfl_u64(FULL, item, 0);
-    // the hand-over lists in order: most CA steps taken so far first
-    const unsigned long long c0 = args.n_items[0], c1 = args.n_items[1], c2 = args.n_items[2];
-    if (item >= c0 + c1 + c2) break;
-    const int bucket = item < c0 ? 0 : (item < c0 + c1 ? 1 : 2);
-    const unsigned long long bi = item - (bucket == 0 ? 0 : (bucket == 1 ? c0 : c0 + c1));
+    // ---- claim a handed-over query: the lists in order (most CA steps taken so far first).  In the early launch the
+    // main kernel is still appending: wait for more until all its warps are done
+    int bucket = -1;
+    unsigned long long bi = 0;
+    if (lane == 0)
+    {
+      volatile unsigned long long *ctl = args.ctl;
+      bool final_scan = !args.early;
+      while (true)
+      {
+        const bool main_done = final_scan || ctl[SPILL_CTL_DONE] >= (unsigned long long)args.main_blocks * WARPS_PER_BLOCK;
+        for (int b = 0; b < SPILL_BUCKETS && bucket < 0; b++)
+        {
+          unsigned long long c = ctl[SPILL_CTL_CLAIMED + b];
+          while (c < min(ctl[b], (unsigned long long)args.items_cap))
+          {
+            const unsigned long long old = atomicCAS(args.ctl + SPILL_CTL_CLAIMED + b, c, c + 1);
+            if (old == c) { bucket = b; bi = c; break; }
+            c = old;
+          }
+        }
+        if (bucket >= 0 || final_scan) break;
+        if (main_done) final_scan = true;   // the lengths read after this point are final: one more look
+        else __nanosleep(2000);
+      }
+    }
+    bucket = __shfl_sync(FULL, bucket, 0);
+    bi = shfl_u64(FULL, bi, 0);
+    if (bucket < 0) break;
     const double *r = args.items + ((size_t)bucket * args.items_cap + bi) * MB_DOUBLES;
-    const long long q = __double_as_longlong(__ldcg(r + 0));
+    long long q;
+    while ((q = *reinterpret_cast<const volatile long long *>(r)) < 0) __nanosleep(200);   // reserved, not yet written
+    __threadfence();
     double lamda = __ldcg(r + 1), lastLamda = __ldcg(r + 2), mint = __ldcg(r + 3), upb = __ldcg(r + 4);
     const double c5 = __ldcg(r + 5), c6 = __ldcg(r + 6), c7 = __ldcg(r + 7);
     int numCA = __double2hiint(c5), nItrs = __double2loint(c5);
