@@ -25,7 +25,7 @@ class Bvh(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("n_tris", C.c_int32),
                 ("R", C.c_void_p), ("Tr", C.c_void_p), ("l", C.c_void_p), ("r", C.c_void_p),
                 ("R_loc", C.c_void_p), ("ang_radius", C.c_void_p), ("first_child", C.c_void_p),
-                ("tris", C.c_void_p), ("tri_vidx", C.c_void_p)]
+                ("tris", C.c_void_p), ("tri_vidx", C.c_void_p), ("obb_d", C.c_void_p), ("obb_To", C.c_void_p)]
 
 
 # mirrors struct c2a_b200_contact
@@ -95,6 +95,8 @@ def build_bvh(tris9, vidx=None):
                "first_child": arr(v.first_child, nn, C.c_int32, np.int32),
                "tris": arr(v.tris, 9 * n, C.c_double, np.float64).reshape(n, 9),
                "tri_ids": arr(ids, n, C.c_int32, np.int32),
+               "obb_d": arr(v.obb_d, 3 * nn, C.c_double, np.float64).reshape(nn, 3),
+               "obb_To": arr(v.obb_To, 3 * nn, C.c_double, np.float64).reshape(nn, 3),
                "depth": depth.value}
         if v.tri_vidx:
             out["tri_vidx"] = arr(v.tri_vidx, 3 * n, C.c_int32, np.int32).reshape(n, 3)
@@ -105,7 +107,8 @@ def build_bvh(tris9, vidx=None):
 
 class Model:
     """A C2A model resident on one GPU.  ``bvh`` is a dict of contiguous numpy arrays with the keys of
-    ``struct c2a_b200_bvh`` (R, Tr, l, r, R_loc, ang_radius float64; first_child int32; tris float64)."""
+    ``struct c2a_b200_bvh`` (R, Tr, l, r, R_loc, ang_radius float64; first_child int32; tris float64; optionally
+    tri_vidx int32 and obb_d / obb_To float64)."""
 
     def __init__(self, bvh, device=0):
         s = Bvh()
@@ -123,6 +126,11 @@ class Model:
             tv = np.ascontiguousarray(bvh["tri_vidx"], dtype=np.int32)
             keep.append(tv)
             s.tri_vidx = tv.ctypes.data
+        if bvh.get("obb_d") is not None and bvh.get("obb_To") is not None:   # (C2A_Collide only)
+            for k in ("obb_d", "obb_To"):
+                a = np.ascontiguousarray(bvh[k], dtype=np.float64)
+                keep.append(a)
+                setattr(s, k, a.ctypes.data)
         h = C.c_void_p()
         _check(lib().c2a_b200_model_upload(C.byref(s), C.c_int32(device), C.byref(h)))
         self.h = h
@@ -270,7 +278,7 @@ def contacts_batch(model_a, model_b, poses24, threshold, max_contacts=64):
     return num, recs
 
 
-def distance_batch(model_a, model_b, poses24, seed_a=None, seed_b=None, rel_err=0.0, abs_err=0.0):
+def distance_batch(model_a, model_b, poses24, seed_a=None, seed_b=None, rel_err=0.0, abs_err=0.0, _entry="c2a_b200_distance_batch"):
     """Batched C2A_Distance (depth-first routine): poses24 [n,24] = pose of A, pose of B.  Returns a dict with
     distance [n], p1p2 [n,6], tri_pair [n,2], num_bv_tests [n], num_tri_tests [n]."""
     poses24 = np.ascontiguousarray(poses24, dtype=np.float64).reshape(-1, 24)
@@ -279,13 +287,36 @@ def distance_batch(model_a, model_b, poses24, seed_a=None, seed_b=None, rel_err=
     sb = None if seed_b is None else np.ascontiguousarray(seed_b, dtype=np.int32)
     out = {"distance": np.zeros(n), "p1p2": np.zeros((n, 6)), "tri_pair": np.zeros((n, 2), dtype=np.int32),
            "num_bv_tests": np.zeros(n, dtype=np.int32), "num_tri_tests": np.zeros(n, dtype=np.int32)}
-    _check(lib().c2a_b200_distance_batch(model_a.h, model_b.h, poses24.ctypes.data_as(C.c_void_p),
+    _check(getattr(lib(), _entry)(model_a.h, model_b.h, poses24.ctypes.data_as(C.c_void_p),
                                          sa.ctypes.data_as(C.c_void_p) if sa is not None else None,
                                          sb.ctypes.data_as(C.c_void_p) if sb is not None else None,
                                          C.c_int64(n), C.c_double(rel_err), C.c_double(abs_err),
                                          out["distance"].ctypes.data_as(C.c_void_p), out["p1p2"].ctypes.data_as(C.c_void_p),
                                          out["tri_pair"].ctypes.data_as(C.c_void_p), out["num_bv_tests"].ctypes.data_as(C.c_void_p),
                                          out["num_tri_tests"].ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def collide_distance_batch(model_a, model_b, poses24, seed_a=None, seed_b=None, rel_err=0.0, abs_err=0.0):
+    """Batched C2A_Collide, C2A_DistanceResult overload: ``distance_batch`` restricted to node pairs whose boxes overlap."""
+    return distance_batch(model_a, model_b, poses24, seed_a, seed_b, rel_err, abs_err, _entry="c2a_b200_collide_distance_batch")
+
+
+ALL_CONTACTS, FIRST_CONTACT = 1, 2   # C2A_ALL_CONTACTS / C2A_FIRST_CONTACT (C2A/C2A.h:246-247)
+
+
+def collide_batch(model_a, model_b, poses24, flag=ALL_CONTACTS, max_pairs=256):
+    """Batched C2A_Collide, PQP_CollideResult overload: poses24 [n,24] = pose of A, pose of B.  Returns a dict with
+    num_pairs [n], pairs [n,max_pairs,2] (builder-order triangle indices in the reference's reporting order, -1 beyond
+    min(num_pairs, max_pairs)), num_bv_tests [n], num_tri_tests [n]."""
+    poses24 = np.ascontiguousarray(poses24, dtype=np.float64).reshape(-1, 24)
+    n = poses24.shape[0]
+    out = {"num_pairs": np.zeros(n, dtype=np.int32), "pairs": np.full((n, max_pairs, 2), -1, dtype=np.int32),
+           "num_bv_tests": np.zeros(n, dtype=np.int32), "num_tri_tests": np.zeros(n, dtype=np.int32)}
+    _check(lib().c2a_b200_collide_batch(model_a.h, model_b.h, poses24.ctypes.data_as(C.c_void_p), C.c_int64(n), C.c_int32(flag),
+                                        C.c_int32(max_pairs), out["num_pairs"].ctypes.data_as(C.c_void_p),
+                                        out["pairs"].ctypes.data_as(C.c_void_p) if max_pairs else None,
+                                        out["num_bv_tests"].ctypes.data_as(C.c_void_p), out["num_tri_tests"].ctypes.data_as(C.c_void_p)))
     return out
 
 

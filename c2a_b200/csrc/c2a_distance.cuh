@@ -5,8 +5,13 @@
 // (rss_rect_dist, tri_distance).  The result depends on the visiting order exactly as in the CCD traversal
 // (res->distance shrinks as leaves are visited and gates the pruning), so a query is one thread walking the
 // reference's depth-first order with a local stack; parallelism is across queries.
+//
+// GATE = true is C2A_Collide's C2A_DistanceResult overload (C2A_PQP.cpp:1060-1280): the same walk, except that a node
+// pair whose boxes do not overlap is left at once (C2A_BV_Overlap at the top of C2ACollideRecurse, :1068).  The gate is
+// handed the transform this walk chains through the RSS corners Tr, as the reference does (its RSS_TYPE branch comes
+// first, :1118-1152), with the boxes' half-dimensions BV::d.
 #pragma once
-#include "c2a_solve.cuh"
+#include "c2a_collide.cuh"
 
 namespace c2a {
 
@@ -22,12 +27,13 @@ struct DistanceArgs
   int *tri_pair;              // [n][2] or NULL: closest triangle pair, builder order (o->last_tri coming out)
   int *num_bv_tests, *num_tri_tests;  // [n] or NULL
   double *gstack;             // GS = true: [entries][DIST_ENTRY][threads] traversal stacks in global memory
+  const double *obbA, *obbB;  // GATE = true: [n_nodes][OBB_STRIDE] box half-dimensions d(3) (+ centre, unused here)
 };
 
 constexpr int DIST_STACK = 96;  // local-memory stack; deeper hierarchies run the GS = true instance
 constexpr int DIST_ENTRY = 14;  // R(9) T(3) ids d
 
-template <bool GS>
+template <bool GS, bool GATE>
 __global__ void __launch_bounds__(128) c2a_distance_kernel(const DistanceArgs args)
 {
   const DevModel &A = args.A, &B = args.B;
@@ -76,6 +82,13 @@ __global__ void __launch_bounds__(128) c2a_distance_kernel(const DistanceArgs ar
       T[0] = STK(ei, 9); T[1] = STK(ei, 10); T[2] = STK(ei, 11);
       const double e_ids = STK(ei, 12);
       const int b1 = __double2hiint(e_ids), b2 = __double2loint(e_ids);
+      if (GATE)
+      {
+        double da[3], db[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) { da[i] = __ldg(args.obbA + (size_t)b1 * OBB_STRIDE + i); db[i] = __ldg(args.obbB + (size_t)b2 * OBB_STRIDE + i); }
+        if (obb_disjoint(R, T, da, db) != 0) continue;
+      }
       const NodeMeta ma = A.meta[b1], mb = B.meta[b2];
       const bool l1 = ma.first_child < 0, l2 = mb.first_child < 0;
       if (l1 && l2)

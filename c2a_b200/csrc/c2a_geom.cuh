@@ -108,6 +108,9 @@ C2A_DEV bool in_voronoi(double a, double b, double AnB, double AnT, double AdB, 
 // each pair's operands with selects (no 16-way branch) and running the Voronoi tests (the FP64
 // divisions) in code common to all lanes.  The expressions and the acceptance order are the
 // reference's, so the result is bit-identical.
+#ifdef C2A_RD_STATS   // development aid (scripts/build_variant.py ... -DC2A_RD_STATS): candidate / trip histograms
+__device__ unsigned long long g_rd_stats[64];
+#endif
 C2A_DEV double rss_rect_dist(const double R[9], const double T[3], double a0, double a1, double b0, double b1,
                              double S[3])
 {
@@ -218,8 +221,17 @@ C2A_DEV double rss_rect_dist(const double R[9], const double T[3], double a0, do
   // counts when the first is rejected, so the accepted pair is the ladder's.
   int kf = -1;
   double t = 0, u = 0;
+#ifdef C2A_RD_STATS
+  atomicAdd(&g_rd_stats[__popc(mask)], 1ull);
+  int rd_trips = 0;
+  { const unsigned act = __activemask(); if ((threadIdx.x & 31) == __ffs(act) - 1) { atomicAdd(&g_rd_stats[60], 1ull); atomicAdd(&g_rd_stats[61], (unsigned long long)__popc(act)); } }
+#endif
   while (mask)
   {
+#ifdef C2A_RD_STATS
+    rd_trips++;
+    { const unsigned act = __activemask(); if ((threadIdx.x & 31) == __ffs(act) - 1) { atomicAdd(&g_rd_stats[62], 1ull); atomicAdd(&g_rd_stats[63], (unsigned long long)__popc(act)); } }
+#endif
     const int k1 = __ffs(mask) - 1;
     mask &= mask - 1;
     const int k2 = mask ? __ffs(mask) - 1 : k1;
@@ -238,9 +250,17 @@ C2A_DEV double rss_rect_dist(const double R[9], const double T[3], double a0, do
       const PairOps &o = ok1 ? o1 : o2;
       seg_params(t, u, o.la, o.lb, o.AdB, o.dB, o.eB);
       kf = ok1 ? k1 : k2;
+#ifdef C2A_RD_STATS
+      atomicAdd(&g_rd_stats[ok1 ? 26 : 27], 1ull);
+      atomicAdd(&g_rd_stats[32 + kf], 1ull);
+#endif
       break;
     }
   }
+#ifdef C2A_RD_STATS
+  atomicAdd(&g_rd_stats[17 + min(rd_trips, 8)], 1ull);
+  if (kf < 0) atomicAdd(&g_rd_stats[28], 1ull);
+#endif
 
   if (kf >= 0)
   {

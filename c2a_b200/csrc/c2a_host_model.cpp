@@ -8,8 +8,9 @@
 //   C2A_BV::FitToTris_Corner (RSS branch), ComputeAngularRadius    C2A/src/C2A_BV.cpp:354-635, 71-111
 //   make_parent_relative                           C2A/src/C2A_Build.cpp:493-544
 //   Meigen (PQP, un-vendored): cyclic Jacobi eigen-solver, the classical threshold-sweep form.
-// Only the fields the traversal reads are produced (R, Tr, l, r, R_loc, angularRadius, first_child);
-// OBB fields, corners and the uninitialised bookkeeping of the reference are not.
+// Only the fields the traversals read are produced (R, Tr, l, r, R_loc, angularRadius, first_child, and the OBB
+// half-dimensions d / centre To that C2A_Collide's overlap test reads, C2A_BV.cpp:398-418); corners and the
+// uninitialised bookkeeping of the reference are not.
 // Compile with -ffp-contract=off.
 #include <math.h>
 #include <stdint.h>
@@ -27,6 +28,7 @@ struct Tri9 { double p[9]; int id; };
 struct HostBvh
 {
   std::vector<double> R, Tr, l, r, R_loc, ang;
+  std::vector<double> obb_d, obb_To;  // [n][3] each: OBB half-dimensions and centre (parent-relative like Tr)
   std::vector<int32_t> first_child;
   std::vector<double> tris;      // permuted order
   std::vector<int32_t> tri_ids;  // original index of each permuted triangle
@@ -207,6 +209,19 @@ struct Builder
     auto Z = [&](int i) { return P[(size_t)3 * i + 2]; };
 
     double minx, maxx, miny, maxy, minz, maxz;
+    {
+      // OBB fit (C2A_BV.cpp:398-418): extents of the projected points, centre back in the model frame
+      minx = maxx = X(0); miny = maxy = Y(0); minz = maxz = Z(0);
+      for (int i = 1; i < np; i++)
+      {
+        if (X(i) < minx) minx = X(i); else if (X(i) > maxx) maxx = X(i);
+        if (Y(i) < miny) miny = Y(i); else if (Y(i) > maxy) maxy = Y(i);
+        if (Z(i) < minz) minz = Z(i); else if (Z(i) > maxz) maxz = Z(i);
+      }
+      const double c[3] = {0.5 * (maxx + minx), 0.5 * (maxy + miny), 0.5 * (maxz + minz)};
+      mv(&out.obb_To[3 * bn], O, c);
+      out.obb_d[3 * bn] = 0.5 * (maxx - minx); out.obb_d[3 * bn + 1] = 0.5 * (maxy - miny); out.obb_d[3 * bn + 2] = 0.5 * (maxz - minz);
+    }
     minz = maxz = Z(0);
     for (int i = 1; i < np; i++)
     {
@@ -350,16 +365,24 @@ struct Builder
   }
 
   // world-relative -> parent-relative (children first, then self)
-  void parent_relative(int bn, const double pR[9], const double pT[3])
+  void parent_relative(int bn, const double pR[9], const double pT[3], const double pTo[3])
   {
     const int fc = out.first_child[bn];
     if (fc >= 0)
     {
-      double myR[9], myT[3];
+      double myR[9], myT[3], myTo[3];
       memcpy(myR, &out.R[9 * bn], sizeof(myR));
       memcpy(myT, &out.Tr[3 * bn], sizeof(myT));
-      parent_relative(fc, myR, myT);
-      parent_relative(fc + 1, myR, myT);
+      memcpy(myTo, &out.obb_To[3 * bn], sizeof(myTo));
+      parent_relative(fc, myR, myT, myTo);
+      parent_relative(fc + 1, myR, myT, myTo);
+    }
+    {
+      double *To = &out.obb_To[3 * bn];
+      const double d[3] = {To[0] - pTo[0], To[1] - pTo[1], To[2] - pTo[2]};
+      To[0] = (pR[0] * d[0] + pR[3] * d[1] + pR[6] * d[2]);
+      To[1] = (pR[1] * d[0] + pR[4] * d[1] + pR[7] * d[2]);
+      To[2] = (pR[2] * d[0] + pR[5] * d[1] + pR[8] * d[2]);
     }
     double *R = &out.R[9 * bn], *T = &out.Tr[3 * bn], Rpc[9], Tpc[3];
     for (int i = 0; i < 3; i++)
@@ -378,12 +401,12 @@ static void build(const double *tris9, int n, HostBvh &out)
   for (int i = 0; i < n; i++) { memcpy(tris[i].p, tris9 + 9 * (size_t)i, sizeof(double) * 9); tris[i].id = i; }
   const int nb = 2 * n - 1;
   out.R.assign((size_t)9 * nb, 0); out.Tr.assign((size_t)3 * nb, 0); out.l.assign((size_t)2 * nb, 0);
-  out.r.assign(nb, 0); out.R_loc.assign((size_t)9 * nb, 0); out.ang.assign(nb, 0); out.first_child.assign(nb, 0);
+  out.r.assign(nb, 0); out.obb_d.assign((size_t)3 * nb, 0); out.obb_To.assign((size_t)3 * nb, 0); out.R_loc.assign((size_t)9 * nb, 0); out.ang.assign(nb, 0); out.first_child.assign(nb, 0);
   Builder b(tris, out);
   b.num_bvs = 1;
   b.recurse(0, 0, n, 0);
   const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Z[3] = {0, 0, 0};
-  b.parent_relative(0, I, Z);
+  b.parent_relative(0, I, Z, Z);
   out.tris.resize((size_t)9 * n);
   out.tri_ids.resize(n);
   for (int i = 0; i < n; i++) { memcpy(&out.tris[(size_t)9 * i], tris[i].p, sizeof(double) * 9); out.tri_ids[i] = tris[i].id; }
@@ -429,6 +452,7 @@ int c2a_b200_bvh_view(const c2a_b200_host_bvh *h, c2a_b200_bvh *view, const int3
   view->R_loc = h->b.R_loc.data(); view->ang_radius = h->b.ang.data(); view->first_child = h->b.first_child.data();
   view->tris = h->b.tris.data();
   view->tri_vidx = h->b.tri_vidx.empty() ? nullptr : h->b.tri_vidx.data();
+  view->obb_d = h->b.obb_d.data(); view->obb_To = h->b.obb_To.data();
   if (tri_ids) *tri_ids = h->b.tri_ids.data();
   if (depth) *depth = h->b.depth;
   return C2A_B200_OK;

@@ -66,6 +66,7 @@ struct c2a_b200_model
   double *geom, *rloc, *tris;
   c2a::NodeMeta *meta;
   int *tri_vidx;  // may be NULL
+  double *obb;    // [n_nodes][OBB_STRIDE]: d(3), To(3); NULL when the model came without OBB data (C2A_Collide refuses it)
 };
 
 using namespace c2a;
@@ -224,7 +225,7 @@ int c2a_b200_model_upload(const c2a_b200_bvh *bvh, int32_t device, c2a_b200_mode
   c2a_b200_model *m = new c2a_b200_model();
   m->device = device; m->n_nodes = n; m->n_tris = nt; m->depth = depth;
   m->root_ang_radius = bvh->ang_radius[0];
-  m->geom = m->rloc = m->tris = nullptr; m->meta = nullptr; m->tri_vidx = nullptr;
+  m->geom = m->rloc = m->tris = m->obb = nullptr; m->meta = nullptr; m->tri_vidx = nullptr;
   cudaError_t e;
   if ((e = cudaMalloc(&m->geom, geom.size() * sizeof(double))) != cudaSuccess ||
       (e = cudaMalloc(&m->rloc, rloc.size() * sizeof(double))) != cudaSuccess ||
@@ -240,6 +241,21 @@ int c2a_b200_model_upload(const c2a_b200_bvh *bvh, int32_t device, c2a_b200_mode
     c2a_b200_model_free(m);
     return fail(C2A_B200_ERR_CUDA, std::string("model upload: ") + cudaGetErrorString(e));
   }
+  if (bvh->obb_d && bvh->obb_To)
+  {
+    std::vector<double> obb((size_t)n * OBB_STRIDE, 0.0);
+    for (int i = 0; i < n; i++)
+    {
+      memcpy(&obb[(size_t)i * OBB_STRIDE], bvh->obb_d + 3 * (size_t)i, 3 * sizeof(double));
+      memcpy(&obb[(size_t)i * OBB_STRIDE + 3], bvh->obb_To + 3 * (size_t)i, 3 * sizeof(double));
+    }
+    if ((e = cudaMalloc(&m->obb, obb.size() * sizeof(double))) != cudaSuccess ||
+        (e = cudaMemcpy(m->obb, obb.data(), obb.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess)
+    {
+      c2a_b200_model_free(m);
+      return fail(C2A_B200_ERR_CUDA, std::string("model upload (OBB data): ") + cudaGetErrorString(e));
+    }
+  }
   *out = m;
   return C2A_B200_OK;
 }
@@ -248,7 +264,7 @@ int c2a_b200_model_free(c2a_b200_model *m)
 {
   if (!m) return C2A_B200_OK;
   DeviceGuard device_guard_(m->device);
-  cudaFree(m->geom); cudaFree(m->rloc); cudaFree(m->meta); cudaFree(m->tris); cudaFree(m->tri_vidx);
+  cudaFree(m->geom); cudaFree(m->rloc); cudaFree(m->meta); cudaFree(m->tris); cudaFree(m->tri_vidx); cudaFree(m->obb);
   delete m;
   return C2A_B200_OK;
 }
@@ -594,12 +610,15 @@ int c2a_b200_contacts_batch(const c2a_b200_model *a, const c2a_b200_model *b, co
   return rc;
 }
 
-int c2a_b200_distance_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses24, const int32_t *seed_a,
-                            const int32_t *seed_b, int64_t n, double rel_err, double abs_err, double *distance, double *p1p2,
-                            int32_t *tri_pair, int32_t *num_bv_tests, int32_t *num_tri_tests)
+// C2A_Distance (gate = false) and C2A_Collide's C2A_DistanceResult overload (gate = true: the same walk behind the
+// box-overlap test) share everything but one template flag of the kernel
+static int distance_like(bool gate, const c2a_b200_model *a, const c2a_b200_model *b, const double *poses24, const int32_t *seed_a,
+                         const int32_t *seed_b, int64_t n, double rel_err, double abs_err, double *distance, double *p1p2,
+                         int32_t *tri_pair, int32_t *num_bv_tests, int32_t *num_tri_tests)
 {
   if (!a || !b || n < 0 || (n > 0 && (!poses24 || !distance))) return fail(C2A_B200_ERR_ARG, "NULL argument");
   if (a->device != b->device) return fail(C2A_B200_ERR_DEVICE, "models live on different devices");
+  if (gate && (!a->obb || !b->obb)) return fail(C2A_B200_ERR_ARG, "C2A_Collide needs models uploaded with obb_d / obb_To");
   if (n == 0) return C2A_B200_OK;
   if (int rc = check_seeds(seed_a, n, a->n_tris, "seed_a")) return rc;
   if (int rc = check_seeds(seed_b, n, b->n_tris, "seed_b")) return rc;
@@ -636,13 +655,22 @@ int c2a_b200_distance_batch(const c2a_b200_model *a, const c2a_b200_model *b, co
     const long long need = (n + 127) / 128;
     if (blocks > need) blocks = need;
     args.gstack = nullptr;
+    args.obbA = a->obb; args.obbB = b->obb;
     const int entries = a->depth + b->depth + 2;
-    if (entries <= DIST_STACK) c2a_distance_kernel<false><<<(unsigned)blocks, 128>>>(args);
+    if (entries <= DIST_STACK)
+    {
+      if (gate) c2a_distance_kernel<false, true><<<(unsigned)blocks, 128>>>(args);
+      else c2a_distance_kernel<false, false><<<(unsigned)blocks, 128>>>(args);
+    }
     else
     {
       if (blocks > 16) blocks = 16;
       STEP(cudaMalloc(&args.gstack, (size_t)blocks * 128 * entries * DIST_ENTRY * sizeof(double)));
-      if (rc == C2A_B200_OK) c2a_distance_kernel<true><<<(unsigned)blocks, 128>>>(args);
+      if (rc == C2A_B200_OK)
+      {
+        if (gate) c2a_distance_kernel<true, true><<<(unsigned)blocks, 128>>>(args);
+        else c2a_distance_kernel<true, false><<<(unsigned)blocks, 128>>>(args);
+      }
     }
     g_launches.fetch_add(1);
     STEP(cudaGetLastError());
@@ -652,6 +680,81 @@ int c2a_b200_distance_batch(const c2a_b200_model *a, const c2a_b200_model *b, co
   STEP(cudaMemcpy(distance, arena + o_d, N * 8, cudaMemcpyDeviceToHost));
   if (p1p2) STEP(cudaMemcpy(p1p2, arena + o_pp, N * 48, cudaMemcpyDeviceToHost));
   if (tri_pair) STEP(cudaMemcpy(tri_pair, arena + o_tp, N * 8, cudaMemcpyDeviceToHost));
+  if (num_bv_tests) STEP(cudaMemcpy(num_bv_tests, arena + o_nbv, N * 4, cudaMemcpyDeviceToHost));
+  if (num_tri_tests) STEP(cudaMemcpy(num_tri_tests, arena + o_ntri, N * 4, cudaMemcpyDeviceToHost));
+#undef STEP
+  cudaFree(arena);
+  return rc;
+}
+
+int c2a_b200_distance_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses24, const int32_t *seed_a,
+                            const int32_t *seed_b, int64_t n, double rel_err, double abs_err, double *distance, double *p1p2,
+                            int32_t *tri_pair, int32_t *num_bv_tests, int32_t *num_tri_tests)
+{
+  return distance_like(false, a, b, poses24, seed_a, seed_b, n, rel_err, abs_err, distance, p1p2, tri_pair, num_bv_tests, num_tri_tests);
+}
+
+int c2a_b200_collide_distance_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses24, const int32_t *seed_a,
+                                    const int32_t *seed_b, int64_t n, double rel_err, double abs_err, double *distance,
+                                    double *p1p2, int32_t *tri_pair, int32_t *num_bv_tests, int32_t *num_tri_tests)
+{
+  return distance_like(true, a, b, poses24, seed_a, seed_b, n, rel_err, abs_err, distance, p1p2, tri_pair, num_bv_tests, num_tri_tests);
+}
+
+int c2a_b200_collide_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses24, int64_t n, int32_t flag,
+                           int32_t max_pairs, int32_t *num_pairs, int32_t *pairs, int32_t *num_bv_tests, int32_t *num_tri_tests)
+{
+  if (!a || !b || n < 0 || (n > 0 && (!poses24 || !num_pairs))) return fail(C2A_B200_ERR_ARG, "NULL argument");
+  if (flag != 1 && flag != 2) return fail(C2A_B200_ERR_ARG, "flag must be 1 (all contacts) or 2 (first contact)");
+  if (max_pairs < 0 || (max_pairs > 0 && !pairs)) return fail(C2A_B200_ERR_ARG, "max_pairs > 0 needs a pairs array");
+  if (a->device != b->device) return fail(C2A_B200_ERR_DEVICE, "models live on different devices");
+  if (!a->obb || !b->obb) return fail(C2A_B200_ERR_ARG, "C2A_Collide needs models uploaded with obb_d / obb_To");
+  if (n == 0) return C2A_B200_OK;
+  ON_DEVICE(a->device);
+  const size_t N = (size_t)n;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_pose = take(N * 192), o_np = take(N * 4), o_pairs = max_pairs ? take(N * (size_t)max_pairs * 8) : 0;
+  const size_t o_nbv = num_bv_tests ? take(N * 4) : 0, o_ntri = num_tri_tests ? take(N * 4) : 0;
+  char *arena = nullptr;
+  CUDA_TRY(cudaMalloc(&arena, off));
+  int rc = C2A_B200_OK;
+  cudaError_t e = cudaSuccess;
+#define STEP(x) if (rc == C2A_B200_OK && (e = (x)) != cudaSuccess) rc = fail(C2A_B200_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e));
+  STEP(cudaMemcpy(arena + o_pose, poses24, N * 192, cudaMemcpyHostToDevice));
+  if (max_pairs) STEP(cudaMemset(arena + o_pairs, 0xff, N * (size_t)max_pairs * 8));   // unused entries read -1
+  if (rc == C2A_B200_OK)
+  {
+    CollideArgs args;
+    args.A = DevModel{a->geom, a->rloc, a->meta, a->tris, a->n_nodes, a->n_tris};
+    args.B = DevModel{b->geom, b->rloc, b->meta, b->tris, b->n_nodes, b->n_tris};
+    args.obbA = a->obb; args.obbB = b->obb;
+    args.poses = (const double *)(arena + o_pose);
+    args.n = n; args.flag = flag; args.max_pairs = max_pairs;
+    args.num_pairs = (int *)(arena + o_np); args.pairs = max_pairs ? (int *)(arena + o_pairs) : nullptr;
+    args.num_bv_tests = num_bv_tests ? (int *)(arena + o_nbv) : nullptr;
+    args.num_tri_tests = num_tri_tests ? (int *)(arena + o_ntri) : nullptr;
+    int sms = 0;
+    STEP(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, a->device));
+    long long blocks = (long long)sms * 8;
+    const long long need = (n + 127) / 128;
+    if (blocks > need) blocks = need;
+    args.gstack = nullptr;
+    const int entries = a->depth + b->depth + 2;
+    if (entries <= COLL_STACK) c2a_collide_kernel<false><<<(unsigned)blocks, 128>>>(args);
+    else
+    {
+      if (blocks > 16) blocks = 16;
+      STEP(cudaMalloc(&args.gstack, (size_t)blocks * 128 * entries * COLL_ENTRY * sizeof(double)));
+      if (rc == C2A_B200_OK) c2a_collide_kernel<true><<<(unsigned)blocks, 128>>>(args);
+    }
+    g_launches.fetch_add(1);
+    STEP(cudaGetLastError());
+    STEP(cudaDeviceSynchronize());
+    if (args.gstack) cudaFree(args.gstack);
+  }
+  STEP(cudaMemcpy(num_pairs, arena + o_np, N * 4, cudaMemcpyDeviceToHost));
+  if (max_pairs) STEP(cudaMemcpy(pairs, arena + o_pairs, N * (size_t)max_pairs * 8, cudaMemcpyDeviceToHost));
   if (num_bv_tests) STEP(cudaMemcpy(num_bv_tests, arena + o_nbv, N * 4, cudaMemcpyDeviceToHost));
   if (num_tri_tests) STEP(cudaMemcpy(num_tri_tests, arena + o_ntri, N * 4, cudaMemcpyDeviceToHost));
 #undef STEP
@@ -1550,3 +1653,10 @@ extern "C" int c2a_b200_fp64_peak(double *tflops_fma, double *tflops_mul_add)
   if (tflops_mul_add) *tflops_mul_add = res[1];
   return C2A_B200_OK;
 }
+
+#ifdef C2A_RD_STATS
+extern "C" int c2a_b200_rd_stats(unsigned long long *out64)
+{
+  return cudaMemcpyFromSymbol(out64, c2a::g_rd_stats, 64 * sizeof(unsigned long long)) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -41,6 +41,7 @@ namespace c2a {
 constexpr int GEOM_STRIDE = 16;
 constexpr int RLOC_STRIDE = 10;   // R_loc(9) + pad: 80-byte records, so that they can be fetched with 128-bit loads
 constexpr int TRI_STRIDE = 10;    // p1 p2 p3 (9) + pad, likewise
+constexpr int OBB_STRIDE = 6;    // OBB half-dimensions d(3) + centre To(3) (C2A_Collide only)
 struct NodeMeta { double size; int first_child; int pad; };
 struct DevModel
 {

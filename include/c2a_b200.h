@@ -53,6 +53,10 @@ typedef struct c2a_b200_bvh
   const double *tris;         /* [n_tris][9]  p1,p2,p3 */
   const int32_t *tri_vidx;    /* [n_tris][3]  vertex indices of each triangle (C2A_Tri::Index(), C2A/C2A_Tri.h:46-52),
                                               builder order; only used to label contact features; may be NULL */
+  const double *obb_d;        /* [n_nodes][3] OBB half-dimensions BV::d (C2A/src/C2A_BV.cpp:414-416) and           */
+  const double *obb_To;       /* [n_nodes][3] OBB centre BV::To, parent-relative (C2A_Build.cpp:540-541): read by   */
+                              /*              the C2A_Collide entries only; both may be NULL (those entries then    */
+                              /*              refuse the model)                                                     */
 } c2a_b200_bvh;
 
 /* One contact of the contact pass (ContactF, C2A/C2A.h:117-153). */
@@ -164,6 +168,28 @@ int c2a_b200_contacts_batch(const c2a_b200_model *a, const c2a_b200_model *b, co
 int c2a_b200_distance_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses24, const int32_t *seed_a,
                             const int32_t *seed_b, int64_t n, double rel_err, double abs_err, double *distance, double *p1p2,
                             int32_t *tri_pair, int32_t *num_bv_tests, int32_t *num_tri_tests);
+
+/* Batched C2A_Collide, PQP_CollideResult overload (C2A/C2A.h:249-253, C2A/src/C2A_PQP.cpp:798-968): the pairs of
+ * intersecting triangles of the two models at the static poses poses24[i].  flag: 1 = C2A_ALL_CONTACTS, 2 =
+ * C2A_FIRST_CONTACT (C2A/C2A.h:246-247).  num_pairs [n] = PQP_CollideResult::NumPairs(); pairs [n][max_pairs][2]: the
+ * first min(num_pairs, max_pairs) pairs of each query in the order the reference's traversal reports them, as
+ * BUILDER-ORDER triangle indices (tri_ids of c2a_b200_bvh_view maps them to the reference's Tri::id = AddTri index);
+ * unused entries are -1.  num_bv_tests / num_tri_tests as PQP_CollideResult (may be NULL; pairs may be NULL with
+ * max_pairs 0).  Both models must have been uploaded with obb_d / obb_To.
+ * The box and triangle overlap tests are PQP's obb_disjoint / TriContact (not in the reference's tree): restated from
+ * the published separating-axis tests; parity is against the reference compiled with this repo's PQP stand-in
+ * (oracle/pqp_shim), see DESIGN.md section 8.  Host buffers; not part of the CCD hot path. */
+int c2a_b200_collide_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses24, int64_t n, int32_t flag,
+                           int32_t max_pairs, int32_t *num_pairs, int32_t *pairs, int32_t *num_bv_tests,
+                           int32_t *num_tri_tests);
+
+/* Batched C2A_Collide, C2A_DistanceResult overload (C2A/C2A.h:262-267, C2A/src/C2A_PQP.cpp:1060-1280): the walk of
+ * c2a_b200_distance_batch restricted to node pairs whose boxes overlap (the result is the seed pair's distance when
+ * the root boxes are apart).  Arguments and outputs as c2a_b200_distance_batch. */
+int c2a_b200_collide_distance_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses24,
+                                    const int32_t *seed_a, const int32_t *seed_b, int64_t n, double rel_err, double abs_err,
+                                    double *distance, double *p1p2, int32_t *tri_pair, int32_t *num_bv_tests,
+                                    int32_t *num_tri_tests);
 
 /* Host half of the motion model: what constructing the two CInterpMotion_Linear objects does in
  * C2A_Solve (C2A/src/C2A.cpp:2378-2379 -> C2A/src/InterpMotion.cpp:148-168, 486-491, 228-270).

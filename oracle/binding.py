@@ -194,6 +194,36 @@ class _Port:
                                   C.c_void_p(out[i:i + 1].ctypes.data))
         return out
 
+    def collide(self, bvhA, bvhB, poses24, flag=1, max_pairs=4096):
+        """C2A_Collide (PQP_CollideResult overload) per query.  Returns (num_pairs [n], list of [k,2] builder-order
+        triangle index pairs in traversal order, num_bv_tests [n], num_tri_tests [n])."""
+        sA, sB = bvh_struct(bvhA), bvh_struct(bvhB)
+        obb = [np.ascontiguousarray(x, np.float64) for x in (bvhA["obb_d"], bvhA["obb_To"], bvhB["obb_d"], bvhB["obb_To"])]
+        poses24 = np.ascontiguousarray(poses24, np.float64).reshape(-1, 24)
+        n = len(poses24)
+        num = np.zeros(n, np.int32); nbv = np.zeros(n, np.int32); ntri = np.zeros(n, np.int32); pairs = []
+        buf = np.zeros((max_pairs, 2), np.int32)
+        self.lib.orc_collide.restype = C.c_int32
+        for i in range(n):
+            a, b = C.c_int32(), C.c_int32()
+            num[i] = self.lib.orc_collide(C.byref(sA), C.byref(sB), _ptr(obb[0]), _ptr(obb[1]), _ptr(obb[2]), _ptr(obb[3]),
+                                          _ptr(poses24[i]), C.c_int32(flag), C.c_int32(max_pairs), _ptr(buf), C.byref(a), C.byref(b))
+            nbv[i], ntri[i] = a.value, b.value
+            pairs.append(buf[:min(int(num[i]), max_pairs)].copy())
+        return num, pairs, nbv, ntri
+
+    def collide_distance(self, bvhA, bvhB, poses24, seedA=None, seedB=None, rel_err=0.0, abs_err=0.0):
+        """C2A_Collide (C2A_DistanceResult overload) per query; records like distance()."""
+        sA, sB = bvh_struct(bvhA), bvh_struct(bvhB)
+        dA = np.ascontiguousarray(bvhA["obb_d"], np.float64); dB = np.ascontiguousarray(bvhB["obb_d"], np.float64)
+        poses24 = np.ascontiguousarray(poses24, np.float64).reshape(-1, 24)
+        out = np.zeros(len(poses24), dtype=DISTANCE_DTYPE)
+        for i in range(len(poses24)):
+            self.lib.orc_collide_distance(C.byref(sA), C.byref(sB), _ptr(dA), _ptr(dB), _ptr(poses24[i]),
+                                          C.c_int32(0 if seedA is None else int(seedA[i])), C.c_int32(0 if seedB is None else int(seedB[i])),
+                                          C.c_double(rel_err), C.c_double(abs_err), C.c_void_p(out[i:i + 1].ctypes.data))
+        return out
+
     def rect_dist(self, Rab, Tab, a, b):
         Rab = np.ascontiguousarray(Rab, np.float64); Tab = np.ascontiguousarray(Tab, np.float64)
         a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64)
@@ -230,6 +260,8 @@ class RefModel:
              "tris": np.zeros((nt, 9)), "tri_ids": np.zeros(nt, np.int32)}
         self.lib.ref_model_export(self.h, _ptr(b["R"]), _ptr(b["Tr"]), _ptr(b["l"]), _ptr(b["r"]), _ptr(b["R_loc"]),
                                   _ptr(b["ang_radius"]), _ptr(b["first_child"]), _ptr(b["tris"]), _ptr(b["tri_ids"]))
+        b["obb_d"] = np.zeros((nn, 3)); b["obb_To"] = np.zeros((nn, 3))
+        self.lib.ref_model_export_obb(self.h, _ptr(b["obb_d"]), _ptr(b["obb_To"]))
         return b
 
 
@@ -266,6 +298,30 @@ class _Ref:
             self.lib.ref_distance(mA.h, mB.h, _ptr(poses24[i]), C.c_int32(0 if seedA is None else int(seedA[i])),
                                   C.c_int32(0 if seedB is None else int(seedB[i])), C.c_double(rel_err), C.c_double(abs_err),
                                   C.c_int32(qsize), C.c_void_p(out[i:i + 1].ctypes.data))
+        return out
+
+    def collide(self, mA, mB, poses24, flag=1, max_pairs=4096):
+        """The reference's own C2A_Collide (PQP_CollideResult overload), one query at a time.  Pairs are AddTri ids."""
+        poses24 = np.ascontiguousarray(poses24, np.float64).reshape(-1, 24)
+        n = len(poses24)
+        num = np.zeros(n, np.int32); nbv = np.zeros(n, np.int32); ntri = np.zeros(n, np.int32); pairs = []
+        buf = np.zeros((max_pairs, 2), np.int32)
+        self.lib.ref_collide.restype = C.c_int32
+        for i in range(n):
+            a, b = C.c_int32(), C.c_int32()
+            num[i] = self.lib.ref_collide(mA.h, mB.h, _ptr(poses24[i]), C.c_int32(flag), C.c_int32(max_pairs), _ptr(buf), C.byref(a), C.byref(b))
+            nbv[i], ntri[i] = a.value, b.value
+            pairs.append(buf[:min(int(num[i]), max_pairs)].copy())
+        return num, pairs, nbv, ntri
+
+    def collide_distance(self, mA, mB, poses24, seedA=None, seedB=None, rel_err=0.0, abs_err=0.0):
+        """The reference's own C2A_Collide (C2A_DistanceResult overload), one query at a time."""
+        poses24 = np.ascontiguousarray(poses24, np.float64).reshape(-1, 24)
+        out = np.zeros(len(poses24), dtype=DISTANCE_DTYPE)
+        for i in range(len(poses24)):
+            self.lib.ref_collide_distance(mA.h, mB.h, _ptr(poses24[i]), C.c_int32(0 if seedA is None else int(seedA[i])),
+                                          C.c_int32(0 if seedB is None else int(seedB[i])), C.c_double(rel_err), C.c_double(abs_err),
+                                          C.c_void_p(out[i:i + 1].ctypes.data))
         return out
 
     def rect_dist(self, Rab, Tab, a, b):

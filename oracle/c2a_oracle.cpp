@@ -1923,6 +1923,248 @@ extern "C" void orc_distance(const orc_bvh *A, const orc_bvh *B, const double po
   mt_v(res->p2, cx.Rrel, u);
 }
 
+// ---- discrete collision queries -----------------------------------------------------------------
+// C2A_Collide, both overloads (C2A/src/C2A_PQP.cpp:798-968 and :1060-1280).  Their box-overlap and triangle-overlap
+// tests are PQP's (obb_disjoint, TriContact: un-vendored, no in-tree source): restated here from the published
+// separating-axis formulations, in the arithmetic of oracle/pqp_shim/pqp_shim.cpp, which is what the compiled
+// reference (_ref) links -- parity for these two functions is therefore pinned to the shim, not to PQP itself.
+extern "C" int32_t orc_obb_disjoint(const double B[9], const double T[3], const double a[3], const double b[3])
+{
+  const double reps = 1e-6;
+  double Bf[9];
+  for (int i = 0; i < 9; i++) Bf[i] = fabs(B[i]) + reps;
+  for (int i = 0; i < 3; i++)
+  {
+    const double t = fabs(T[i]);
+    if (t > a[i] + b[0] * Bf[3 * i + 0] + b[1] * Bf[3 * i + 1] + b[2] * Bf[3 * i + 2]) return 1 + i;
+  }
+  for (int j = 0; j < 3; j++)
+  {
+    const double s = T[0] * B[0 + j] + T[1] * B[3 + j] + T[2] * B[6 + j];
+    const double t = fabs(s);
+    if (t > b[j] + a[0] * Bf[0 + j] + a[1] * Bf[3 + j] + a[2] * Bf[6 + j]) return 4 + j;
+  }
+  int code = 7;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++, code++)
+    {
+      const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      const double s = T[i2] * B[3 * i1 + j] - T[i1] * B[3 * i2 + j];
+      const double t = fabs(s);
+      const double ra = a[i1] * Bf[3 * i2 + j] + a[i2] * Bf[3 * i1 + j];
+      const double rb = b[j1] * Bf[3 * i + j2] + b[j2] * Bf[3 * i + j1];
+      if (t > ra + rb) return code;
+    }
+  return 0;
+}
+
+namespace {
+inline void cross3(double r[3], const double a[3], const double b[3])
+{
+  r[0] = a[1] * b[2] - a[2] * b[1];
+  r[1] = a[2] * b[0] - a[0] * b[2];
+  r[2] = a[0] * b[1] - a[1] * b[0];
+}
+inline bool axis_separates(const double ax[3], const double p[3][3], const double q[3][3])
+{
+  double pmin = v_dot(ax, p[0]), pmax = pmin, qmin = v_dot(ax, q[0]), qmax = qmin;
+  for (int i = 1; i < 3; i++)
+  {
+    const double v = v_dot(ax, p[i]); if (v < pmin) pmin = v; if (v > pmax) pmax = v;
+    const double w = v_dot(ax, q[i]); if (w < qmin) qmin = w; if (w > qmax) qmax = w;
+  }
+  return (pmin > qmax) || (qmin > pmax);
+}
+}  // namespace
+
+// P: triangle 1 (p1,p2,p3), Q: triangle 2 already in triangle 1's frame
+extern "C" int32_t orc_tri_contact(const double P[9], const double Q[9])
+{
+  double p[3][3], q[3][3], e[3][3], f[3][3], n[3], m[3], ax[3];
+  for (int k = 0; k < 3; k++) { v_sub(p[k], &P[3 * k], &P[0]); v_sub(q[k], &Q[3 * k], &P[0]); }
+  v_sub(e[0], p[1], p[0]); v_sub(e[1], p[2], p[1]); v_sub(e[2], p[0], p[2]);
+  v_sub(f[0], q[1], q[0]); v_sub(f[1], q[2], q[1]); v_sub(f[2], q[0], q[2]);
+  cross3(n, e[0], e[1]);
+  cross3(m, f[0], f[1]);
+  if (axis_separates(n, p, q)) return 0;
+  if (axis_separates(m, p, q)) return 0;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+    {
+      cross3(ax, e[i], f[j]);
+      if (axis_separates(ax, p, q)) return 0;
+    }
+  for (int i = 0; i < 3; i++)
+  {
+    cross3(ax, e[i], n); if (axis_separates(ax, p, q)) return 0;
+    cross3(ax, f[i], m); if (axis_separates(ax, p, q)) return 0;
+  }
+  return 1;
+}
+
+namespace {
+struct CollideCtx
+{
+  const orc_bvh *A, *B;
+  const double *dA, *ToA, *dB, *ToB;  // OBB half-dimensions and centres, [n_nodes][3]
+  double Rrel[9], Trel[3];
+  int flag, max_pairs, num_pairs, num_bv_tests, num_tri_tests;
+  int32_t *pairs;
+};
+
+// CollideRecurse, C2A_PQP.cpp:798-909 (transforms chained through the box centres To, OBB_TYPE branch)
+void collide_recurse(CollideCtx &cx, const double R[9], const double T[3], int b1, int b2)
+{
+  const orc_bvh *A = cx.A, *B = cx.B;
+  cx.num_bv_tests++;
+  if (orc_obb_disjoint(R, T, &cx.dA[3 * b1], &cx.dB[3 * b2]) != 0) return;
+  const int l1 = A->first_child[b1] < 0, l2 = B->first_child[b2] < 0;
+  if (l1 && l2)
+  {
+    cx.num_tri_tests++;
+    const int ta = -A->first_child[b1] - 1, tb = -B->first_child[b2] - 1;
+    double Q[9];
+    for (int k = 0; k < 3; k++) m_v_p(&Q[3 * k], cx.Rrel, &B->tris[9 * tb + 3 * k], cx.Trel);
+    if (orc_tri_contact(&A->tris[9 * ta], Q))
+    {
+      if (cx.num_pairs < cx.max_pairs) { cx.pairs[2 * cx.num_pairs] = ta; cx.pairs[2 * cx.num_pairs + 1] = tb; }
+      cx.num_pairs++;
+    }
+    return;
+  }
+  const double sz1 = bv_size(A, b1), sz2 = bv_size(B, b2);
+  double Rc[9], Tc[3], Tt[3];
+  if (l2 || (!l1 && (sz1 > sz2)))
+  {
+    const int c1 = A->first_child[b1], c2 = c1 + 1;
+    mt_m(Rc, &A->R[9 * c1], R); v_sub(Tt, T, &cx.ToA[3 * c1]); mt_v(Tc, &A->R[9 * c1], Tt);
+    collide_recurse(cx, Rc, Tc, c1, b2);
+    if (cx.flag == 2 && cx.num_pairs > 0) return;
+    mt_m(Rc, &A->R[9 * c2], R); v_sub(Tt, T, &cx.ToA[3 * c2]); mt_v(Tc, &A->R[9 * c2], Tt);
+    collide_recurse(cx, Rc, Tc, c2, b2);
+  }
+  else
+  {
+    const int c1 = B->first_child[b2], c2 = c1 + 1;
+    m_m(Rc, R, &B->R[9 * c1]); m_v_p(Tc, R, &cx.ToB[3 * c1], T);
+    collide_recurse(cx, Rc, Tc, b1, c1);
+    if (cx.flag == 2 && cx.num_pairs > 0) return;
+    m_m(Rc, R, &B->R[9 * c2]); m_v_p(Tc, R, &cx.ToB[3 * c2], T);
+    collide_recurse(cx, Rc, Tc, b1, c2);
+  }
+}
+}  // namespace
+
+// C2A_Collide(PQP_CollideResult*, ..., flag), C2A_PQP.cpp:910-968.  flag 1: all contacts, 2: first contact.  pairs: builder-order
+// triangle indices (the reference reports Tri::id) of the first min(num_pairs, max_pairs) pairs in traversal order.
+extern "C" int32_t orc_collide(const orc_bvh *A, const orc_bvh *B, const double *dA, const double *ToA, const double *dB,
+                               const double *ToB, const double pose24[24], int32_t flag, int32_t max_pairs, int32_t *pairs,
+                               int32_t *num_bv_tests, int32_t *num_tri_tests)
+{
+  CollideCtx cx;
+  cx.A = A; cx.B = B; cx.dA = dA; cx.ToA = ToA; cx.dB = dB; cx.ToB = ToB;
+  cx.flag = flag; cx.max_pairs = max_pairs; cx.pairs = pairs; cx.num_pairs = cx.num_bv_tests = cx.num_tri_tests = 0;
+  const double *R1 = &pose24[0], *T1 = &pose24[9], *R2 = &pose24[12], *T2 = &pose24[21];
+  double Tt[3], Rt[9], R[9], T[3];
+  mt_m(cx.Rrel, R1, R2);
+  v_sub(Tt, T2, T1);
+  mt_v(cx.Trel, R1, Tt);
+  m_m(Rt, cx.Rrel, &B->R[0]);
+  mt_m(R, &A->R[0], Rt);
+  m_v_p(Tt, cx.Rrel, &ToB[0], cx.Trel);
+  v_sub(Tt, Tt, &ToA[0]);
+  mt_v(T, &A->R[0], Tt);
+  collide_recurse(cx, R, T, 0, 0);
+  if (num_bv_tests) *num_bv_tests = cx.num_bv_tests;
+  if (num_tri_tests) *num_tri_tests = cx.num_tri_tests;
+  return cx.num_pairs;
+}
+
+namespace {
+struct CollideDistCtx { DistCtx base; const double *dA, *dB; };
+
+// C2ACollideRecurse, C2A_PQP.cpp:1060-1196: C2ADistanceRecurse behind a box-overlap gate.  The gate is handed the
+// transform chained through the RSS corners Tr (the RSS_TYPE branch comes first in the source), as the reference does.
+void collide_distance_recurse(CollideDistCtx &cx, const double R[9], const double T[3], int b1, int b2)
+{
+  const orc_bvh *A = cx.base.A, *B = cx.base.B;
+  const double sz1 = bv_size(A, b1), sz2 = bv_size(B, b2);
+  if (orc_obb_disjoint(R, T, &cx.dA[3 * b1], &cx.dB[3 * b2]) != 0) return;
+  const int l1 = A->first_child[b1] < 0, l2 = B->first_child[b2] < 0;
+  orc_distance_result *res = cx.base.res;
+  if (l1 && l2)
+  {
+    res->num_tri_tests++;
+    double p[3], q[3];
+    const int ta = -A->first_child[b1] - 1, tb = -B->first_child[b2] - 1;
+    const double d = orc_tri_distance(cx.base.Rrel, cx.base.Trel, &A->tris[9 * ta], &B->tris[9 * tb], p, q);
+    if (d < res->distance)
+    {
+      res->distance = d;
+      res->tri_a = ta; res->tri_b = tb;
+      v_cpy(res->p1, p); v_cpy(res->p2, q);
+    }
+    return;
+  }
+  int a1, a2, c1, c2;
+  double R1[9], T1[3], R2[9], T2[3], Tt[3];
+  if (l2 || (!l1 && (sz1 > sz2)))
+  {
+    a1 = A->first_child[b1]; a2 = b2; c1 = a1 + 1; c2 = b2;
+    mt_m(R1, &A->R[9 * a1], R); v_sub(Tt, T, &A->Tr[3 * a1]); mt_v(T1, &A->R[9 * a1], Tt);
+    mt_m(R2, &A->R[9 * c1], R); v_sub(Tt, T, &A->Tr[3 * c1]); mt_v(T2, &A->R[9 * c1], Tt);
+  }
+  else
+  {
+    a1 = b1; a2 = B->first_child[b2]; c1 = b1; c2 = a2 + 1;
+    m_m(R1, R, &B->R[9 * a2]); m_v_p(T1, R, &B->Tr[3 * a2], T);
+    m_m(R2, R, &B->R[9 * c2]); m_v_p(T2, R, &B->Tr[3 * c2], T);
+  }
+  res->num_bv_tests += 2;
+  double S[3];
+  const double d1 = bv_distance(R1, T1, A, a1, B, a2, S);
+  const double d2 = bv_distance(R2, T2, A, c1, B, c2, S);
+#define CLOSER(d) (((d) < (res->distance - cx.base.abs_err)) || ((d) * (1 + cx.base.rel_err) < res->distance))
+  if (d2 < d1)
+  {
+    if (CLOSER(d2)) collide_distance_recurse(cx, R2, T2, c1, c2);
+    if (CLOSER(d1)) collide_distance_recurse(cx, R1, T1, a1, a2);
+  }
+  else
+  {
+    if (CLOSER(d1)) collide_distance_recurse(cx, R1, T1, a1, a2);
+    if (CLOSER(d2)) collide_distance_recurse(cx, R2, T2, c1, c2);
+  }
+#undef CLOSER
+}
+}  // namespace
+
+// C2A_Collide(C2A_DistanceResult*, ..., rel_err, abs_err), C2A_PQP.cpp:1199-1280
+extern "C" void orc_collide_distance(const orc_bvh *A, const orc_bvh *B, const double *dA, const double *dB, const double pose24[24],
+                                     int32_t seedA, int32_t seedB, double rel_err, double abs_err, orc_distance_result *res)
+{
+  CollideDistCtx cx;
+  cx.base.A = A; cx.base.B = B; cx.base.rel_err = rel_err; cx.base.abs_err = abs_err; cx.base.res = res; cx.dA = dA; cx.dB = dB;
+  const double *R1 = &pose24[0], *T1 = &pose24[9], *R2 = &pose24[12], *T2 = &pose24[21];
+  double Tt[3], Rt[9], R[9], T[3], p[3], q[3];
+  mt_m(cx.base.Rrel, R1, R2);
+  v_sub(Tt, T2, T1);
+  mt_v(cx.base.Trel, R1, Tt);
+  res->distance = orc_tri_distance(cx.base.Rrel, cx.base.Trel, &A->tris[9 * seedA], &B->tris[9 * seedB], p, q);
+  res->tri_a = seedA; res->tri_b = seedB;
+  v_cpy(res->p1, p); v_cpy(res->p2, q);
+  res->num_bv_tests = 0; res->num_tri_tests = 0;
+  m_m(Rt, cx.base.Rrel, &B->R[0]);
+  mt_m(R, &A->R[0], Rt);
+  m_v_p(Tt, cx.base.Rrel, &B->Tr[0], cx.base.Trel);
+  v_sub(Tt, Tt, &A->Tr[0]);
+  mt_v(T, &A->R[0], Tt);
+  collide_distance_recurse(cx, R, T, 0, 0);
+  double u[3];
+  v_sub(u, res->p2, cx.base.Trel);
+  mt_v(res->p2, cx.base.Rrel, u);
+}
+
 // Design study entry: orc_solve with every exact-mode CA step run through the speculative subtree split at
 // frontier depth K; results must equal orc_solve's bit for bit (tests/test_oracle.py), stats accumulate.
 extern "C" void orc_solve_spec(const orc_bvh *A, const orc_bvh *B, const double poses[48], int32_t seedA, int32_t seedB,

@@ -126,6 +126,17 @@ typedef struct orc_distance_result
 void orc_distance(const orc_bvh *A, const orc_bvh *B, const double pose24[24], int32_t seedA, int32_t seedB,
                   double rel_err, double abs_err, orc_distance_result *res);
 
+/* C2A_Collide, both overloads (C2A/src/C2A_PQP.cpp:910-968, 1199-1280).  dA/ToA/dB/ToB: [n_nodes][3] OBB half-dimensions
+ * and centres (BV::d, BV::To).  orc_obb_disjoint / orc_tri_contact restate PQP's un-vendored obb_disjoint / TriContact in
+ * the arithmetic of oracle/pqp_shim (what the compiled reference links). */
+int32_t orc_obb_disjoint(const double B[9], const double T[3], const double a[3], const double b[3]);
+int32_t orc_tri_contact(const double P[9], const double Q[9]);
+int32_t orc_collide(const orc_bvh *A, const orc_bvh *B, const double *dA, const double *ToA, const double *dB,
+                    const double *ToB, const double pose24[24], int32_t flag, int32_t max_pairs, int32_t *pairs,
+                    int32_t *num_bv_tests, int32_t *num_tri_tests);
+void orc_collide_distance(const orc_bvh *A, const orc_bvh *B, const double *dA, const double *dB, const double pose24[24],
+                          int32_t seedA, int32_t seedB, double rel_err, double abs_err, orc_distance_result *res);
+
 /* Round-2 design study (test infrastructure): a CA step split into subtrees run under a guessed entry distance with a
  * recorded validity interval, stitched back in the reference's order.  Work is counted in node-pair visits. */
 typedef struct orc_spec_stats

@@ -318,6 +318,53 @@ void ref_distance(void *hA, void *hB, const double *pose24, int32_t seedA, int32
   out->num_bv_tests = res.num_bv_tests; out->num_tri_tests = res.num_tri_tests;
 }
 
+// OBB fields of the built model (BV::d, BV::To after make_parent_relative), read by C2A_Collide only.
+void ref_model_export_obb(void *h, double *d, double *To)
+{
+  C2A_Model *m = (C2A_Model *)h;
+  for (int n = 0; n < m->num_bvs; n++)
+  {
+    BV *b = m->child(n);
+    for (int i = 0; i < 3; i++) { d[3 * n + i] = b->d[i]; To[3 * n + i] = b->To[i]; }
+  }
+}
+
+// The reference's C2A_Collide(PQP_CollideResult*, ...) (C2A/src/C2A_PQP.cpp:910-968) for one query.  pairs: the first
+// min(num_pairs, max_pairs) (Id1, Id2) = AddTri ids, in the order the traversal reported them.  Returns num_pairs.
+int32_t ref_collide(void *hA, void *hB, const double *pose24, int32_t flag, int32_t max_pairs, int32_t *pairs,
+                    int32_t *num_bv_tests, int32_t *num_tri_tests)
+{
+  C2A_Model *A = (C2A_Model *)hA, *B = (C2A_Model *)hB;
+  PQP_REAL R1[3][3], T1[3], R2[3][3], T2[3];
+  pose_to_RT(pose24, R1, T1); pose_to_RT(pose24 + 12, R2, T2);
+  PQP_CollideResult res;
+  C2A_Collide(&res, R1, T1, A, R2, T2, B, flag);
+  const int n = res.NumPairs();
+  for (int k = 0; k < n && k < max_pairs; k++) { pairs[2 * k] = res.Id1(k); pairs[2 * k + 1] = res.Id2(k); }
+  if (num_bv_tests) *num_bv_tests = res.NumBVTests();
+  if (num_tri_tests) *num_tri_tests = res.NumTriTests();
+  return n;
+}
+
+// The reference's C2A_Collide(C2A_DistanceResult*, ...) (C2A/src/C2A_PQP.cpp:1199-1280): the distance walk restricted to
+// node pairs whose boxes overlap.  Seeds and closest pair as in ref_distance.
+void ref_collide_distance(void *hA, void *hB, const double *pose24, int32_t seedA, int32_t seedB, double rel_err,
+                          double abs_err, orc_distance_result *out)
+{
+  C2A_Model *A = (C2A_Model *)hA, *B = (C2A_Model *)hB;
+  PQP_REAL R1[3][3], T1[3], R2[3][3], T2[3];
+  pose_to_RT(pose24, R1, T1); pose_to_RT(pose24 + 12, R2, T2);
+  A->last_tri = A->GetTriangle(seedA);
+  B->last_tri = B->GetTriangle(seedB);
+  C2A_DistanceResult res;
+  C2A_Collide(&res, R1, T1, A, R2, T2, B, rel_err, abs_err, 2);
+  out->distance = res.distance;
+  for (int k = 0; k < 3; k++) { out->p1[k] = res.p1[k]; out->p2[k] = res.p2[k]; }
+  out->tri_a = (int)((C2A_Tri *)A->last_tri - (C2A_Tri *)A->tris);
+  out->tri_b = (int)((C2A_Tri *)B->last_tri - (C2A_Tri *)B->tris);
+  out->num_bv_tests = res.num_bv_tests; out->num_tri_tests = res.num_tri_tests;
+}
+
 // ---- unit-level entry points for pinning the port / the device functions ----
 double ref_rect_dist(const double Rab[9], const double Tab[3], const double a[2], const double b[2], double P[3],
                      double Q[3], double S[3])

@@ -123,6 +123,46 @@ def distance_fixture(R):
     np.savez_compressed(os.path.join(HERE, "ref_distance_knot_128x16.npz"), **out)
 
 
+def collide_fixture(R):
+    """The reference's C2A_Collide, both overloads (C2A_PQP.cpp:798-968, 1060-1280), on static pose pairs: a knot against
+    itself and the bunny against a larger knot.  Pairs are the reference's Tri::id values in its reporting order."""
+    m = np.load(os.path.join(HERE, "bunny_mesh.npz"))
+    bunny_tris = m["verts"][m["vidx"]].reshape(-1, 9).copy()
+    cases = (("knot_128x16", meshes.torus_knot(128, 16)[0], meshes.torus_knot(128, 16)[0], 400, workloads.KNOT_RADIUS),
+             ("bunny_vs_knot_512x32", bunny_tris, meshes.torus_knot(512, 32)[0], 150, workloads.BUNNY_RADIUS))
+    for tag, ta, tb, n, radius in cases:
+        a, b = R.model(ta), R.model(tb)  # two objects: the distance overload reads and writes each model's last_tri
+        poses24 = workloads.static_pose_batch(n, 20260031, radius=radius)
+        out = {"poses24": poses24}
+        for name, flag in (("all", 1), ("first", 2)):
+            num, pairs, nbv, ntri = R.collide(a, b, poses24, flag=flag, max_pairs=1 << 16)
+            assert num.max() < (1 << 16)
+            out[f"{name}_num_pairs"] = num; out[f"{name}_num_bv_tests"] = nbv; out[f"{name}_num_tri_tests"] = ntri
+            out[f"{name}_pairs"] = np.concatenate(pairs).astype(np.int32).reshape(-1, 2)
+            print(f"ref_collide_{tag} {name}: colliding {int((num > 0).sum())}/{n}, pairs {int(num.sum())} (max {int(num.max())}), mean nbv {nbv.mean():.0f}")
+        rng = np.random.default_rng(11)
+        sa = rng.integers(0, a.n_tris, n).astype(np.int32); sb = rng.integers(0, b.n_tris, n).astype(np.int32)
+        out["seed_a"] = sa; out["seed_b"] = sb
+        for name, rel, ab in (("exact", 0.0, 0.0), ("approx", 0.25, 2.0)):
+            r = R.collide_distance(a, b, poses24, sa, sb, rel, ab)
+            for k in r.dtype.names:
+                out[f"dist_{name}_{k}"] = r[k]
+            out[f"dist_{name}_err"] = np.array([rel, ab])
+            print(f"ref_collide_{tag} distance overload {name}: reached a leaf {int((r['num_tri_tests'] > 0).sum())}/{n}, touching {int((r['distance'] == 0).sum())}")
+        np.savez_compressed(os.path.join(HERE, f"ref_collide_{tag}.npz"), **out)
+
+
+def digest_only(R):
+    """bvh_digest.json alone (sha256 of every array the reference's builder made, OBB fields included)."""
+    m = np.load(os.path.join(HERE, "bunny_mesh.npz"))
+    digests = {"bunny": digest(R.model(m["verts"][m["vidx"]].reshape(-1, 9).copy(), m["vidx"]).export())}
+    for nu, nvv in ((128, 16), (512, 32), (1024, 32)):
+        tris, vi = meshes.torus_knot(nu, nvv)
+        digests[f"knot_{nu}x{nvv}"] = digest(R.model(tris, vi).export())
+    with open(os.path.join(HERE, "bvh_digest.json"), "w") as f:
+        json.dump(digests, f, indent=1, sort_keys=True)
+
+
 def save_compact(name, res, gen, poses, tol_d, tol_t, extra=None):
     """Large fixtures keep the reference's outputs and a recipe for the poses (generator + seed, or a source fixture
     plus the doubles that differ) instead of the poses themselves; tests/conftest.py rebuilds them and checks the
@@ -180,6 +220,12 @@ def main():
         return
     if "--only-distance" in sys.argv:
         distance_fixture(R)
+        return
+    if "--only-collide" in sys.argv:
+        collide_fixture(R)
+        return
+    if "--only-digest" in sys.argv:
+        digest_only(R)
         return
     if "--only-translation" in sys.argv:
         m = np.load(os.path.join(HERE, "bunny_mesh.npz"))
@@ -272,6 +318,7 @@ def main():
 
     translation_fixtures(R, bunny)
     distance_fixture(R)
+    collide_fixture(R)
     bunny_grazing_fixture(R, bunny)
 
     with open(os.path.join(HERE, "bvh_digest.json"), "w") as f:

@@ -13,7 +13,7 @@ import pytest
 import oracle
 from c2a_b200 import api, meshes, workloads
 from conftest import GOLDEN_CASES
-from test_oracle import rect_cases, tri_cases, TRANSLATION_CASES
+from test_oracle import rect_cases, tri_cases, TRANSLATION_CASES, COLLIDE_CASES, split_pairs
 
 pytestmark = pytest.mark.gpu
 
@@ -403,6 +403,68 @@ def test_deep_hierarchies_run_on_global_memory_stacks():
         assert num[i] == n_ref, i
         k = min(n_ref, 64)
         assert np.array_equal(recs[i][:k]["tri_a"], r_ref["tri_a"][:k]) and np.array_equal(recs[i][:k]["dist"], r_ref["dist"][:k]), i
+
+
+    # C2A_Collide, both overloads, on the same chain-shaped hierarchy
+    rn, rp, rbv, rtr = P.collide(bvh, bvh, sp, max_pairs=64)
+    gc = api.collide_batch(m, m, sp, max_pairs=64)
+    assert np.array_equal(gc["num_pairs"], rn) and np.array_equal(gc["num_bv_tests"], rbv) and np.array_equal(gc["num_tri_tests"], rtr)
+    for i in range(len(sp)):
+        assert np.array_equal(gc["pairs"][i, :min(rn[i], 64)], rp[i]), i
+    rd = P.collide_distance(bvh, bvh, sp)
+    gd = api.collide_distance_batch(m, m, sp)
+    assert np.array_equal(gd["distance"], rd["distance"]) and np.array_equal(gd["num_bv_tests"], rd["num_bv_tests"])
+
+
+@pytest.mark.parametrize("case,ma,mb", COLLIDE_CASES)
+def test_collide_bit_exact(case, ma, mb, golden, models, bvhs):
+    """Batched C2A_Collide, PQP_CollideResult overload (c2a_collide_kernel): pair lists in the reference's reporting order,
+    counters, both flags, against the reference's object code; truncated and count-only output."""
+    g = golden(f"ref_collide_{case}")
+    a, b = models(ma), models(mb)
+    ia, ib = bvhs(ma)["tri_ids"], bvhs(mb)["tri_ids"]
+    cap = int(g["all_num_pairs"].max())
+    for name, flag in (("all", api.ALL_CONTACTS), ("first", api.FIRST_CONTACT)):
+        got = api.collide_batch(a, b, g["poses24"], flag=flag, max_pairs=cap)
+        assert np.array_equal(got["num_pairs"], g[f"{name}_num_pairs"])
+        assert np.array_equal(got["num_bv_tests"], g[f"{name}_num_bv_tests"]) and np.array_equal(got["num_tri_tests"], g[f"{name}_num_tri_tests"])
+        for i, want in enumerate(split_pairs(g[f"{name}_num_pairs"], g[f"{name}_pairs"])):
+            k = len(want)
+            assert np.array_equal(np.stack([ia[got["pairs"][i, :k, 0]], ib[got["pairs"][i, :k, 1]]], 1), want), (name, i)
+            assert (got["pairs"][i, k:] == -1).all()
+    few = api.collide_batch(a, b, g["poses24"], max_pairs=3)      # more pairs than room: all counted, the first three kept
+    full = api.collide_batch(a, b, g["poses24"], max_pairs=cap)
+    assert np.array_equal(few["num_pairs"], g["all_num_pairs"]) and np.array_equal(few["pairs"], full["pairs"][:, :3])
+    none = api.collide_batch(a, b, g["poses24"], max_pairs=0)
+    assert np.array_equal(none["num_pairs"], g["all_num_pairs"])
+    assert api.collide_batch(a, b, np.zeros((0, 24)))["num_pairs"].shape == (0,)
+    with pytest.raises(api.C2AError):
+        api.collide_batch(a, b, g["poses24"], flag=3)
+
+
+@pytest.mark.parametrize("case,ma,mb", COLLIDE_CASES)
+@pytest.mark.parametrize("tag", ["exact", "approx"])
+def test_collide_distance_overload_bit_exact(case, ma, mb, tag, golden, models):
+    """C2A_Collide, C2A_DistanceResult overload: c2a_distance_kernel behind the box-overlap gate."""
+    g = golden(f"ref_collide_{case}")
+    rel, ab = g[f"dist_{tag}_err"]
+    got = api.collide_distance_batch(models(ma), models(mb), g["poses24"], g["seed_a"], g["seed_b"], rel, ab)
+    assert np.array_equal(got["distance"], g[f"dist_{tag}_distance"])
+    assert np.array_equal(got["p1p2"], np.concatenate([g[f"dist_{tag}_p1"], g[f"dist_{tag}_p2"]], 1))
+    assert np.array_equal(got["tri_pair"], np.stack([g[f"dist_{tag}_tri_a"], g[f"dist_{tag}_tri_b"]], 1))
+    assert np.array_equal(got["num_bv_tests"], g[f"dist_{tag}_num_bv_tests"]) and np.array_equal(got["num_tri_tests"], g[f"dist_{tag}_num_tri_tests"])
+
+
+def test_collide_needs_box_data(bvhs):
+    """A model uploaded without obb_d / obb_To serves every other query; the C2A_Collide entries refuse it."""
+    b = {k: v for k, v in bvhs("knot_128x16").items() if not k.startswith("obb_")}
+    m = api.Model(b, 0)
+    sp = workloads.static_pose_batch(8, 5, radius=workloads.KNOT_RADIUS)
+    assert api.distance_batch(m, m, sp)["distance"].shape == (8,)
+    with pytest.raises(api.C2AError):
+        api.collide_batch(m, m, sp)
+    with pytest.raises(api.C2AError):
+        api.collide_distance_batch(m, m, sp)
 
 
 def test_multi_device_entry_matches_single_device(models, bvhs, golden):

@@ -187,6 +187,67 @@ def test_port_distance_matches_golden(tag, golden, bvhs):
         assert (g["approx_distance"] >= g["exact_distance"]).all()
 
 
+COLLIDE_CASES = [("knot_128x16", "knot_128x16", "knot_128x16"), ("bunny_vs_knot_512x32", "bunny", "knot_512x32")]
+
+
+def split_pairs(num, flat):
+    """Per-query pair lists from the fixture's concatenated [sum(num), 2] array."""
+    ends = np.cumsum(num)
+    return [flat[e - k:e] for k, e in zip(num, ends)]
+
+
+@pytest.mark.parametrize("case,ma,mb", COLLIDE_CASES)
+def test_port_collide_matches_golden(case, ma, mb, golden, bvhs):
+    """C2A_Collide, PQP_CollideResult overload (C2A_PQP.cpp:798-968), both flags: the port against the reference's object
+    code (pairs as Tri::id in the reference's reporting order)."""
+    g = golden(f"ref_collide_{case}")
+    a, b = bvhs(ma), bvhs(mb)
+    for name, flag in (("all", 1), ("first", 2)):
+        num, pairs, nbv, ntri = oracle.port().collide(a, b, g["poses24"], flag=flag, max_pairs=4096)
+        assert np.array_equal(num, g[f"{name}_num_pairs"]) and np.array_equal(nbv, g[f"{name}_num_bv_tests"])
+        assert np.array_equal(ntri, g[f"{name}_num_tri_tests"])
+        for got, want in zip(pairs, split_pairs(g[f"{name}_num_pairs"], g[f"{name}_pairs"])):
+            assert np.array_equal(np.stack([a["tri_ids"][got[:, 0]], b["tri_ids"][got[:, 1]]], 1), want)
+    assert (g["all_num_pairs"] > 0).sum() > 50 and (g["all_num_pairs"] == 0).sum() > 50 and g["first_num_pairs"].max() == 1
+    assert g["first_num_bv_tests"].sum() < g["all_num_bv_tests"].sum()
+
+
+@pytest.mark.parametrize("case,ma,mb", COLLIDE_CASES)
+@pytest.mark.parametrize("tag", ["exact", "approx"])
+def test_port_collide_distance_matches_golden(case, ma, mb, tag, golden, bvhs):
+    """C2A_Collide, C2A_DistanceResult overload (C2A_PQP.cpp:1060-1280): the distance walk behind the box-overlap gate."""
+    g = golden(f"ref_collide_{case}")
+    rel, ab = g[f"dist_{tag}_err"]
+    out = oracle.port().collide_distance(bvhs(ma), bvhs(mb), g["poses24"], g["seed_a"], g["seed_b"], rel, ab)
+    for k in out.dtype.names:
+        assert np.array_equal(out[k], g[f"dist_{tag}_{k}"]), (case, tag, k)
+    assert 20 < (g[f"dist_{tag}_num_tri_tests"] > 0).sum() < len(out)   # gate open for some queries, shut at the root for others
+
+
+def test_port_box_and_triangle_overlap_vs_shim():
+    """The port's obb_disjoint / TriContact against the stand-ins the compiled reference links (oracle/pqp_shim), through
+    the reference's own C2A_Collide on two-triangle models: every random placement gives the same verdict and counters."""
+    if not oracle.have_ref():
+        pytest.skip("needs oracle/_ref (built where /root/reference exists)")
+    from c2a_b200 import api
+    rng = np.random.default_rng(3)
+    R, P = oracle.ref(), oracle.port()
+    for trial in range(40):
+        ta = rng.normal(size=(2, 9)); tb = rng.normal(size=(2, 9))
+        ba, bb = api.build_bvh(ta), api.build_bvh(tb)
+        ra, rb = R.model(ta), R.model(tb)
+        q = rng.normal(size=(8, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+        poses = np.zeros((8, 24)); poses[:, 0:9] = np.eye(3).reshape(9)
+        w, x, y, z = q.T
+        poses[:, 12:21] = np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w), 2 * (x * y + z * w), 1 - 2 * (x * x + z * z),
+                                    2 * (y * z - x * w), 2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], 1)
+        poses[:, 21:24] = rng.normal(scale=0.7, size=(8, 3))
+        n0, p0, v0, t0 = R.collide(ra, rb, poses); n1, p1, v1, t1 = P.collide(ba, bb, poses)
+        assert np.array_equal(n0, n1) and np.array_equal(v0, v1) and np.array_equal(t0, t1)
+        for u, w_ in zip(p0, p1):
+            assert np.array_equal(u, np.stack([ba["tri_ids"][w_[:, 0]], bb["tri_ids"][w_[:, 1]]], 1))
+
+
 def test_speculative_step_split_is_exact(golden, bvhs):
     """Round-2 design study (oracle/c2a_oracle.cpp, orc_solve_spec): CA steps split into subtrees run under a guessed entry
     distance + validity interval and stitched in the reference's order reproduce the sequential result bit for bit."""
