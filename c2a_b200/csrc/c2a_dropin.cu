@@ -389,8 +389,9 @@ PQP_REAL C2A_QueryTimeOfContact(CInterpMotion *objmotion1, CInterpMotion *objmot
 }
 
 // C2A/src/C2A_PQP.cpp:970-1056
-int C2A_Distance(C2A_DistanceResult *res, PQP_REAL R1[3][3], PQP_REAL T1[3], C2A_Model *o1, PQP_REAL R2[3][3],
-                 PQP_REAL T2[3], C2A_Model *o2, PQP_REAL rel_err, PQP_REAL abs_err, int qsize)
+// C2A_Distance and C2A_Collide's C2A_DistanceResult overload: the same call but for the entry point
+static int distance_like(bool gate, C2A_DistanceResult *res, PQP_REAL R1[3][3], PQP_REAL T1[3], C2A_Model *o1, PQP_REAL R2[3][3],
+                         PQP_REAL T2[3], C2A_Model *o2, PQP_REAL rel_err, PQP_REAL abs_err, int qsize)
 {
   if (!o1 || !o2 || !o1->gpu || !o2->gpu) return PQP_ERR_UNPROCESSED_MODEL;
   const auto t_begin = std::chrono::steady_clock::now();
@@ -402,7 +403,8 @@ int C2A_Distance(C2A_DistanceResult *res, PQP_REAL R1[3][3], PQP_REAL T1[3], C2A
   }
   int32_t sa = seed_index(o1, o1->last_tri), sb = seed_index(o2, o2->last_tri), pair[2] = {0, 0}, nbv = 0, ntri = 0;
   double dist = 0, p1p2[6];
-  const int rc = c2a_b200_distance_batch(o1->gpu, o2->gpu, pose, &sa, &sb, 1, rel_err, abs_err, &dist, p1p2, pair, &nbv, &ntri);
+  const int rc = (gate ? c2a_b200_collide_distance_batch : c2a_b200_distance_batch)(o1->gpu, o2->gpu, pose, &sa, &sb, 1, rel_err,
+                                                                                    abs_err, &dist, p1p2, pair, &nbv, &ntri);
   if (rc) { fprintf(stderr, "c2a_b200: %s\n", c2a_b200_last_error()); return rc; }
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) res->R[i][j] = (R1[0][i] * R2[0][j] + R1[1][i] * R2[1][j] + R1[2][i] * R2[2][j]);
@@ -416,6 +418,72 @@ int C2A_Distance(C2A_DistanceResult *res, PQP_REAL R1[3][3], PQP_REAL T1[3], C2A
   o1->last_tri = &o1->tris[pair[0]];
   o2->last_tri = &o2->tris[pair[1]];
   res->t1 = o1->tris[pair[0]].id; res->t2 = o2->tris[pair[1]].id;
+  res->query_time_secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+  return PQP_OK;
+}
+
+int C2A_Distance(C2A_DistanceResult *res, PQP_REAL R1[3][3], PQP_REAL T1[3], C2A_Model *o1, PQP_REAL R2[3][3],
+                 PQP_REAL T2[3], C2A_Model *o2, PQP_REAL rel_err, PQP_REAL abs_err, int qsize)
+{
+  return distance_like(false, res, R1, T1, o1, R2, T2, o2, rel_err, abs_err, qsize);
+}
+
+// C2A/src/C2A_PQP.cpp:1199-1280
+int C2A_Collide(C2A_DistanceResult *res, PQP_REAL R1[3][3], PQP_REAL T1[3], C2A_Model *o1, PQP_REAL R2[3][3],
+                PQP_REAL T2[3], C2A_Model *o2, PQP_REAL rel_err, PQP_REAL abs_err, int qsize)
+{
+  return distance_like(true, res, R1, T1, o1, R2, T2, o2, rel_err, abs_err, qsize);
+}
+
+void PQP_CollideResult::SizeTo(int n)
+{
+  if (n < num_pairs) return;
+  CollisionPair *t = new CollisionPair[n];
+  for (int i = 0; i < num_pairs; i++) t[i] = pairs[i];
+  delete[] pairs;
+  pairs = t;
+  num_pairs_alloced = n;
+}
+
+void PQP_CollideResult::Add(int a, int b)
+{
+  if (num_pairs >= num_pairs_alloced) SizeTo(num_pairs_alloced * 2 + 8);
+  pairs[num_pairs].id1 = a; pairs[num_pairs].id2 = b;
+  num_pairs++;
+}
+
+// C2A/src/C2A_PQP.cpp:910-968.  The pair list is fetched with room for 256 pairs and once more with room for all of
+// them when there are more.
+int C2A_Collide(PQP_CollideResult *res, PQP_REAL R1[3][3], PQP_REAL T1[3], C2A_Model *o1, PQP_REAL R2[3][3], PQP_REAL T2[3],
+                C2A_Model *o2, int flag)
+{
+  if (!o1 || !o2 || !o1->gpu || !o2->gpu) return PQP_ERR_UNPROCESSED_MODEL;
+  const auto t_begin = std::chrono::steady_clock::now();
+  double pose[24];
+  for (int i = 0; i < 3; i++)
+  {
+    for (int j = 0; j < 3; j++) { pose[3 * i + j] = R1[i][j]; pose[12 + 3 * i + j] = R2[i][j]; }
+    pose[9 + i] = T1[i]; pose[21 + i] = T2[i];
+  }
+  int32_t cap = 256, n = 0, nbv = 0, ntri = 0;
+  std::vector<int32_t> buf((size_t)2 * cap);
+  int rc = c2a_b200_collide_batch(o1->gpu, o2->gpu, pose, 1, flag, cap, &n, buf.data(), &nbv, &ntri);
+  if (rc == 0 && n > cap)
+  {
+    cap = n;
+    buf.resize((size_t)2 * cap);
+    rc = c2a_b200_collide_batch(o1->gpu, o2->gpu, pose, 1, flag, cap, &n, buf.data(), &nbv, &ntri);
+  }
+  if (rc) { fprintf(stderr, "c2a_b200: %s\n", c2a_b200_last_error()); return rc; }
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) res->R[i][j] = (R1[0][i] * R2[0][j] + R1[1][i] * R2[1][j] + R1[2][i] * R2[2][j]);
+  {
+    const PQP_REAL Tt[3] = {T2[0] - T1[0], T2[1] - T1[1], T2[2] - T1[2]};
+    for (int i = 0; i < 3; i++) res->T[i] = (R1[0][i] * Tt[0] + R1[1][i] * Tt[1] + R1[2][i] * Tt[2]);
+  }
+  res->num_bv_tests = nbv; res->num_tri_tests = ntri;
+  res->num_pairs = 0;   // the reference keeps the allocation and resets the counter (:931)
+  for (int k = 0; k < n; k++) res->Add(o1->tris[buf[2 * k]].id, o2->tris[buf[2 * k + 1]].id);
   res->query_time_secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
   return PQP_OK;
 }

@@ -275,6 +275,44 @@ struct C2A_DistanceResult
 int C2A_Distance(C2A_DistanceResult *result, PQP_REAL R1[3][3], PQP_REAL T1[3], C2A_Model *o1, PQP_REAL R2[3][3],
                  PQP_REAL T2[3], C2A_Model *o2, PQP_REAL rel_err, PQP_REAL abs_err, int qsize = 2);
 
+// PQP's collision result (PQP.h; the reference takes it from the un-vendored PQP): the pairs of intersecting triangles
+struct CollisionPair { int id1, id2; };
+struct PQP_CollideResult
+{
+  int num_bv_tests, num_tri_tests;
+  double query_time_secs;
+  PQP_REAL R[3][3], T[3];   // model 2 -> model 1
+  int num_pairs_alloced, num_pairs;
+  CollisionPair *pairs;
+  PQP_CollideResult() : num_bv_tests(0), num_tri_tests(0), query_time_secs(0), num_pairs_alloced(0), num_pairs(0), pairs(0) {}
+  ~PQP_CollideResult() { FreePairsList(); }
+  PQP_CollideResult(const PQP_CollideResult &) = delete;
+  PQP_CollideResult &operator=(const PQP_CollideResult &) = delete;
+  void SizeTo(int n);
+  void Add(int i1, int i2);
+  void FreePairsList() { delete[] pairs; pairs = 0; num_pairs = num_pairs_alloced = 0; }
+  int NumBVTests() { return num_bv_tests; }
+  int NumTriTests() { return num_tri_tests; }
+  double QueryTimeSecs() { return query_time_secs; }
+  int Colliding() { return num_pairs > 0; }
+  int NumPairs() { return num_pairs; }
+  int Id1(int k) { return pairs[k].id1; }
+  int Id2(int k) { return pairs[k].id2; }
+};
+
+const int C2A_ALL_CONTACTS = 1;   // find all pairwise intersecting triangles (C2A/C2A.h:246)
+const int C2A_FIRST_CONTACT = 2;  // report the first intersecting pair found (:247)
+
+// C2A/C2A.h:249-253, C2A/src/C2A_PQP.cpp:798-968: the intersecting triangle pairs (Tri::id) in the order the reference's
+// traversal reports them.  The box and triangle overlap tests are PQP's, restated.
+int C2A_Collide(PQP_CollideResult *result, PQP_REAL R1[3][3], PQP_REAL T1[3], C2A_Model *o1, PQP_REAL R2[3][3],
+                PQP_REAL T2[3], C2A_Model *o2, int flag = C2A_ALL_CONTACTS);
+
+// C2A/C2A.h:262-267, C2A/src/C2A_PQP.cpp:1060-1280: C2A_Distance's walk restricted to node pairs whose boxes overlap.
+// Reads and updates o1->last_tri / o2->last_tri like the reference.
+int C2A_Collide(C2A_DistanceResult *result, PQP_REAL R1[3][3], PQP_REAL T1[3], C2A_Model *o1, PQP_REAL R2[3][3],
+                PQP_REAL T2[3], C2A_Model *o2, PQP_REAL rel_err, PQP_REAL abs_err, int qsize = 2);
+
 C2A_Result C2A_Solve(Transform *trans00, Transform *trans01, C2A_Model *obj1_tested, Transform *trans10,
                      Transform *trans11, C2A_Model *obj2_tested, Transform &trans0, Transform &trans1,
                      PQP_REAL &time_of_contact, int &number_of_iteration, int &number_of_contact, PQP_REAL th_ca,

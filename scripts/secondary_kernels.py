@@ -30,3 +30,11 @@ thr = np.full(n, 2.0)
 api.contacts_batch(m, m, sp[:256], thr[:256], max_contacts=16)
 t = time.perf_counter(); num, recs = api.contacts_batch(m, m, sp, thr, max_contacts=16); dt = time.perf_counter() - t
 print(f"contact pass: {n} queries at threshold 2.0, call {dt * 1e3:.1f} ms = {n / dt:.0f} queries/s, mean contacts {num.mean():.2f}")
+t = time.perf_counter(); c = api.collide_batch(m, m, sp, max_pairs=64); dt = time.perf_counter() - t
+t = time.perf_counter(); rn, rp, rbv, rtr = oracle.port().collide(bvh, bvh, sp[:512], max_pairs=64); dc = time.perf_counter() - t
+print(f"C2A_Collide (all contacts): {n} queries, call {dt * 1e3:.1f} ms = {n / dt:.0f} queries/s, colliding {(c['num_pairs'] > 0).mean():.2f}, mean BV tests {c['num_bv_tests'].mean():.0f}, "
+      f"mean pairs {c['num_pairs'].mean():.0f}; port on one core {512 / dc:.0f} queries/s; bit-exact {np.array_equal(c['num_pairs'][:512], rn) and np.array_equal(c['num_bv_tests'][:512], rbv)}")
+t = time.perf_counter(); c1 = api.collide_batch(m, m, sp, flag=api.FIRST_CONTACT, max_pairs=1); dt = time.perf_counter() - t
+print(f"C2A_Collide (first contact): call {dt * 1e3:.1f} ms = {n / dt:.0f} queries/s, mean BV tests {c1['num_bv_tests'].mean():.0f}")
+t = time.perf_counter(); cd = api.collide_distance_batch(m, m, sp); dt = time.perf_counter() - t
+print(f"C2A_Collide (distance overload): call {dt * 1e3:.1f} ms = {n / dt:.0f} queries/s, mean BV tests {cd['num_bv_tests'].mean():.0f}")

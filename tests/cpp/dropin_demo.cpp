@@ -185,6 +185,26 @@ int main(int argc, char **argv)
            dr.P1()[2], dr.P2()[0], dr.P2()[1], dr.P2()[2]);
   }
 
+  // C2A_Collide, both overloads, at each frame's END poses (many interpenetrate): pair ids folded into a checksum
+  object1_tested->last_tri = object1_tested->tris; object2_tested->last_tri = object2_tested->tris;
+  {
+    PQP_CollideResult cr;   // reused across calls like the reference's callers do
+    for (int f = 0; f < nframes && f < 24; f++)
+    {
+      PQP_REAL R1[3][3], T1[3], R2[3][3], T2[3];
+      t01[f].Rotation().Get_Value(R1); t01[f].Translation().Get_Value(T1);
+      t11[f].Rotation().Get_Value(R2); t11[f].Translation().Get_Value(T2);
+      if (C2A_Collide(&cr, R1, T1, object1_tested, R2, T2, object2_tested, C2A_ALL_CONTACTS) != PQP_OK) return 11;
+      unsigned long long h = 1469598103934665603ull;
+      for (int k = 0; k < cr.NumPairs(); k++) { h = (h ^ (unsigned)cr.Id1(k)) * 1099511628211ull; h = (h ^ (unsigned)cr.Id2(k)) * 1099511628211ull; }
+      const int all = cr.NumPairs(), nbv = cr.NumBVTests(), ntri = cr.NumTriTests();
+      if (C2A_Collide(&cr, R1, T1, object1_tested, R2, T2, object2_tested, C2A_FIRST_CONTACT) != PQP_OK) return 11;
+      C2A_DistanceResult dr;
+      if (C2A_Collide(&dr, R1, T1, object1_tested, R2, T2, object2_tested, 0.0, 0.0) != PQP_OK) return 11;
+      printf("C %d %d %d %llu %d %d %a %d %d\n", all, nbv, ntri, h, cr.NumPairs(), cr.Colliding(), dr.Distance(), dr.t1, dr.t2);
+    }
+  }
+
   // pure translations through C2A_Solve (the reference's translation-only branch): optional 4th/5th arguments =
   // a pose file and a count; seeds are triangle 0 of each model, as the fixture was generated
   if (argc >= 6)

@@ -91,3 +91,22 @@ def test_cpp_dropin_matches_reference_fixture(tmp_path, golden):
         if ids is not None:
             assert int(r[2]) == ids[ref["tri_a"]] and int(r[3]) == ids[ref["tri_b"]]
         sa, sb = int(ref["tri_a"]), int(ref["tri_b"])
+    # C2A_Collide (both overloads) at the first 24 END poses: pair ids in the reference's order (checksum), counters, the
+    # first-contact flag, and the distance overload with last_tri carried from call to call
+    crows = [l.split() for l in out.stdout.splitlines() if l.startswith("C ")]
+    assert len(crows) == 24
+    sa = sb = 0
+    some = 0
+    for i, r in enumerate(crows):
+        pose = np.concatenate([g["poses"][i][12:24], g["poses"][i][36:48]])
+        num, pairs, nbv, ntri = oracle.port().collide(bvh, bvh, pose[None], max_pairs=1 << 15)
+        h = 1469598103934665603
+        for a, b in pairs[0]:
+            h = ((h ^ int(ids[a])) * 1099511628211) % (1 << 64); h = ((h ^ int(ids[b])) * 1099511628211) % (1 << 64)
+        assert [int(r[1]), int(r[2]), int(r[3]), int(r[4])] == [int(num[0]), int(nbv[0]), int(ntri[0]), h], i
+        assert int(r[5]) == min(1, int(num[0])) and int(r[6]) == min(1, int(num[0]))
+        rd = oracle.port().collide_distance(bvh, bvh, pose[None], [sa], [sb])[0]
+        assert float.fromhex(r[7]) == rd["distance"] and int(r[8]) == ids[rd["tri_a"]] and int(r[9]) == ids[rd["tri_b"]]
+        sa, sb = int(rd["tri_a"]), int(rd["tri_b"])
+        some += int(num[0] > 0)
+    assert 3 <= some <= 22
