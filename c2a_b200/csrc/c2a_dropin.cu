@@ -161,23 +161,26 @@ int C2A_Model::EndModel()
   std::vector<int32_t> vi((size_t)3 * num_tris);
   for (int i = 0; i < num_tris; i++)
     for (int k = 0; k < 3; k++) vi[3 * (size_t)i + k] = storage_[i].index_[k];
+  if (host_bvh) { c2a_b200_bvh_free(host_bvh); host_bvh = 0; }   // (left by an EndModel() that failed to upload)
   int rc = c2a_b200_bvh_build_indexed(t9.data(), vi.data(), num_tris, &host_bvh);
   if (rc) return PQP_ERR_MODEL_OUT_OF_MEMORY;
   c2a_b200_bvh view;
   const int32_t *ids = 0;
   c2a_b200_bvh_view(host_bvh, &view, &ids, 0);
+  rc = c2a_b200_model_upload(&view, device, &gpu);
+  if (rc)
+  {
+    // nothing of the model has changed yet: EndModel() can be called again (e.g. after freeing device memory)
+    fprintf(stderr, "c2a_b200: model upload failed: %s\n", c2a_b200_last_error());
+    c2a_b200_bvh_free(host_bvh); host_bvh = 0;
+    return PQP_ERR_MODEL_OUT_OF_MEMORY;
+  }
   // like the reference, the triangle array ends up in the builder's permuted order (Tri::id keeps the AddTri index)
   std::vector<C2A_Tri> perm(num_tris);
   for (int i = 0; i < num_tris; i++) perm[i] = storage_[ids[i]];
   storage_.swap(perm);
   tris = storage_.data();
   num_bvs = view.n_nodes;
-  rc = c2a_b200_model_upload(&view, device, &gpu);
-  if (rc)
-  {
-    fprintf(stderr, "c2a_b200: model upload failed: %s\n", c2a_b200_last_error());
-    return PQP_ERR_MODEL_OUT_OF_MEMORY;
-  }
   build_state = C2A_BUILD_STATE_PROCESSED;
   last_tri = tris;
   return PQP_OK;

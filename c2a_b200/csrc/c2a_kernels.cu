@@ -279,6 +279,7 @@ int c2a_b200_model_info(const c2a_b200_model *m, int32_t *device, int32_t *n_nod
   return C2A_B200_OK;
 }
 
+static int g_stats_device = -1, g_trace_device = -1, g_wide_stats_device = -1;  // the device each debug buffer lives on
 static unsigned long long *g_stats_dev = nullptr;  // phase statistics (c2a_b200_phase_stats), off by default
 static unsigned long long *g_trace_dev = nullptr;  // per-query claim / finish times (c2a_b200_query_trace), off by default
 static unsigned long long *g_wide_stats_dev = nullptr;  // counters of c2a_wide_kernel (c2a_b200_wide_stats), off by default
@@ -335,6 +336,40 @@ SideStream *side_stream(int device)  // the caller has made `device` current; nu
 }
 }  // namespace
 
+// The library's own stream-ordered memory pool, one per device: per-launch scratch (traversal stacks, hand-over lists,
+// staging arenas) is kept between launches without touching the release threshold of the device's DEFAULT pool, which
+// belongs to the caller.  Falls back to the default pool (threshold untouched) if a pool cannot be created.
+namespace {
+cudaMemPool_t device_pool(int device)
+{
+  static std::mutex m;
+  static std::vector<std::pair<int, cudaMemPool_t>> pools;
+  std::lock_guard<std::mutex> lk(m);
+  for (auto &p : pools) if (p.first == device) return p.second;
+  cudaMemPoolProps props;
+  memset(&props, 0, sizeof(props));
+  props.allocType = cudaMemAllocationTypePinned;
+  props.handleTypes = cudaMemHandleTypeNone;
+  props.location.type = cudaMemLocationTypeDevice;
+  props.location.id = device;
+  cudaMemPool_t pool = nullptr;
+  if (cudaMemPoolCreate(&pool, &props) == cudaSuccess)
+  {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  else { pool = nullptr; cudaGetLastError(); }
+  pools.push_back({device, pool});
+  return pool;
+}
+cudaError_t pool_malloc_(void **p, size_t bytes, int device, cudaStream_t stream)
+{
+  cudaMemPool_t pool = device_pool(device);
+  return pool ? cudaMallocFromPoolAsync(p, bytes, pool, stream) : cudaMallocAsync(p, bytes, stream);
+}
+#define pool_malloc(p, bytes, device, stream) pool_malloc_((void **)(p), (bytes), (device), (stream))
+}  // namespace
+
 // per-device scratch: the claim counter
 static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses, const int32_t *sa,
                         const int32_t *sb, int64_t n, double tol_d, double tol_t, const c2a_b200_results *out,
@@ -351,8 +386,7 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
 
   {
     // once per device (function attributes and memory pools are per device; the callers have made a->device current):
-    // opt in to the 106 KB of dynamic shared memory per block, and keep the per-launch scratch (traversal stacks,
-    // staging arena) in the stream-ordered pool between launches
+    // opt in to the 106 KB of dynamic shared memory per block
     static std::mutex m;
     static std::vector<int> done;
     std::lock_guard<std::mutex> lk(m);
@@ -362,12 +396,6 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
       CUDA_TRY(cudaFuncSetAttribute(c2a_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIDE_BLOCK_SMEM));
       if (env_ll("C2A_B200_WIDE_CARVEOUT", -1) >= 0)  // development aid (no measurable effect: profiles/experiments/README.md)
         cudaFuncSetAttribute(c2a_wide_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)env_ll("C2A_B200_WIDE_CARVEOUT", -1));
-      cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, a->device) == cudaSuccess)
-      {
-        unsigned long long keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-      }
       done.push_back(a->device);
     }
   }
@@ -416,7 +444,7 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   const size_t wleaf_bytes = wide ? up((size_t)wwarps * WIDE_UL * WIDE_LEAFOUT_DOUBLES * sizeof(double)) : 0;
   const size_t waux_bytes = wide ? up((size_t)wwarps * WIDE_AUX_DOUBLES * sizeof(double)) : 0;
   double *stacks = nullptr;
-  CUDA_TRY(cudaMallocAsync(&stacks, up(stack_bytes) + spill_bytes + wctl_bytes + wstack_bytes + wrec_bytes + wleaf_bytes + waux_bytes, stream));
+  CUDA_TRY(pool_malloc(&stacks, up(stack_bytes) + spill_bytes + wctl_bytes + wstack_bytes + wrec_bytes + wleaf_bytes + waux_bytes, a->device, stream));
   struct Freer { void *p; cudaStream_t s; ~Freer() { cudaFreeAsync(p, s); } } freer{stacks, stream};
   args.stacks = stacks;
   args.spill_recs = nullptr; args.spill_count = nullptr; args.spill_cap = 0; args.spill_live = 0;
@@ -435,8 +463,8 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   // it for whatever is left.  Only when the main kernel fills the machine -- smaller launches end too soon to overlap.
   SideStream *side = nullptr;
   if (wide && blocks == (long long)sms * per_sm && !getenv("C2A_B200_NO_EARLY_WIDE")) side = side_stream(a->device);
-  args.stats = g_stats_dev;
-  args.trace = (g_trace_dev && n <= g_trace_n && !step_in) ? g_trace_dev : nullptr;
+  args.stats = g_stats_device == a->device ? g_stats_dev : nullptr;
+  args.trace = (g_trace_dev && g_trace_device == a->device && n <= g_trace_n && !step_in) ? g_trace_dev : nullptr;
   CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
   if (g_kev.device != a->device)
   {
@@ -469,7 +497,7 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
     w.aux = reinterpret_cast<double *>(extra + spill_bytes + wctl_bytes + wstack_bytes + wrec_bytes + wleaf_bytes);
     w.stack_cap = w_stack_cap; w.rec_cap = w_rec_cap;
     w.window = (int)std::min<long long>(16, std::max<long long>(1, env_ll("C2A_B200_WIDE_WINDOW", 16)));
-    w.stats = g_wide_stats_dev; w.trace = args.trace;
+    w.stats = g_wide_stats_device == a->device ? g_wide_stats_dev : nullptr; w.trace = args.trace;
     if (side)
     {
       w.early = 1;
@@ -508,7 +536,7 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
     {
       // hierarchies deeper than the local-memory stack: the same kernel with its stacks in global memory, on a small grid
       if (tb > 16) tb = 16;
-      CUDA_TRY(cudaMallocAsync(&t.gstack, (size_t)tb * 128 * args.stack_entries * TRANS_ENTRY * sizeof(double), stream));
+      CUDA_TRY(pool_malloc(&t.gstack, (size_t)tb * 128 * args.stack_entries * TRANS_ENTRY * sizeof(double), a->device, stream));
       c2a_translation_kernel<true><<<(unsigned)tb, 128, 0, stream>>>(t);
       cudaFreeAsync(t.gstack, stream);
     }
@@ -546,7 +574,7 @@ static int launch_contacts(const c2a_b200_model *a, const c2a_b200_model *b, con
   {
     // hierarchies deeper than the local-memory stack: stacks in global memory, small grid
     if (blocks > 16) blocks = 16;
-    CUDA_TRY(cudaMallocAsync(&args.gstack, (size_t)blocks * 128 * entries * CONTACT_ENTRY * sizeof(double), stream));
+    CUDA_TRY(pool_malloc(&args.gstack, (size_t)blocks * 128 * entries * CONTACT_ENTRY * sizeof(double), a->device, stream));
     c2a_contact_kernel<true><<<(unsigned)blocks, 128, 0, stream>>>(args);
     cudaFreeAsync(args.gstack, stream);
   }
@@ -788,7 +816,7 @@ int c2a_b200_solve_batch_device(const c2a_b200_model *a, const c2a_b200_model *b
   ON_DEVICE(a->device);
   cudaStream_t stream = (cudaStream_t)cuda_stream;
   unsigned long long *counter = nullptr;
-  CUDA_TRY(cudaMallocAsync(&counter, sizeof(unsigned long long), stream));
+  CUDA_TRY(pool_malloc(&counter, sizeof(unsigned long long), a->device, stream));
   rc = launch_batch(a, b, poses_dev, seed_a_dev, seed_b_dev, n, tol_d, tol_t, out_dev, counter, stream, nullptr, order_dev);
   cudaFreeAsync(counter, stream);
   return rc;
@@ -939,7 +967,7 @@ static int solve_host(const c2a_b200_model *a, const c2a_b200_model *b, const do
     }
     arena = ctx->dev;
   }
-  else e = cudaMallocAsync(&arena, off, stream);
+  else e = pool_malloc(&arena, off, a->device, stream);
   if (e != cudaSuccess) return fail(C2A_B200_ERR_CUDA, std::string("device arena: ") + cudaGetErrorString(e));
   c2a_b200_results d;
   memset(&d, 0, sizeof(d));
@@ -1166,24 +1194,35 @@ int c2a_b200_solve_pairs(const c2a_b200_model *const *models, int32_t n_models, 
     if (models[m]->device != models[0]->device) return fail(C2A_B200_ERR_DEVICE, "models live on different devices");
   }
   if (n == 0) return C2A_B200_OK;
-  // group the queries by (model_a, model_b): every group is one launch whose claim order lists its queries
+  // group the queries by (model_a, model_b): every group is one launch whose claim order lists its queries.  Only the
+  // pairs that occur are listed (sorted keys), so a scene with thousands of models costs what its queries cost
   const size_t N = (size_t)n;
-  std::vector<int64_t> start((size_t)n_models * n_models + 1, 0);
+  std::vector<int64_t> key(N);
   for (size_t i = 0; i < N; i++)
   {
     if (model_a[i] < 0 || model_a[i] >= n_models || model_b[i] < 0 || model_b[i] >= n_models)
       return fail(C2A_B200_ERR_ARG, "model index out of range");
     if ((seed_a && (uint32_t)seed_a[i] >= (uint32_t)models[model_a[i]]->n_tris) || (seed_b && (uint32_t)seed_b[i] >= (uint32_t)models[model_b[i]]->n_tris))
       return fail(C2A_B200_ERR_ARG, "seed of query " + std::to_string(i) + " is not a triangle of its model");
-    start[(size_t)model_a[i] * n_models + model_b[i] + 1]++;
+    key[i] = (int64_t)model_a[i] * n_models + model_b[i];
   }
-  for (size_t g = 0; g < (size_t)n_models * n_models; g++) start[g + 1] += start[g];
-  for (size_t g = 0; g < (size_t)n_models * n_models; g++)
-    if (start[g + 1] > start[g])
-    {
-      int rc = check_pair(models[g / n_models], models[g % n_models], n, poses, out);
-      if (rc) return rc;
-    }
+  std::vector<int64_t> groups(key);
+  std::sort(groups.begin(), groups.end());
+  groups.erase(std::unique(groups.begin(), groups.end()), groups.end());
+  const size_t G = groups.size();
+  std::vector<int32_t> group_of(N);
+  std::vector<int64_t> start(G + 1, 0);
+  for (size_t i = 0; i < N; i++)
+  {
+    group_of[i] = (int32_t)(std::lower_bound(groups.begin(), groups.end(), key[i]) - groups.begin());
+    start[(size_t)group_of[i] + 1]++;
+  }
+  for (size_t g = 0; g < G; g++) start[g + 1] += start[g];
+  for (size_t g = 0; g < G; g++)
+  {
+    int rc = check_pair(models[groups[g] / n_models], models[groups[g] % n_models], n, poses, out);
+    if (rc) return rc;
+  }
   ON_DEVICE(models[0]->device);
   cudaStream_t stream;
   CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -1199,9 +1238,9 @@ int c2a_b200_solve_pairs(const c2a_b200_model *const *models, int32_t n_models, 
   const size_t o_toc = out->toc ? take(N * 8) : 0, o_dist = out->distance ? take(N * 8) : 0;
   const size_t o_mint = out->mint ? take(N * 8) : 0, o_pp = out->p1p2 ? take(N * 48) : 0;
   const size_t o_pt = out->pose_toc ? take(N * 192) : 0, o_lt = out->last_tri ? take(N * 8) : 0;
-  const size_t o_cnt = take((size_t)n_models * n_models * 8);
+  const size_t o_cnt = take(G * 8);
   char *arena = nullptr;
-  cudaError_t e = cudaMallocAsync(&arena, off, stream);
+  cudaError_t e = pool_malloc(&arena, off, models[0]->device, stream);
   if (e != cudaSuccess)
   {
     cudaStreamDestroy(stream);
@@ -1239,7 +1278,7 @@ int c2a_b200_solve_pairs(const c2a_b200_model *const *models, int32_t n_models, 
     for (size_t k = 0; k < N; k++)
     {
       const int32_t i = by_cost[k];
-      order[(size_t)cur[(size_t)model_a[i] * n_models + model_b[i]]++] = i;
+      order[(size_t)cur[(size_t)group_of[i]]++] = i;
     }
   }
   STEP(cudaMemcpyAsync(arena + o_pose, pin.ptr, N * 48 * 8, cudaMemcpyHostToDevice, stream));
@@ -1259,11 +1298,10 @@ int c2a_b200_solve_pairs(const c2a_b200_model *const *models, int32_t n_models, 
     if (rc == C2A_B200_OK) STEP(cudaStreamWaitEvent(side[k], ready, 0));
   }
   int launched = 0;
-  for (size_t g = 0; g < (size_t)n_models * n_models && rc == C2A_B200_OK; g++)
+  for (size_t g = 0; g < G && rc == C2A_B200_OK; g++)
   {
     const int64_t ng = start[g + 1] - start[g];
-    if (ng == 0) continue;
-    rc = launch_batch(models[g / n_models], models[g % n_models], (const double *)(arena + o_pose),
+    rc = launch_batch(models[groups[g] / n_models], models[groups[g] % n_models], (const double *)(arena + o_pose),
                       seed_a ? (const int32_t *)(arena + o_sa) : nullptr, seed_b ? (const int32_t *)(arena + o_sb) : nullptr, ng,
                       tol_d, tol_t, &d, (unsigned long long *)(arena + o_cnt) + g, side[launched % NSIDE], nullptr,
                       (const int32_t *)(arena + o_order) + start[g]);
@@ -1517,6 +1555,7 @@ int c2a_b200_query_trace(int64_t n, uint64_t *out)
     if (g_trace_dev) cudaFree(g_trace_dev);
     g_trace_dev = nullptr; g_trace_n = 0;
     CUDA_TRY(cudaMalloc(&g_trace_dev, (size_t)n * 16));
+    cudaGetDevice(&g_trace_device);
     CUDA_TRY(cudaMemset(g_trace_dev, 0, (size_t)n * 16));
     g_trace_n = n;
   }
@@ -1537,7 +1576,7 @@ int c2a_b200_phase_stats(int32_t enable, uint64_t *out20)
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(out9, g_stats_dev, 20 * 8, cudaMemcpyDeviceToHost));
   }
-  if (enable && !g_stats_dev) CUDA_TRY(cudaMalloc(&g_stats_dev, 24 * 8));
+  if (enable && !g_stats_dev) { CUDA_TRY(cudaMalloc(&g_stats_dev, 24 * 8)); cudaGetDevice(&g_stats_device); }
   if (enable)
   {
     const unsigned long long init[24] = {0, 0, 0, 0, 0, 0, ~0ull, ~0ull};
@@ -1574,7 +1613,7 @@ int c2a_b200_wide_stats(int32_t enable, uint64_t *out16)
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(out16, g_wide_stats_dev, WIDE_NSTATS * 8, cudaMemcpyDeviceToHost));
   }
-  if (enable && !g_wide_stats_dev) CUDA_TRY(cudaMalloc(&g_wide_stats_dev, WIDE_NSTATS * 8));
+  if (enable && !g_wide_stats_dev) { CUDA_TRY(cudaMalloc(&g_wide_stats_dev, WIDE_NSTATS * 8)); cudaGetDevice(&g_wide_stats_device); }
   if (enable)
   {
     unsigned long long init[WIDE_NSTATS] = {0};

@@ -18,7 +18,14 @@
 //     query from the two motions' m_angVel (the reference reads a global that C2A_Solve sets); where the
 //     reference reads uninitialised memory in that branch (see c2a_b200/csrc/c2a_translation.cuh) the
 //     behaviour of its object code under any finite non-zero garbage is reproduced; res->p1/p2 stay zero;
-//   * degenerate rotations do not exit(0) (C2A/LinearMath.h:768).
+//   * degenerate rotations do not exit(0) (C2A/LinearMath.h:768);
+//   * C2A_QueryTimeOfContact / C2A_TimeOfContactStep called DIRECTLY (C2A_Solve always constructs fresh motions, for
+//     which none of this is visible): the first CA step starts from the motions' start pose transform_s, where the
+//     reference reads their current pose ->transform (C2A/src/C2A.cpp:2015-2018) -- the two differ only if the caller
+//     integrate()d a motion before the query; and after a rotational query the motions are not left integrate()d at
+//     the last lamda the loop tried (:2111-2112) -- objmotion1 is at the TOC pose after a hit (:2143), objmotion2 and
+//     the motions of a collision-free query keep the pose they had, so a C2A_QueryContact issued right after a direct
+//     C2A_QueryTimeOfContact must integrate() them itself (C2A_Solve does: it runs its contact pass at the TOC poses).
 #ifndef C2A_B200_DROPIN_C2A_H
 #define C2A_B200_DROPIN_C2A_H
 
