@@ -278,9 +278,11 @@ def contacts_batch(model_a, model_b, poses24, threshold, max_contacts=64):
     return num, recs
 
 
-def distance_batch(model_a, model_b, poses24, seed_a=None, seed_b=None, rel_err=0.0, abs_err=0.0, _entry="c2a_b200_distance_batch"):
-    """Batched C2A_Distance (depth-first routine): poses24 [n,24] = pose of A, pose of B.  Returns a dict with
-    distance [n], p1p2 [n,6], tri_pair [n,2], num_bv_tests [n], num_tri_tests [n]."""
+def distance_batch(model_a, model_b, poses24, seed_a=None, seed_b=None, rel_err=0.0, abs_err=0.0, _entry="c2a_b200_distance_batch", qsize=2):
+    """Batched C2A_Distance (depth-first routine; qsize > 2: the priority-queue routine): poses24 [n,24] = pose of A, pose
+    of B.  Returns a dict with distance [n], p1p2 [n,6], tri_pair [n,2], num_bv_tests [n], num_tri_tests [n]."""
+    if qsize > 2:
+        _entry = "c2a_b200_distance_queue_batch"
     poses24 = np.ascontiguousarray(poses24, dtype=np.float64).reshape(-1, 24)
     n = poses24.shape[0]
     sa = None if seed_a is None else np.ascontiguousarray(seed_a, dtype=np.int32)
@@ -291,6 +293,7 @@ def distance_batch(model_a, model_b, poses24, seed_a=None, seed_b=None, rel_err=
                                          sa.ctypes.data_as(C.c_void_p) if sa is not None else None,
                                          sb.ctypes.data_as(C.c_void_p) if sb is not None else None,
                                          C.c_int64(n), C.c_double(rel_err), C.c_double(abs_err),
+                                         *([C.c_int32(qsize)] if _entry == "c2a_b200_distance_queue_batch" else []),
                                          out["distance"].ctypes.data_as(C.c_void_p), out["p1p2"].ctypes.data_as(C.c_void_p),
                                          out["tri_pair"].ctypes.data_as(C.c_void_p), out["num_bv_tests"].ctypes.data_as(C.c_void_p),
                                          out["num_tri_tests"].ctypes.data_as(C.c_void_p)))

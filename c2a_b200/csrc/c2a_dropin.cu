@@ -406,8 +406,8 @@ static int distance_like(bool gate, C2A_DistanceResult *res, PQP_REAL R1[3][3], 
   }
   int32_t sa = seed_index(o1, o1->last_tri), sb = seed_index(o2, o2->last_tri), pair[2] = {0, 0}, nbv = 0, ntri = 0;
   double dist = 0, p1p2[6];
-  const int rc = (gate ? c2a_b200_collide_distance_batch : c2a_b200_distance_batch)(o1->gpu, o2->gpu, pose, &sa, &sb, 1, rel_err,
-                                                                                    abs_err, &dist, p1p2, pair, &nbv, &ntri);
+  const int rc = gate ? c2a_b200_collide_distance_batch(o1->gpu, o2->gpu, pose, &sa, &sb, 1, rel_err, abs_err, &dist, p1p2, pair, &nbv, &ntri)
+                      : c2a_b200_distance_queue_batch(o1->gpu, o2->gpu, pose, &sa, &sb, 1, rel_err, abs_err, qsize, &dist, p1p2, pair, &nbv, &ntri);
   if (rc) { fprintf(stderr, "c2a_b200: %s\n", c2a_b200_last_error()); return rc; }
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) res->R[i][j] = (R1[0][i] * R2[0][j] + R1[1][i] * R2[1][j] + R1[2][i] * R2[2][j]);

@@ -642,8 +642,9 @@ int c2a_b200_contacts_batch(const c2a_b200_model *a, const c2a_b200_model *b, co
 // box-overlap test) share everything but one template flag of the kernel
 static int distance_like(bool gate, const c2a_b200_model *a, const c2a_b200_model *b, const double *poses24, const int32_t *seed_a,
                          const int32_t *seed_b, int64_t n, double rel_err, double abs_err, double *distance, double *p1p2,
-                         int32_t *tri_pair, int32_t *num_bv_tests, int32_t *num_tri_tests)
+                         int32_t *tri_pair, int32_t *num_bv_tests, int32_t *num_tri_tests, int32_t qsize = 2)
 {
+  if (qsize > 4096) return fail(C2A_B200_ERR_ARG, "qsize above 4096");
   if (!a || !b || n < 0 || (n > 0 && (!poses24 || !distance))) return fail(C2A_B200_ERR_ARG, "NULL argument");
   if (a->device != b->device) return fail(C2A_B200_ERR_DEVICE, "models live on different devices");
   if (gate && (!a->obb || !b->obb)) return fail(C2A_B200_ERR_ARG, "C2A_Collide needs models uploaded with obb_d / obb_To");
@@ -685,7 +686,20 @@ static int distance_like(bool gate, const c2a_b200_model *a, const c2a_b200_mode
     args.gstack = nullptr;
     args.obbA = a->obb; args.obbB = b->obb;
     const int entries = a->depth + b->depth + 2;
-    if (entries <= DIST_STACK)
+    if (qsize > 2 && !gate)
+    {
+      // priority-queue routine: a stack of queue frames per thread in global memory, at most ~1 GB of it
+      DistanceQueueArgs qa;
+      qa.d = args; qa.qsize = qsize; qa.frames = entries; qa.arena = nullptr;
+      const size_t per_thread = (size_t)entries * (1 + (size_t)qsize * DQ_ENTRY) * sizeof(double);
+      long long fit = (long long)(((size_t)1 << 30) / (per_thread * 128));
+      if (fit < 1) fit = 1;
+      if (blocks > fit) blocks = fit;
+      STEP(cudaMalloc(&qa.arena, (size_t)blocks * 128 * per_thread));
+      if (rc == C2A_B200_OK) c2a_distance_queue_kernel<<<(unsigned)blocks, 128>>>(qa);
+      args.gstack = qa.arena;   // (released below)
+    }
+    else if (entries <= DIST_STACK)
     {
       if (gate) c2a_distance_kernel<false, true><<<(unsigned)blocks, 128>>>(args);
       else c2a_distance_kernel<false, false><<<(unsigned)blocks, 128>>>(args);
@@ -720,6 +734,13 @@ int c2a_b200_distance_batch(const c2a_b200_model *a, const c2a_b200_model *b, co
                             int32_t *tri_pair, int32_t *num_bv_tests, int32_t *num_tri_tests)
 {
   return distance_like(false, a, b, poses24, seed_a, seed_b, n, rel_err, abs_err, distance, p1p2, tri_pair, num_bv_tests, num_tri_tests);
+}
+
+int c2a_b200_distance_queue_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses24, const int32_t *seed_a,
+                                  const int32_t *seed_b, int64_t n, double rel_err, double abs_err, int32_t qsize, double *distance,
+                                  double *p1p2, int32_t *tri_pair, int32_t *num_bv_tests, int32_t *num_tri_tests)
+{
+  return distance_like(false, a, b, poses24, seed_a, seed_b, n, rel_err, abs_err, distance, p1p2, tri_pair, num_bv_tests, num_tri_tests, qsize);
 }
 
 int c2a_b200_collide_distance_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses24, const int32_t *seed_a,

@@ -276,8 +276,9 @@ struct C2A_DistanceResult
   const PQP_REAL *P2() { return p2; }
 };
 
-// C2A/C2A.h:256-261, C2A/src/C2A_PQP.cpp:970-1056.  Runs the reference's depth-first routine whatever qsize says
-// (the reference switches to a priority queue for qsize > 2, which may report another pair within the same bounds).
+// C2A/C2A.h:256-261, C2A/src/C2A_PQP.cpp:970-1056: the depth-first routine for qsize <= 2, the priority-queue one
+// (C2ADistanceQueueRecurse, :624-787) above, like the reference; equally distant pending pairs leave the queue in the
+// order they entered it (PQP's own queue is not in the reference's tree and may break such ties differently).
 // Reads and updates o1->last_tri / o2->last_tri like the reference.
 int C2A_Distance(C2A_DistanceResult *result, PQP_REAL R1[3][3], PQP_REAL T1[3], C2A_Model *o1, PQP_REAL R2[3][3],
                  PQP_REAL T2[3], C2A_Model *o2, PQP_REAL rel_err, PQP_REAL abs_err, int qsize = 2);

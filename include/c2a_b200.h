@@ -169,6 +169,17 @@ int c2a_b200_distance_batch(const c2a_b200_model *a, const c2a_b200_model *b, co
                             const int32_t *seed_b, int64_t n, double rel_err, double abs_err, double *distance, double *p1p2,
                             int32_t *tri_pair, int32_t *num_bv_tests, int32_t *num_tri_tests);
 
+/* The same query with the routine C2A_Distance takes for qsize > 2 (C2ADistanceQueueRecurse, C2A/src/C2A_PQP.cpp:624-787):
+ * best-first over a bounded queue of pending node pairs (PQP's BVTQ, not in the reference's tree), recursing with a fresh
+ * queue when it is full.  With both error bounds zero the distance equals the depth-first routine's; the reported pair,
+ * points and counters are those of this visiting order.  Among equally distant pending pairs the one queued first is
+ * taken first -- the behaviour of the queue stand-in the reference is compiled with here (oracle/pqp_shim/BVTQ.h); PQP's
+ * own heap may break such ties differently.  qsize <= 2 runs the depth-first routine, like the reference (:1031). */
+int c2a_b200_distance_queue_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses24,
+                                  const int32_t *seed_a, const int32_t *seed_b, int64_t n, double rel_err, double abs_err,
+                                  int32_t qsize, double *distance, double *p1p2, int32_t *tri_pair, int32_t *num_bv_tests,
+                                  int32_t *num_tri_tests);
+
 /* Batched C2A_Collide, PQP_CollideResult overload (C2A/C2A.h:249-253, C2A/src/C2A_PQP.cpp:798-968): the pairs of
  * intersecting triangles of the two models at the static poses poses24[i].  flag: 1 = C2A_ALL_CONTACTS, 2 =
  * C2A_FIRST_CONTACT (C2A/C2A.h:246-247).  num_pairs [n] = PQP_CollideResult::NumPairs(); pairs [n][max_pairs][2]: the

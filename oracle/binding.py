@@ -183,15 +183,15 @@ class _Port:
                                   C.c_int64(max_out), _ptr(out))
         return int(n), out[:min(int(n), max_out)]
 
-    def distance(self, bvhA, bvhB, poses24, seedA=None, seedB=None, rel_err=0.0, abs_err=0.0):
-        """C2A_Distance (depth-first routine) per query: poses24 [n,24] = pose of A, pose of B."""
+    def distance(self, bvhA, bvhB, poses24, seedA=None, seedB=None, rel_err=0.0, abs_err=0.0, qsize=2):
+        """C2A_Distance per query (depth-first routine; the priority-queue one for qsize > 2): poses24 [n,24] = pose of A, pose of B."""
         sA, sB = bvh_struct(bvhA), bvh_struct(bvhB)
         poses24 = np.ascontiguousarray(poses24, np.float64).reshape(-1, 24)
         out = np.zeros(len(poses24), dtype=DISTANCE_DTYPE)
         for i in range(len(poses24)):
-            self.lib.orc_distance(C.byref(sA), C.byref(sB), _ptr(poses24[i]), C.c_int32(0 if seedA is None else int(seedA[i])),
-                                  C.c_int32(0 if seedB is None else int(seedB[i])), C.c_double(rel_err), C.c_double(abs_err),
-                                  C.c_void_p(out[i:i + 1].ctypes.data))
+            self.lib.orc_distance_queue(C.byref(sA), C.byref(sB), _ptr(poses24[i]), C.c_int32(0 if seedA is None else int(seedA[i])),
+                                        C.c_int32(0 if seedB is None else int(seedB[i])), C.c_double(rel_err), C.c_double(abs_err),
+                                        C.c_int32(qsize), C.c_void_p(out[i:i + 1].ctypes.data))
         return out
 
     def collide(self, bvhA, bvhB, poses24, flag=1, max_pairs=4096):

@@ -1923,6 +1923,104 @@ extern "C" void orc_distance(const orc_bvh *A, const orc_bvh *B, const double po
   mt_v(res->p2, cx.Rrel, u);
 }
 
+// C2A_Distance with qsize > 2: C2ADistanceQueueRecurse (C2A/src/C2A_PQP.cpp:624-787), best-first over a bounded queue of
+// pending node pairs, recursing with a fresh queue whenever the current one cannot take two more.  The queue is PQP's BVTQ
+// (un-vendored); what matters of it here is only which of several equally distant pairs comes out first: the stand-in the
+// compiled reference links (oracle/pqp_shim/BVTQ.h) takes the one inserted earliest, and so does this.
+namespace {
+struct QTest { double d; int b1, b2; double R[9], T[3]; };
+
+void distance_queue_recurse(DistCtx &cx, int qsize, const QTest &root)
+{
+  const orc_bvh *A = cx.A, *B = cx.B;
+  orc_distance_result *res = cx.res;
+  std::vector<QTest> q;
+  q.reserve(qsize);
+  QTest cur = root;
+  while (true)
+  {
+    const int l1 = A->first_child[cur.b1] < 0, l2 = B->first_child[cur.b2] < 0;
+    if (l1 && l2)
+    {
+      res->num_tri_tests++;
+      double p[3], qq[3];
+      const int ta = -A->first_child[cur.b1] - 1, tb = -B->first_child[cur.b2] - 1;
+      const double d = orc_tri_distance(cx.Rrel, cx.Trel, &A->tris[9 * ta], &B->tris[9 * tb], p, qq);
+      if (d < res->distance)
+      {
+        res->distance = d;
+        res->tri_a = ta; res->tri_b = tb;
+        v_cpy(res->p1, p); v_cpy(res->p2, qq);
+      }
+    }
+    else if ((int)q.size() == qsize - 1) distance_queue_recurse(cx, qsize, cur);
+    else
+    {
+      const double sz1 = bv_size(A, cur.b1), sz2 = bv_size(B, cur.b2);
+      res->num_bv_tests += 2;
+      QTest t1, t2;
+      double Tt[3], S[3];
+      if (l2 || (!l1 && (sz1 > sz2)))
+      {
+        const int c1 = A->first_child[cur.b1], c2 = c1 + 1;
+        t1.b1 = c1; t1.b2 = cur.b2;
+        mt_m(t1.R, &A->R[9 * c1], cur.R); v_sub(Tt, cur.T, &A->Tr[3 * c1]); mt_v(t1.T, &A->R[9 * c1], Tt);
+        t1.d = bv_distance(t1.R, t1.T, A, t1.b1, B, t1.b2, S);
+        t2.b1 = c2; t2.b2 = cur.b2;
+        mt_m(t2.R, &A->R[9 * c2], cur.R); v_sub(Tt, cur.T, &A->Tr[3 * c2]); mt_v(t2.T, &A->R[9 * c2], Tt);
+        t2.d = bv_distance(t2.R, t2.T, A, t2.b1, B, t2.b2, S);
+      }
+      else
+      {
+        const int c1 = B->first_child[cur.b2], c2 = c1 + 1;
+        t1.b1 = cur.b1; t1.b2 = c1;
+        m_m(t1.R, cur.R, &B->R[9 * c1]); m_v_p(t1.T, cur.R, &B->Tr[3 * c1], cur.T);
+        t1.d = bv_distance(t1.R, t1.T, A, t1.b1, B, t1.b2, S);
+        t2.b1 = cur.b1; t2.b2 = c2;
+        m_m(t2.R, cur.R, &B->R[9 * c2]); m_v_p(t2.T, cur.R, &B->Tr[3 * c2], cur.T);
+        t2.d = bv_distance(t2.R, t2.T, A, t2.b1, B, t2.b2, S);
+      }
+      q.push_back(t1);
+      q.push_back(t2);
+    }
+    if (q.empty()) break;
+    size_t k = 0;
+    for (size_t i = 1; i < q.size(); i++) if (q[i].d < q[k].d) k = i;
+    cur = q[k];
+    q.erase(q.begin() + k);
+    if ((cur.d + cx.abs_err >= res->distance) && ((cur.d * (1 + cx.rel_err)) >= res->distance)) break;
+  }
+}
+}  // namespace
+
+extern "C" void orc_distance_queue(const orc_bvh *A, const orc_bvh *B, const double pose24[24], int32_t seedA, int32_t seedB,
+                                   double rel_err, double abs_err, int32_t qsize, orc_distance_result *res)
+{
+  if (qsize <= 2) { orc_distance(A, B, pose24, seedA, seedB, rel_err, abs_err, res); return; }   // :1031-1034
+  DistCtx cx;
+  cx.A = A; cx.B = B; cx.rel_err = rel_err; cx.abs_err = abs_err; cx.res = res;
+  const double *R1 = &pose24[0], *T1 = &pose24[9], *R2 = &pose24[12], *T2 = &pose24[21];
+  double Tt[3], Rt[9], p[3], q[3];
+  mt_m(cx.Rrel, R1, R2);
+  v_sub(Tt, T2, T1);
+  mt_v(cx.Trel, R1, Tt);
+  res->distance = orc_tri_distance(cx.Rrel, cx.Trel, &A->tris[9 * seedA], &B->tris[9 * seedB], p, q);
+  res->tri_a = seedA; res->tri_b = seedB;
+  v_cpy(res->p1, p); v_cpy(res->p2, q);
+  res->num_bv_tests = 0; res->num_tri_tests = 0;
+  QTest root;
+  root.b1 = 0; root.b2 = 0; root.d = 0;
+  m_m(Rt, cx.Rrel, &B->R[0]);
+  mt_m(root.R, &A->R[0], Rt);
+  m_v_p(Tt, cx.Rrel, &B->Tr[0], cx.Trel);
+  v_sub(Tt, Tt, &A->Tr[0]);
+  mt_v(root.T, &A->R[0], Tt);
+  distance_queue_recurse(cx, qsize, root);
+  double u[3];
+  v_sub(u, res->p2, cx.Trel);
+  mt_v(res->p2, cx.Rrel, u);
+}
+
 // ---- discrete collision queries -----------------------------------------------------------------
 // C2A_Collide, both overloads (C2A/src/C2A_PQP.cpp:798-968 and :1060-1280).  Their box-overlap and triangle-overlap
 // tests are PQP's (obb_disjoint, TriContact: un-vendored, no in-tree source): restated here from the published

@@ -126,6 +126,11 @@ typedef struct orc_distance_result
 void orc_distance(const orc_bvh *A, const orc_bvh *B, const double pose24[24], int32_t seedA, int32_t seedB,
                   double rel_err, double abs_err, orc_distance_result *res);
 
+/* C2A_Distance with the priority-queue routine it takes for qsize > 2 (C2ADistanceQueueRecurse, C2A/src/C2A_PQP.cpp:624-787);
+ * among equally distant pending pairs the one queued first is taken first, as oracle/pqp_shim/BVTQ.h does. */
+void orc_distance_queue(const orc_bvh *A, const orc_bvh *B, const double pose24[24], int32_t seedA, int32_t seedB,
+                        double rel_err, double abs_err, int32_t qsize, orc_distance_result *res);
+
 /* C2A_Collide, both overloads (C2A/src/C2A_PQP.cpp:910-968, 1199-1280).  dA/ToA/dB/ToB: [n_nodes][3] OBB half-dimensions
  * and centres (BV::d, BV::To).  orc_obb_disjoint / orc_tri_contact restate PQP's un-vendored obb_disjoint / TriContact in
  * the arithmetic of oracle/pqp_shim (what the compiled reference links). */

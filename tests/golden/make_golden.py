@@ -123,6 +123,23 @@ def distance_fixture(R):
     np.savez_compressed(os.path.join(HERE, "ref_distance_knot_128x16.npz"), **out)
 
 
+def distance_queue_fixture(R):
+    """The reference's C2A_Distance with qsize > 2 (C2ADistanceQueueRecurse, C2A_PQP.cpp:624-787; the queue is the PQP
+    stand-in of oracle/pqp_shim) on the poses and seeds of ref_distance_knot_128x16."""
+    g = np.load(os.path.join(HERE, "ref_distance_knot_128x16.npz"))
+    tris, vi = meshes.torus_knot(128, 16)
+    a, b = R.model(tris, vi), R.model(tris, vi)
+    out = {}
+    for qs in (3, 10):
+        for tag, rel, ab in (("exact", 0.0, 0.0), ("approx", 0.25, 2.0)):
+            r = R.distance(a, b, g["poses24"], g["seed_a"], g["seed_b"], rel, ab, qsize=qs)
+            for k in r.dtype.names:
+                out[f"q{qs}_{tag}_{k}"] = r[k]
+            print(f"ref_distance_queue_knot_128x16 qsize {qs} {tag}: mean nbv {r['num_bv_tests'].mean():.0f} (depth-first {g[tag + '_num_bv_tests'].mean():.0f}), "
+                  f"other pair than depth-first {int((r['tri_a'] != g[tag + '_tri_a']).sum())}/{len(r)}")
+    np.savez_compressed(os.path.join(HERE, "ref_distance_queue_knot_128x16.npz"), **out)
+
+
 def collide_fixture(R):
     """The reference's C2A_Collide, both overloads (C2A_PQP.cpp:798-968, 1060-1280), on static pose pairs: a knot against
     itself and the bunny against a larger knot.  Pairs are the reference's Tri::id values in its reporting order."""
@@ -221,6 +238,9 @@ def main():
     if "--only-distance" in sys.argv:
         distance_fixture(R)
         return
+    if "--only-distance-queue" in sys.argv:
+        distance_queue_fixture(R)
+        return
     if "--only-collide" in sys.argv:
         collide_fixture(R)
         return
@@ -318,6 +338,7 @@ def main():
 
     translation_fixtures(R, bunny)
     distance_fixture(R)
+    distance_queue_fixture(R)
     collide_fixture(R)
     bunny_grazing_fixture(R, bunny)
 

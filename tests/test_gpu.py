@@ -195,6 +195,31 @@ def test_distance_query_bit_exact(tag, golden, models, bvhs):
     assert np.array_equal(got["p1p2"], np.concatenate([ref["p1"], ref["p2"]], 1)) and (got["distance"][:20] == 0).all()
 
 
+@pytest.mark.parametrize("qsize", [3, 10])
+@pytest.mark.parametrize("tag", ["exact", "approx"])
+def test_distance_queue_routine_bit_exact(qsize, tag, golden, models, bvhs):
+    """C2A_Distance with qsize > 2 (c2a_distance_queue_kernel: best-first over a bounded queue, a frame per nested call)
+    against the reference's object code, and on a heterogeneous pair against the port."""
+    g, gq = golden("ref_distance_knot_128x16"), golden("ref_distance_queue_knot_128x16")
+    rel, ab = g[f"{tag}_err"]
+    m = models("knot_128x16")
+    got = api.distance_batch(m, m, g["poses24"], g["seed_a"], g["seed_b"], rel, ab, qsize=qsize)
+    pre = f"q{qsize}_{tag}_"
+    assert np.array_equal(got["distance"], gq[pre + "distance"])
+    assert np.array_equal(got["p1p2"], np.concatenate([gq[pre + "p1"], gq[pre + "p2"]], 1))
+    assert np.array_equal(got["tri_pair"], np.stack([gq[pre + "tri_a"], gq[pre + "tri_b"]], 1))
+    assert np.array_equal(got["num_bv_tests"], gq[pre + "num_bv_tests"]) and np.array_equal(got["num_tri_tests"], gq[pre + "num_tri_tests"])
+    poses = workloads.static_pose_batch(200, 123, radius=workloads.BUNNY_RADIUS)
+    ref = oracle.port().distance(bvhs("bunny"), bvhs("knot_512x32"), poses, None, None, rel, ab, qsize=qsize)
+    got = api.distance_batch(models("bunny"), models("knot_512x32"), poses, None, None, rel, ab, qsize=qsize)
+    assert np.array_equal(got["distance"], ref["distance"]) and np.array_equal(got["num_bv_tests"], ref["num_bv_tests"])
+    assert np.array_equal(got["tri_pair"], np.stack([ref["tri_a"], ref["tri_b"]], 1)) and np.array_equal(got["num_tri_tests"], ref["num_tri_tests"])
+    # qsize <= 2 is the depth-first routine, whichever entry is called
+    a = api.distance_batch(m, m, g["poses24"][:50], g["seed_a"][:50], g["seed_b"][:50], rel, ab)
+    b = api.distance_batch(m, m, g["poses24"][:50], g["seed_a"][:50], g["seed_b"][:50], rel, ab, _entry="c2a_b200_distance_queue_batch", qsize=2)
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+
+
 def test_degenerate_motions_against_oracle_port(models, bvhs):
     """No motion at all, rotation in place, contact at the start pose, vanishing motions (both branches)."""
     poses = workloads.degenerate_batch(radius=workloads.KNOT_RADIUS)
@@ -405,6 +430,10 @@ def test_deep_hierarchies_run_on_global_memory_stacks():
         assert np.array_equal(recs[i][:k]["tri_a"], r_ref["tri_a"][:k]) and np.array_equal(recs[i][:k]["dist"], r_ref["dist"][:k]), i
 
 
+    rq = P.distance(bvh, bvh, sp, qsize=5)
+    gq = api.distance_batch(m, m, sp, qsize=5)     # 100 frames of nested calls available, a few used
+    assert np.array_equal(gq["distance"], rq["distance"]) and np.array_equal(gq["num_bv_tests"], rq["num_bv_tests"])
+    assert np.array_equal(gq["tri_pair"], np.stack([rq["tri_a"], rq["tri_b"]], 1))
     # C2A_Collide, both overloads, on the same chain-shaped hierarchy
     rn, rp, rbv, rtr = P.collide(bvh, bvh, sp, max_pairs=64)
     gc = api.collide_batch(m, m, sp, max_pairs=64)

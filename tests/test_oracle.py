@@ -187,6 +187,22 @@ def test_port_distance_matches_golden(tag, golden, bvhs):
         assert (g["approx_distance"] >= g["exact_distance"]).all()
 
 
+@pytest.mark.parametrize("qsize", [3, 10])
+@pytest.mark.parametrize("tag", ["exact", "approx"])
+def test_port_distance_queue_matches_golden(qsize, tag, golden, bvhs):
+    """C2A_Distance with qsize > 2 (C2ADistanceQueueRecurse, C2A_PQP.cpp:624-787): the port against the reference's object
+    code (linked with the queue stand-in of oracle/pqp_shim).  With exact bounds the distance is the depth-first one."""
+    g, gq = golden("ref_distance_knot_128x16"), golden("ref_distance_queue_knot_128x16")
+    rel, ab = g[f"{tag}_err"]
+    b = bvhs("knot_128x16")
+    out = oracle.port().distance(b, b, g["poses24"], g["seed_a"], g["seed_b"], rel, ab, qsize=qsize)
+    for k in out.dtype.names:
+        assert np.array_equal(out[k], gq[f"q{qsize}_{tag}_{k}"]), (qsize, tag, k)
+    if tag == "exact":
+        assert np.array_equal(out["distance"], g["exact_distance"])
+    assert (out["num_bv_tests"] != g[f"{tag}_num_bv_tests"]).sum() > 100      # another visiting order than the depth-first walk
+
+
 COLLIDE_CASES = [("knot_128x16", "knot_128x16", "knot_128x16"), ("bunny_vs_knot_512x32", "bunny", "knot_512x32")]
 
 
