@@ -1624,7 +1624,7 @@ int c2a_b200_kernel_times(double *out3)
   return C2A_B200_OK;
 }
 
-// Counters of c2a_wide_kernel (development aid): enable != 0 arms / re-zeroes, out (WIDE_NSTATS = 16 words) reads the
+// Counters of c2a_wide_kernel (development aid): enable != 0 arms / re-zeroes, out (WIDE_NSTATS = 24 words) reads the
 // counters accumulated since: steps, redone steps, rounds, leaf passes, child tests, triangle tests, events, cycles in
 // EXPAND / LEAF / resolve / fold / set-up, queries, one-pair-per-round steps, first / last globaltimer ns.
 int c2a_b200_wide_stats(int32_t enable, uint64_t *out16)

@@ -82,7 +82,13 @@ struct WideArgs
   unsigned long long *trace;
 };
 enum { WS_STEPS = 0, WS_REDO, WS_ROUNDS, WS_LEAF_PASSES, WS_TESTS, WS_LEAVES, WS_EVENTS, WS_CYC_EXPAND, WS_CYC_LEAF,
-       WS_CYC_RESOLVE, WS_CYC_FOLD, WS_CYC_SETUP, WS_QUERIES, WS_SEQ_STEPS, WS_T_FIRST, WS_T_LAST, WIDE_NSTATS };
+       WS_CYC_RESOLVE, WS_CYC_FOLD, WS_CYC_SETUP, WS_QUERIES, WS_SEQ_STEPS, WS_T_FIRST, WS_T_LAST,
+       WS_X_SELECT, WS_X_POP, WS_X_XFORM, WS_X_RECT, WS_X_BOUND, WS_X_SYNC, WS_X_RECORD, WS_X_PUSH, WIDE_NSTATS };  // WS_X_*: lane 0's cycles inside an EXPAND pass
+#if C2A_WIDE_STATS
+#define WIDE_TS(var, dep) { asm volatile("" :: "d"((double)(dep)) : "memory"); var = clock64(); }
+#else
+#define WIDE_TS(var, dep)
+#endif
 
 C2A_DEV unsigned long long shfl_u64(unsigned mask, unsigned long long v, int src) { return __shfl_sync(mask, v, src); }
 C2A_DEV unsigned long long warp_min_u64(unsigned long long v)
@@ -395,6 +401,8 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
             // ------------------------------------------------------------ EXPAND pass (C2A.cpp:1192-1276)
             // window: the first Wn entries from the top that still pass under Dw (stale ones are dropped: their
             // step bounds are folded from their records)
+            long long ts_a = 0, ts_b = 0, ts_c = 0, ts_d = 0, ts_e = 0, ts_s = 0, ts_r = 0, ts_f = 0;
+            (void)ts_a; (void)ts_b; (void)ts_c; (void)ts_d; (void)ts_e; (void)ts_s; (void)ts_r; (void)ts_f;
             const int idx = sp - 1 - lane;
             double Mv = INF;
             if (idx >= 0) Mv = stk[(size_t)idx * ENTRY_DOUBLES + 12];
@@ -430,6 +438,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
             if (!seq && (nrec + 2 * npairs > args.rec_cap)) { redo = true; break; }
             if (sp + 2 * npairs > args.stack_cap) { redo = true; seq = true; break; }  // (cannot happen with the caps the host chooses)
 
+            WIDE_TS(ts_a, npairs);
             double R[9], T[3], Mpar = 0, d = 0, mt = 0, val = INF;
             unsigned long long key = 0, ckey = 0;
             int n1 = 0, n2 = 0;
@@ -454,6 +463,8 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
               const bool l1 = cm1.first_child < 0, l2 = cm2.first_child < 0;
               popped_leaf = l1 && l2;  // (one pair per round only: wide rounds keep leaf pairs off the stack)
             }
+            WIDE_TS(ts_b, cm1.size + cm2.size + R[0]);
+            ts_c = ts_d = ts_e = ts_b;
             if (have && !popped_leaf)
             {
               const bool l1 = cm1.first_child < 0, l2 = cm2.first_child < 0;
@@ -484,6 +495,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
 #pragma unroll
               for (int i = 0; i < 9; i++) R[i] = Rc[i];
               T[0] = Tc[0]; T[1] = Tc[1]; T[2] = Tc[2];
+              WIDE_TS(ts_c, R[0] + R[4] + R[8] + T[0] + T[1] + T[2]);
               // child BV test (C2A.cpp:1237-1276)
               prefetch_l1(rl); prefetch_l1(rl + 8);
               double S[3];
@@ -492,6 +504,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
               d = rss_rect_dist(R, T, la.x, la.y, lb.x, lb.y, S);
               d -= (ra2.x + rb2.x);
               d = (d < 0.0) ? 0.0 : d;
+              WIDE_TS(ts_d, d);
               if (d != 0.0)
               {
                 double Rl[9], tmp[3], S1[3], S2[3], r1[9];
@@ -516,10 +529,13 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
               }
               my_leafpair = cm1.first_child < 0 && cm2.first_child < 0;
               val = (mt < upb) ? d : INF;
+              WIDE_TS(ts_e, mt);
             }
             __syncwarp();
             // the pair exchanges its two tests; the closer child is visited first, ties visit 'a' first (d2 < d1)
             const double d_o = __shfl_xor_sync(FULL, d, 1);
+            WIDE_TS(ts_s, d_o);
+            ts_r = ts_f = ts_s;
             const bool c_first = c ? (d < d_o) : (d_o < d);
             const int j = (c == 1) == c_first ? 0 : 1;   // 0: visited first
             if (seq)
@@ -574,6 +590,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
                 __stcs(rr + 1, make_double2(val, mt));
               }
               nrec += 2 * npairs;
+              WIDE_TS(ts_r, nrec);
               const bool pass = have && val < Dw;   // (the popped pair's M < Dw already)
               const double Mc = Mpar > val ? Mpar : val;
               // waiting leaves
@@ -606,11 +623,17 @@ __global__ void __launch_bounds__(WIDE_THREADS, 2) c2a_wide_kernel(const WideArg
                 top_known = true;
               }
               __syncwarp();
+              WIDE_TS(ts_f, sp);
             }
             if ((C2A_WIDE_STATS && args.stats) && lane == 0)
             {
+              atomicAdd(args.stats + WS_X_SYNC, (unsigned long long)(ts_s - ts_e)); atomicAdd(args.stats + WS_X_RECORD, (unsigned long long)(ts_r - ts_s));
+              atomicAdd(args.stats + WS_X_PUSH, (unsigned long long)(ts_f - ts_r));
               atomicAdd(args.stats + WS_ROUNDS, 1ull); atomicAdd(args.stats + WS_TESTS, (unsigned long long)(2 * npairs));
               atomicAdd(args.stats + WS_CYC_EXPAND, (unsigned long long)(clock64() - t_pass));
+              atomicAdd(args.stats + WS_X_SELECT, (unsigned long long)(ts_a - t_pass)); atomicAdd(args.stats + WS_X_POP, (unsigned long long)(ts_b - ts_a));
+              atomicAdd(args.stats + WS_X_XFORM, (unsigned long long)(ts_c - ts_b)); atomicAdd(args.stats + WS_X_RECT, (unsigned long long)(ts_d - ts_c));
+              atomicAdd(args.stats + WS_X_BOUND, (unsigned long long)(ts_e - ts_d));
             }
           }
           if (seq) continue;

@@ -36,7 +36,7 @@ int c2a_b200_phase_stats(int32_t enable, uint64_t *out20);
 int c2a_b200_kernel_times(double *out3);
 
 /* Counters of the wide traversal kernel (development aid): see c2a_kernels.cu. */
-int c2a_b200_wide_stats(int32_t enable, uint64_t *out16);
+int c2a_b200_wide_stats(int32_t enable, uint64_t *out24);  /* out: 24 words */
 
 /* Per-query timeline (development aid): n > 0 arms a [n][2] device buffer that the next batches of <= n queries fill
  * with the globaltimer (ns) at claim and at result write-out; n == 0 copies it to out; n < 0 frees it. */

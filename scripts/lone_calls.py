@@ -30,7 +30,7 @@ for lo, hi in ((0, 2), (2, 6), (6, 12), (12, 1000)):
     if s.any(): print(f"  numCA in [{lo},{hi}): {s.sum()} calls, call {r[s, 0].mean():.3f} ms, main {r[s, 1].mean():.3f}, wide {r[s, 2].mean():.3f}, BV tests {r[s, 4].mean():.0f}")
 if os.environ.get("WIDE_STATS"):
     # with a library built with -DC2A_WIDE_STATS=1 (scripts/build_variant.py): cycle shares of the wide kernel's phases
-    L = api.lib(); ws = (C.c_uint64 * 16)()
+    L = api.lib(); ws = (C.c_uint64 * 32)()
     L.c2a_b200_wide_stats.argtypes = [C.c_int32, C.c_void_p]
     L.c2a_b200_wide_stats(1, None)
     sa = sb = 0
@@ -43,3 +43,7 @@ if os.environ.get("WIDE_STATS"):
     print(f"wide kernel over the 303 calls: {w[12]} queries, {w[0]} steps ({w[13]} one-pair, {w[1]} redone); per step: {w[2] / w[0]:.1f} rounds x {w[7] / max(1, w[2]):.0f} cyc, "
           f"{w[3] / w[0]:.1f} leaf passes x {w[8] / max(1, w[3]):.0f} cyc, {w[4] / w[0]:.0f} tests, {w[5] / w[0]:.0f} tri tests, {w[6] / w[0]:.1f} events; "
           f"cycles per step {cyc / w[0]:.0f}: expand {w[7] / cyc:.2f} leaf {w[8] / cyc:.2f} resolve {w[9] / cyc:.2f} fold {w[10] / cyc:.2f} setup {w[11] / cyc:.2f}")
+    r_ = max(1, w[2])
+    print(f"inside an EXPAND pass (lane 0, cycles per round): window select {w[16] / r_:.0f}, pop + node meta {w[17] / r_:.0f}, child fetch + transform {w[18] / r_:.0f}, "
+          f"rectangle distance {w[19] / r_:.0f}, motion bounds {w[20] / r_:.0f}, wait for the slowest lane {w[21] / r_:.0f}, records {w[22] / r_:.0f}, "
+          f"leaf list + pushes {w[23] / r_:.0f}, rest (counters) {(w[7] - sum(w[16:24])) / r_:.0f}")

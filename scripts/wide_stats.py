@@ -9,7 +9,7 @@ knot = tuple(int(x) for x in os.environ.get("KNOT", "512x32").split("x"))
 tris = meshes.torus_knot(*knot)[0]
 bvh = api.build_bvh(tris); model = api.Model(bvh, 0)
 f = ("status", "collisionfree", "num_ca", "num_bv_tests", "num_tri_tests", "toc", "distance", "mint", "p1p2", "pose_toc", "last_tri")
-L = api.lib(); st = (C.c_uint64 * 20)(); ws = (C.c_uint64 * 16)(); kt = (C.c_double * 3)()
+L = api.lib(); st = (C.c_uint64 * 20)(); ws = (C.c_uint64 * 32)(); kt = (C.c_double * 3)()
 L.c2a_b200_wide_stats.argtypes = [C.c_int32, C.c_void_p]
 poses_all = workloads.approach_batch(max(sizes), 20260002, radius=workloads.KNOT_RADIUS)
 api.solve_batch(model, model, poses_all[:4096], fields=f)
