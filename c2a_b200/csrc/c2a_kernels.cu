@@ -298,7 +298,7 @@ static int64_t g_trace_n = 0;
 // Per host thread and device: a lowest-priority side stream for the wide kernel's early launch, with the two events that
 // fork it from and join it to the caller's stream.
 namespace {
-struct SideStream { int device = -1; cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+struct SideStream { int device = -1; cudaStream_t of = nullptr; cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
 struct SideStreamSet
 {
   std::vector<SideStream> v;
@@ -315,10 +315,13 @@ struct SideStreamSet
   }
 };
 thread_local SideStreamSet g_side;
-SideStream *side_stream(int device)  // the caller has made `device` current; nullptr: none to be had (no early launch then)
+// One side stream per (device, caller's stream), so that launches a thread issues on several streams do not queue their
+// early wide kernels behind one another; a handful at most (a thread that cycles through more streams goes without).
+SideStream *side_stream(int device, cudaStream_t of)  // the caller has made `device` current; nullptr: no early launch
 {
-  for (auto &c : g_side.v) if (c.device == device) return c.s ? &c : nullptr;
-  SideStream c; c.device = device;
+  for (auto &c : g_side.v) if (c.device == device && c.of == of) return c.s ? &c : nullptr;
+  if (g_side.v.size() >= 8) return nullptr;
+  SideStream c; c.device = device; c.of = of;
   int least = 0, greatest = 0;
   if (cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess &&
       cudaStreamCreateWithPriority(&c.s, cudaStreamNonBlocking, least) == cudaSuccess)
@@ -346,6 +349,7 @@ cudaMemPool_t device_pool(int device)
   static std::vector<std::pair<int, cudaMemPool_t>> pools;
   std::lock_guard<std::mutex> lk(m);
   for (auto &p : pools) if (p.first == device) return p.second;
+  if (getenv("C2A_B200_DEFAULT_POOL")) { pools.push_back({device, nullptr}); return nullptr; }   // development aid
   cudaMemPoolProps props;
   memset(&props, 0, sizeof(props));
   props.allocType = cudaMemAllocationTypePinned;
@@ -370,11 +374,13 @@ cudaError_t pool_malloc_(void **p, size_t bytes, int device, cudaStream_t stream
 #define pool_malloc(p, bytes, device, stream) pool_malloc_((void **)(p), (bytes), (device), (stream))
 }  // namespace
 
+static cudaStream_t thread_stream(int device);  // the calling thread's persistent stream on `device` (defined with HostCtx below)
+
 // per-device scratch: the claim counter
 static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const double *poses, const int32_t *sa,
                         const int32_t *sb, int64_t n, double tol_d, double tol_t, const c2a_b200_results *out,
                         unsigned long long *counter, cudaStream_t stream, const double *step_in = nullptr,
-                        const int32_t *order = nullptr)
+                        const int32_t *order = nullptr, bool allow_early = true)
 {
   BatchArgs args;
   args.A = DevModel{a->geom, a->rloc, a->meta, a->tris, a->n_nodes, a->n_tris};
@@ -462,7 +468,7 @@ static int launch_batch(const c2a_b200_model *a, const c2a_b200_model *b, const 
   // kernel's blocks retire, so the long chains of the heaviest queries overlap the main kernel's run-out), and once after
   // it for whatever is left.  Only when the main kernel fills the machine -- smaller launches end too soon to overlap.
   SideStream *side = nullptr;
-  if (wide && blocks == (long long)sms * per_sm && !getenv("C2A_B200_NO_EARLY_WIDE")) side = side_stream(a->device);
+  if (wide && allow_early && blocks == (long long)sms * per_sm && !getenv("C2A_B200_NO_EARLY_WIDE")) side = side_stream(a->device, stream);
   args.stats = g_stats_device == a->device ? g_stats_dev : nullptr;
   args.trace = (g_trace_dev && g_trace_device == a->device && n <= g_trace_n && !step_in) ? g_trace_dev : nullptr;
   CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
@@ -615,26 +621,29 @@ int c2a_b200_contacts_batch(const c2a_b200_model *a, const c2a_b200_model *b, co
   if (a->device != b->device) return fail(C2A_B200_ERR_DEVICE, "models live on different devices");
   if (n == 0) return C2A_B200_OK;
   ON_DEVICE(a->device);
+  cudaStream_t st = thread_stream(a->device);   // stream-ordered: no cudaMalloc / cudaFree, no device-wide synchronisation
+  if (!st) return fail(C2A_B200_ERR_CUDA, "no stream");
   const size_t N = (size_t)n, cbytes = contacts ? N * (size_t)max_contacts * sizeof(c2a_b200_contact) : 0;
   char *arena = nullptr;
   const size_t o_thr = N * 192, o_nc = o_thr + ((N * 8 + 255) & ~(size_t)255), o_cnt = o_nc + ((N * 4 + 255) & ~(size_t)255),
                o_ct = o_cnt + 256, total = o_ct + cbytes;
-  CUDA_TRY(cudaMalloc(&arena, total));
+  CUDA_TRY(pool_malloc(&arena, total, a->device, st));
   int rc = C2A_B200_OK;
   cudaError_t e;
-  if ((e = cudaMemcpy(arena, poses24, N * 192, cudaMemcpyHostToDevice)) != cudaSuccess ||
-      (e = cudaMemcpy(arena + o_thr, threshold, N * 8, cudaMemcpyHostToDevice)) != cudaSuccess)
+  if ((e = cudaMemcpyAsync(arena, poses24, N * 192, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(arena + o_thr, threshold, N * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess)
     rc = fail(C2A_B200_ERR_CUDA, cudaGetErrorString(e));
   if (rc == C2A_B200_OK)
     rc = launch_contacts(a, b, (const double *)arena, (const double *)(arena + o_thr), nullptr, nullptr, nullptr, n, max_contacts,
                          (int *)(arena + o_nc), contacts ? (c2a_b200_contact *)(arena + o_ct) : nullptr,
-                         (unsigned long long *)(arena + o_cnt), 0);
-  if (rc == C2A_B200_OK && (e = cudaDeviceSynchronize()) != cudaSuccess) rc = fail(C2A_B200_ERR_CUDA, cudaGetErrorString(e));
-  if (rc == C2A_B200_OK && num_contact && (e = cudaMemcpy(num_contact, arena + o_nc, N * 4, cudaMemcpyDeviceToHost)) != cudaSuccess)
+                         (unsigned long long *)(arena + o_cnt), st);
+  if (rc == C2A_B200_OK && (e = cudaStreamSynchronize(st)) != cudaSuccess) rc = fail(C2A_B200_ERR_CUDA, cudaGetErrorString(e));
+  if (rc == C2A_B200_OK && num_contact && (e = cudaMemcpyAsync(num_contact, arena + o_nc, N * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
     rc = fail(C2A_B200_ERR_CUDA, cudaGetErrorString(e));
-  if (rc == C2A_B200_OK && contacts && (e = cudaMemcpy(contacts, arena + o_ct, cbytes, cudaMemcpyDeviceToHost)) != cudaSuccess)
+  if (rc == C2A_B200_OK && contacts && (e = cudaMemcpyAsync(contacts, arena + o_ct, cbytes, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
     rc = fail(C2A_B200_ERR_CUDA, cudaGetErrorString(e));
-  cudaFree(arena);
+  cudaStreamSynchronize(st);   // (the copies into the caller's pageable arrays have landed)
+  cudaFreeAsync(arena, st);
   return rc;
 }
 
@@ -652,6 +661,8 @@ static int distance_like(bool gate, const c2a_b200_model *a, const c2a_b200_mode
   if (int rc = check_seeds(seed_a, n, a->n_tris, "seed_a")) return rc;
   if (int rc = check_seeds(seed_b, n, b->n_tris, "seed_b")) return rc;
   ON_DEVICE(a->device);
+  cudaStream_t st = thread_stream(a->device);   // stream-ordered: no cudaMalloc / cudaFree, no device-wide synchronisation
+  if (!st) return fail(C2A_B200_ERR_CUDA, "no stream");
   const size_t N = (size_t)n;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
@@ -659,13 +670,13 @@ static int distance_like(bool gate, const c2a_b200_model *a, const c2a_b200_mode
   const size_t o_pp = p1p2 ? take(N * 48) : 0, o_tp = tri_pair ? take(N * 8) : 0, o_nbv = num_bv_tests ? take(N * 4) : 0;
   const size_t o_ntri = num_tri_tests ? take(N * 4) : 0;
   char *arena = nullptr;
-  CUDA_TRY(cudaMalloc(&arena, off));
+  CUDA_TRY(pool_malloc(&arena, off, a->device, st));
   int rc = C2A_B200_OK;
   cudaError_t e = cudaSuccess;
 #define STEP(x) if (rc == C2A_B200_OK && (e = (x)) != cudaSuccess) rc = fail(C2A_B200_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e));
-  STEP(cudaMemcpy(arena + o_pose, poses24, N * 192, cudaMemcpyHostToDevice));
-  if (seed_a) STEP(cudaMemcpy(arena + o_sa, seed_a, N * 4, cudaMemcpyHostToDevice));
-  if (seed_b) STEP(cudaMemcpy(arena + o_sb, seed_b, N * 4, cudaMemcpyHostToDevice));
+  STEP(cudaMemcpyAsync(arena + o_pose, poses24, N * 192, cudaMemcpyHostToDevice, st));
+  if (seed_a) STEP(cudaMemcpyAsync(arena + o_sa, seed_a, N * 4, cudaMemcpyHostToDevice, st));
+  if (seed_b) STEP(cudaMemcpyAsync(arena + o_sb, seed_b, N * 4, cudaMemcpyHostToDevice, st));
   if (rc == C2A_B200_OK)
   {
     DistanceArgs args;
@@ -695,37 +706,38 @@ static int distance_like(bool gate, const c2a_b200_model *a, const c2a_b200_mode
       long long fit = (long long)(((size_t)1 << 30) / (per_thread * 128));
       if (fit < 1) fit = 1;
       if (blocks > fit) blocks = fit;
-      STEP(cudaMalloc(&qa.arena, (size_t)blocks * 128 * per_thread));
-      if (rc == C2A_B200_OK) c2a_distance_queue_kernel<<<(unsigned)blocks, 128>>>(qa);
+      STEP(pool_malloc(&qa.arena, (size_t)blocks * 128 * per_thread, a->device, st));
+      if (rc == C2A_B200_OK) c2a_distance_queue_kernel<<<(unsigned)blocks, 128, 0, st>>>(qa);
       args.gstack = qa.arena;   // (released below)
     }
     else if (entries <= DIST_STACK)
     {
-      if (gate) c2a_distance_kernel<false, true><<<(unsigned)blocks, 128>>>(args);
-      else c2a_distance_kernel<false, false><<<(unsigned)blocks, 128>>>(args);
+      if (gate) c2a_distance_kernel<false, true><<<(unsigned)blocks, 128, 0, st>>>(args);
+      else c2a_distance_kernel<false, false><<<(unsigned)blocks, 128, 0, st>>>(args);
     }
     else
     {
       if (blocks > 16) blocks = 16;
-      STEP(cudaMalloc(&args.gstack, (size_t)blocks * 128 * entries * DIST_ENTRY * sizeof(double)));
+      STEP(pool_malloc(&args.gstack, (size_t)blocks * 128 * entries * DIST_ENTRY * sizeof(double), a->device, st));
       if (rc == C2A_B200_OK)
       {
-        if (gate) c2a_distance_kernel<true, true><<<(unsigned)blocks, 128>>>(args);
-        else c2a_distance_kernel<true, false><<<(unsigned)blocks, 128>>>(args);
+        if (gate) c2a_distance_kernel<true, true><<<(unsigned)blocks, 128, 0, st>>>(args);
+        else c2a_distance_kernel<true, false><<<(unsigned)blocks, 128, 0, st>>>(args);
       }
     }
     g_launches.fetch_add(1);
     STEP(cudaGetLastError());
-    STEP(cudaDeviceSynchronize());
-    if (args.gstack) cudaFree(args.gstack);
+    STEP(cudaStreamSynchronize(st));
+    if (args.gstack) cudaFreeAsync(args.gstack, st);
   }
-  STEP(cudaMemcpy(distance, arena + o_d, N * 8, cudaMemcpyDeviceToHost));
-  if (p1p2) STEP(cudaMemcpy(p1p2, arena + o_pp, N * 48, cudaMemcpyDeviceToHost));
-  if (tri_pair) STEP(cudaMemcpy(tri_pair, arena + o_tp, N * 8, cudaMemcpyDeviceToHost));
-  if (num_bv_tests) STEP(cudaMemcpy(num_bv_tests, arena + o_nbv, N * 4, cudaMemcpyDeviceToHost));
-  if (num_tri_tests) STEP(cudaMemcpy(num_tri_tests, arena + o_ntri, N * 4, cudaMemcpyDeviceToHost));
+  STEP(cudaMemcpyAsync(distance, arena + o_d, N * 8, cudaMemcpyDeviceToHost, st));
+  if (p1p2) STEP(cudaMemcpyAsync(p1p2, arena + o_pp, N * 48, cudaMemcpyDeviceToHost, st));
+  if (tri_pair) STEP(cudaMemcpyAsync(tri_pair, arena + o_tp, N * 8, cudaMemcpyDeviceToHost, st));
+  if (num_bv_tests) STEP(cudaMemcpyAsync(num_bv_tests, arena + o_nbv, N * 4, cudaMemcpyDeviceToHost, st));
+  if (num_tri_tests) STEP(cudaMemcpyAsync(num_tri_tests, arena + o_ntri, N * 4, cudaMemcpyDeviceToHost, st));
 #undef STEP
-  cudaFree(arena);
+  cudaStreamSynchronize(st);   // (the copies into the caller's pageable arrays have landed)
+  cudaFreeAsync(arena, st);
   return rc;
 }
 
@@ -760,18 +772,20 @@ int c2a_b200_collide_batch(const c2a_b200_model *a, const c2a_b200_model *b, con
   if (!a->obb || !b->obb) return fail(C2A_B200_ERR_ARG, "C2A_Collide needs models uploaded with obb_d / obb_To");
   if (n == 0) return C2A_B200_OK;
   ON_DEVICE(a->device);
+  cudaStream_t st = thread_stream(a->device);   // stream-ordered: no cudaMalloc / cudaFree, no device-wide synchronisation
+  if (!st) return fail(C2A_B200_ERR_CUDA, "no stream");
   const size_t N = (size_t)n;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_pose = take(N * 192), o_np = take(N * 4), o_pairs = max_pairs ? take(N * (size_t)max_pairs * 8) : 0;
   const size_t o_nbv = num_bv_tests ? take(N * 4) : 0, o_ntri = num_tri_tests ? take(N * 4) : 0;
   char *arena = nullptr;
-  CUDA_TRY(cudaMalloc(&arena, off));
+  CUDA_TRY(pool_malloc(&arena, off, a->device, st));
   int rc = C2A_B200_OK;
   cudaError_t e = cudaSuccess;
 #define STEP(x) if (rc == C2A_B200_OK && (e = (x)) != cudaSuccess) rc = fail(C2A_B200_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e));
-  STEP(cudaMemcpy(arena + o_pose, poses24, N * 192, cudaMemcpyHostToDevice));
-  if (max_pairs) STEP(cudaMemset(arena + o_pairs, 0xff, N * (size_t)max_pairs * 8));   // unused entries read -1
+  STEP(cudaMemcpyAsync(arena + o_pose, poses24, N * 192, cudaMemcpyHostToDevice, st));
+  if (max_pairs) STEP(cudaMemsetAsync(arena + o_pairs, 0xff, N * (size_t)max_pairs * 8, st));   // unused entries read -1
   if (rc == C2A_B200_OK)
   {
     CollideArgs args;
@@ -790,24 +804,25 @@ int c2a_b200_collide_batch(const c2a_b200_model *a, const c2a_b200_model *b, con
     if (blocks > need) blocks = need;
     args.gstack = nullptr;
     const int entries = a->depth + b->depth + 2;
-    if (entries <= COLL_STACK) c2a_collide_kernel<false><<<(unsigned)blocks, 128>>>(args);
+    if (entries <= COLL_STACK) c2a_collide_kernel<false><<<(unsigned)blocks, 128, 0, st>>>(args);
     else
     {
       if (blocks > 16) blocks = 16;
-      STEP(cudaMalloc(&args.gstack, (size_t)blocks * 128 * entries * COLL_ENTRY * sizeof(double)));
-      if (rc == C2A_B200_OK) c2a_collide_kernel<true><<<(unsigned)blocks, 128>>>(args);
+      STEP(pool_malloc(&args.gstack, (size_t)blocks * 128 * entries * COLL_ENTRY * sizeof(double), a->device, st));
+      if (rc == C2A_B200_OK) c2a_collide_kernel<true><<<(unsigned)blocks, 128, 0, st>>>(args);
     }
     g_launches.fetch_add(1);
     STEP(cudaGetLastError());
-    STEP(cudaDeviceSynchronize());
-    if (args.gstack) cudaFree(args.gstack);
+    STEP(cudaStreamSynchronize(st));
+    if (args.gstack) cudaFreeAsync(args.gstack, st);
   }
-  STEP(cudaMemcpy(num_pairs, arena + o_np, N * 4, cudaMemcpyDeviceToHost));
-  if (max_pairs) STEP(cudaMemcpy(pairs, arena + o_pairs, N * (size_t)max_pairs * 8, cudaMemcpyDeviceToHost));
-  if (num_bv_tests) STEP(cudaMemcpy(num_bv_tests, arena + o_nbv, N * 4, cudaMemcpyDeviceToHost));
-  if (num_tri_tests) STEP(cudaMemcpy(num_tri_tests, arena + o_ntri, N * 4, cudaMemcpyDeviceToHost));
+  STEP(cudaMemcpyAsync(num_pairs, arena + o_np, N * 4, cudaMemcpyDeviceToHost, st));
+  if (max_pairs) STEP(cudaMemcpyAsync(pairs, arena + o_pairs, N * (size_t)max_pairs * 8, cudaMemcpyDeviceToHost, st));
+  if (num_bv_tests) STEP(cudaMemcpyAsync(num_bv_tests, arena + o_nbv, N * 4, cudaMemcpyDeviceToHost, st));
+  if (num_tri_tests) STEP(cudaMemcpyAsync(num_tri_tests, arena + o_ntri, N * 4, cudaMemcpyDeviceToHost, st));
 #undef STEP
-  cudaFree(arena);
+  cudaStreamSynchronize(st);   // (the copies into the caller's pageable arrays have landed)
+  cudaFreeAsync(arena, st);
   return rc;
 }
 
@@ -922,6 +937,11 @@ HostCtx *host_ctx(int device)  // the caller has made `device` current
 }
 constexpr size_t SMALL_CALL_BYTES = 8u << 20;  // calls whose device arena is smaller take the persistent-arena path
 }  // namespace
+static cudaStream_t thread_stream(int device)
+{
+  HostCtx *c = host_ctx(device);
+  return c ? c->stream : nullptr;
+}
 
 // wall-clock breakdown of the last host-buffer call on this thread (development aid, c2a_b200_testing.h)
 static thread_local double g_host_timing[8];
@@ -1325,7 +1345,7 @@ int c2a_b200_solve_pairs(const c2a_b200_model *const *models, int32_t n_models, 
     rc = launch_batch(models[groups[g] / n_models], models[groups[g] % n_models], (const double *)(arena + o_pose),
                       seed_a ? (const int32_t *)(arena + o_sa) : nullptr, seed_b ? (const int32_t *)(arena + o_sb) : nullptr, ng,
                       tol_d, tol_t, &d, (unsigned long long *)(arena + o_cnt) + g, side[launched % NSIDE], nullptr,
-                      (const int32_t *)(arena + o_order) + start[g]);
+                      (const int32_t *)(arena + o_order) + start[g], /*allow_early=*/false);   // (the groups overlap one another)
     launched++;
   }
   for (int k = 0; k < NSIDE; k++)
@@ -1388,34 +1408,38 @@ int c2a_b200_broadphase(const double *c0, const double *c1, const double *radius
   *n_pairs = 0;
   if (n < 2) return C2A_B200_OK;
   ON_DEVICE(device);
+  cudaStream_t st = thread_stream(device);   // stream-ordered: no cudaMalloc / cudaFree, no device-wide synchronisation
+  if (!st) return fail(C2A_B200_ERR_CUDA, "no stream");
   const size_t N = (size_t)n, o_c1 = N * 24, o_r = 2 * N * 24, o_cnt = o_r + N * 8, o_pairs = o_cnt + 8;
   char *arena = nullptr;
-  CUDA_TRY(cudaMalloc(&arena, o_pairs + (size_t)max_pairs * 8));
+  CUDA_TRY(pool_malloc(&arena, o_pairs + (size_t)max_pairs * 8, device, st));
   int rc = C2A_B200_OK;
   cudaError_t e;
-  if ((e = cudaMemcpy(arena, c0, N * 24, cudaMemcpyHostToDevice)) != cudaSuccess ||
-      (e = cudaMemcpy(arena + o_c1, c1, N * 24, cudaMemcpyHostToDevice)) != cudaSuccess ||
-      (e = cudaMemcpy(arena + o_r, radius, N * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
-      (e = cudaMemset(arena + o_cnt, 0, 8)) != cudaSuccess)
+  if ((e = cudaMemcpyAsync(arena, c0, N * 24, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(arena + o_c1, c1, N * 24, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(arena + o_r, radius, N * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+      (e = cudaMemsetAsync(arena + o_cnt, 0, 8, st)) != cudaSuccess)
     rc = fail(C2A_B200_ERR_CUDA, cudaGetErrorString(e));
   if (rc == C2A_B200_OK)
   {
-    c2a_broadphase_kernel<<<(unsigned)(n - 1), 128>>>((const double *)arena, (const double *)(arena + o_c1), (const double *)(arena + o_r), n,
+    c2a_broadphase_kernel<<<(unsigned)(n - 1), 128, 0, st>>>((const double *)arena, (const double *)(arena + o_c1), (const double *)(arena + o_r), n,
                                                       margin, (int *)(arena + o_pairs), (unsigned long long)max_pairs,
                                                       (unsigned long long *)(arena + o_cnt));
     g_launches.fetch_add(1);
     unsigned long long cnt = 0;
-    if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaMemcpy(&cnt, arena + o_cnt, 8, cudaMemcpyDeviceToHost)) != cudaSuccess)
+    if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaMemcpyAsync(&cnt, arena + o_cnt, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(st)) != cudaSuccess)
       rc = fail(C2A_B200_ERR_CUDA, cudaGetErrorString(e));
     else
     {
       *n_pairs = (int64_t)cnt;
       const size_t w = (size_t)std::min<unsigned long long>(cnt, (unsigned long long)max_pairs);
-      if (w > 0 && (e = cudaMemcpy(pairs, arena + o_pairs, w * 8, cudaMemcpyDeviceToHost)) != cudaSuccess)
+      if (w > 0 && (e = cudaMemcpyAsync(pairs, arena + o_pairs, w * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
         rc = fail(C2A_B200_ERR_CUDA, cudaGetErrorString(e));
     }
   }
-  cudaFree(arena);
+  cudaStreamSynchronize(st);   // (the copies into the caller's pageable arrays have landed)
+  cudaFreeAsync(arena, st);
   return rc;
 }
 
