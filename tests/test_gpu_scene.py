@@ -76,6 +76,24 @@ def test_solve_pairs_single_group_equals_solve_batch(models, golden):
         assert np.array_equal(a[x], g[y][:n]), x
 
 
+def test_solve_pairs_with_thousands_of_model_slots(models, golden):
+    """A scene with many models of which few pairs occur: the grouping lists only the (model A, model B) pairs that have
+    queries (the model table here has 6 000 slots = 36 M possible pairs; three occur)."""
+    import time
+    g = golden("ref_knot_128x16")
+    n = 240
+    m = models("knot_128x16")
+    table = [m] * 6000
+    ma = np.repeat(np.array([0, 5999, 2500], dtype=np.int32), n // 3)
+    mb = np.repeat(np.array([5999, 17, 2500], dtype=np.int32), n // 3)
+    t = time.perf_counter()
+    a = api.solve_pairs(table, ma, mb, g["poses"][:n])
+    dt = time.perf_counter() - t
+    for x, y in FIELDS:
+        assert np.array_equal(a[x], g[y][:n]), x
+    assert dt < 2.0   # (a table of n_models^2 counters would take seconds and 288 MB here)
+
+
 def test_solve_pairs_argument_errors(models):
     m = models("knot_128x16")
     poses = np.zeros((2, 48))
