@@ -14,8 +14,10 @@
  * object code run here: oracle/_ref (the reference's five .cpp compiled verbatim
  * against oracle/pqp_shim) -- bit-exact on every query of the fixtures under
  * tests/golden/ (see oracle/README.md).  Parity at the PQP boundary itself
- * (Meigen, TriDist) is "unpinned" in the sense of SURVEY.md section 8c: PQP is
- * unpinned upstream; TriDist is cross-checked bit-exactly against the
+ * (Meigen, TriDist; for the discrete queries also obb_disjoint, TriContact and
+ * the BVTQ queue's tie order) is "unpinned" in the sense of SURVEY.md section
+ * 8c: PQP is unpinned upstream and absent here, those functions are restated
+ * once in oracle/pqp_shim; TriDist is cross-checked bit-exactly against the
  * reference's in-tree copy (C2A/src/C2A.cpp:165-405).
  *
  * Build: g++ -O2 -ffp-contract=off (no -ffast-math).
