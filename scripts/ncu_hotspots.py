@@ -39,4 +39,4 @@ for key, a in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:top]:
     ss = sorted(((k[6:], v) for k, v in a.items() if k.startswith("stall_") and v > 0), key=lambda kv: -kv[1])[:3]
     tot = sum(v for k, v in a.items() if k.startswith("stall_")) or 1
     print(f"  {key[0]}:{key[1]:<4d} {a['samples'] / S:.3f} {a['inst'] / I:.3f} {a['thr'] / max(a['inst'], 1):5.1f}  "
-          + " ".join(f"{k} {v / tot:.2f}" for k, v in ss) + f"  loc {a['loc']:.0f} | {src[key].strip()[:90]}")
+          + " ".join(f"{k} {v / tot:.2f}" for k, v in ss) + f"  loc {a['loc']:.0f} | {src.get(key, "").strip()[:90]}")
