@@ -221,6 +221,15 @@ __device__ __noinline__ void motion_pose_nl(const double *rec, double t, double 
   motion_pose(m, t, R, T);
 }
 
+// The phase counters / per-query timeline (c2a_b200_phase_stats, c2a_b200_query_trace: development aids) are compiled out
+// of the product build: merely being there (a clock read and a few predicated atomics per pass, two registers, 2 KB of
+// code) cost the kernel 6 % (1 M queries: 7.35 s -> 6.90 s).  scripts/build_variant.py <name> -DC2A_SOLVE_STATS=1 makes a
+// library with them (scripts/phase_stats.py, wide_stats.py, tail_stats.py, query_trace.py read them).
+#ifndef C2A_SOLVE_STATS
+#define C2A_SOLVE_STATS 0
+#endif
+#define SOLVE_STATS_PTR (C2A_SOLVE_STATS ? args.stats : (unsigned long long *)nullptr)
+#define SOLVE_TRACE_PTR (C2A_SOLVE_STATS ? args.trace : (unsigned long long *)nullptr)
 __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(const BatchArgs args)
 {
   extern __shared__ double smem[];
@@ -236,7 +245,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
 #define SD(f, s) sd[(f) * Q + (s)]
 #define SI(f, s) si[(f) * Q + (s)]
 
-  if (args.stats && threadIdx.x == 0) atomicMin(args.stats + 6, global_ns());  // launch start
+  if (SOLVE_STATS_PTR && threadIdx.x == 0) atomicMin(SOLVE_STATS_PTR + 6, global_ns());  // launch start
   for (int sl = lane; sl < Q; sl += 32)
   {
     SI(I_STATE, sl) = sl < args.max_slots ? ST_ADVANCE : ST_EXIT;
@@ -266,13 +275,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
     else phase = ST_TRAVERSE;
 
     const bool steady = n_live == args.max_slots && n_live == Q;  // statistics cover warps whose slots are all live (not the tail)
-    if (args.stats && lane == 0 && steady)
+    if (SOLVE_STATS_PTR && lane == 0 && steady)
     {
       const int k = phase == ST_TRAVERSE ? 0 : (phase == ST_LEAF ? 2 : 4);
-      atomicAdd(args.stats + k, 1ull);
-      atomicAdd(args.stats + k + 1, (unsigned long long)(phase == ST_TRAVERSE ? (nT >= 5 ? 2 * min(nT, 16) : (nT >= 3 ? 6 * nT : (nT == 2 ? 28 : 30))) : (phase == ST_LEAF ? nL : nA)));  // LEAF: slots served (9 lanes each, 3 per round)
+      atomicAdd(SOLVE_STATS_PTR + k, 1ull);
+      atomicAdd(SOLVE_STATS_PTR + k + 1, (unsigned long long)(phase == ST_TRAVERSE ? (nT >= 5 ? 2 * min(nT, 16) : (nT >= 3 ? 6 * nT : (nT == 2 ? 28 : 30))) : (phase == ST_LEAF ? nL : nA)));  // LEAF: slots served (9 lanes each, 3 per round)
     }
-    const long long pass_t0 = args.stats ? clock64() : 0;
+    const long long pass_t0 = SOLVE_STATS_PTR ? clock64() : 0;
     if (phase == ST_TRAVERSE)
     {
       // -------------------------------------------------------------------- EXPAND ----------
@@ -557,7 +566,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
             }
             if (t == 0)
             {
-              if (args.stats && G == 32) { atomicAdd(args.stats + 9, 1ull); atomicAdd(args.stats + 10, (unsigned long long)levels); }
+              if (SOLVE_STATS_PTR && G == 32) { atomicAdd(SOLVE_STATS_PTR + 9, 1ull); atomicAdd(SOLVE_STATS_PTR + 10, (unsigned long long)levels); }
               SD(F_MINT, slot) = mint;
               SI(I_SP, slot) = sp;
               SI(I_NBV, slot) = SI(I_NBV, slot) + 2 * levels;
@@ -713,7 +722,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
             if (o.distance) o.distance[q] = dist;
             if (o.mint) o.mint[q] = mint;
             if (o.last_tri) { o.last_tri[2 * q] = SI(I_LASTA, slot); o.last_tri[2 * q + 1] = SI(I_LASTB, slot); }
-            if (args.trace) args.trace[2 * q + 1] = global_ns();
+            if (SOLVE_TRACE_PTR) SOLVE_TRACE_PTR[2 * q + 1] = global_ns();
             q = -1;
           }
         }
@@ -749,12 +758,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
           if (nq >= args.n)
           {
             SI(I_STATE, slot) = ST_EXIT;
-            if (args.stats) { atomicMin(args.stats + 7, global_ns()); atomicMax(args.stats + 8, global_ns()); }  // batch drained / last slot retired
+            if (SOLVE_STATS_PTR) { atomicMin(SOLVE_STATS_PTR + 7, global_ns()); atomicMax(SOLVE_STATS_PTR + 8, global_ns()); }  // batch drained / last slot retired
           }
           else
           {
             q = args.order ? (long long)__ldg(args.order + nq) : nq;
-            if (args.trace) args.trace[2 * q] = global_ns();
+            if (SOLVE_TRACE_PTR) SOLVE_TRACE_PTR[2 * q] = global_ns();
             const double *rec = args.motions + (size_t)(2 * MOTION_DOUBLES) * q;
             const double w1 = __ldg(rec + 18), w2 = __ldg(rec + MOTION_DOUBLES + 18);
             if (!args.step_in && w1 < 1e-8 && w2 < 1e-8)
@@ -856,12 +865,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, C2A_MINB) c2a_solve_kernel(cons
       }
     }
     __syncwarp();
-    if (args.stats && lane == 0 && steady) atomicAdd(args.stats + 11 + (phase == ST_TRAVERSE ? 0 : (phase == ST_LEAF ? 1 : 2)), (unsigned long long)(clock64() - pass_t0));
-    if (args.stats && lane == 0 && n_live == 1)
+    if (SOLVE_STATS_PTR && lane == 0 && steady) atomicAdd(SOLVE_STATS_PTR + 11 + (phase == ST_TRAVERSE ? 0 : (phase == ST_LEAF ? 1 : 2)), (unsigned long long)(clock64() - pass_t0));
+    if (SOLVE_STATS_PTR && lane == 0 && n_live == 1)
     {
       // a query alone on its warp (the tail of a launch, or a single-query call): passes and cycles per phase
       const int k = 14 + 2 * (phase == ST_TRAVERSE ? 0 : (phase == ST_LEAF ? 1 : 2));
-      atomicAdd(args.stats + k, 1ull); atomicAdd(args.stats + k + 1, (unsigned long long)(clock64() - pass_t0));
+      atomicAdd(SOLVE_STATS_PTR + k, 1ull); atomicAdd(SOLVE_STATS_PTR + k + 1, (unsigned long long)(clock64() - pass_t0));
     }
   }
   // this warp hands nothing over any more (its records are complete: fence before the count)

@@ -29,7 +29,8 @@ int c2a_b200_test_motion(const double *rec, const double *t, const double *ang_r
 int c2a_b200_test_sincos(const double *x, int64_t n, double *s, double *c);
 int c2a_b200_host_sincos(const double *x, int64_t n, double *s, double *c);
 
-/* Phase statistics of the solve kernel (development aid): see c2a_kernels.cu. */
+/* Phase statistics of the solve kernel (development aid): see c2a_kernels.cu.  The counters are compiled out of the product
+ * build (they cost 6 %): all zeros unless the library was built with -DC2A_SOLVE_STATS=1 (scripts/build_variant.py). */
 int c2a_b200_phase_stats(int32_t enable, uint64_t *out20);
 
 /* Durations (ms) of the three kernels of the calling thread's last batch launch (CUDA events on its stream). */

@@ -1,4 +1,5 @@
-"""Phase fill statistics of the solve kernel on a bounded knot batch (development aid)."""
+"""Phase fill statistics of the solve kernel on a bounded knot batch (development aid).
+Needs a library built with the solve kernel's counters: python scripts/build_variant.py stats -DC2A_SOLVE_STATS=1 -DC2A_WIDE_STATS=1, then C2A_B200_LIB=$PWD/variants/stats.so (the product build has them compiled out: they cost 6 %)."""
 import ctypes as C, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

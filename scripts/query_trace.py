@@ -1,5 +1,6 @@
 """Per-query timeline of one batch (development aid): when each query was claimed and finished, against its cost.
-Usage: python scripts/query_trace.py [n]   (env C2A_B200_PRIO=heavy,lead to vary the in-warp priority)"""
+Usage: python scripts/query_trace.py [n]   (env C2A_B200_PRIO=heavy,lead to vary the in-warp priority)
+Needs a library built with the solve kernel's counters: python scripts/build_variant.py stats -DC2A_SOLVE_STATS=1 -DC2A_WIDE_STATS=1, then C2A_B200_LIB=$PWD/variants/stats.so (the product build has them compiled out: they cost 6 %)."""
 import ctypes as C, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,5 +1,6 @@
 """Timeline and counters of c2a_solve_kernel + c2a_wide_kernel on knot batches of several sizes (development aid).
-Usage: python scripts/wide_stats.py [n ...]   (env: C2A_B200_NO_WIDE, C2A_B200_SPILL_LIVE, C2A_B200_WIDE_WINDOW, CHECK=k)"""
+Usage: python scripts/wide_stats.py [n ...]   (env: C2A_B200_NO_WIDE, C2A_B200_SPILL_LIVE, C2A_B200_WIDE_WINDOW, CHECK=k)
+Needs a library built with the solve kernel's counters: python scripts/build_variant.py stats -DC2A_SOLVE_STATS=1 -DC2A_WIDE_STATS=1, then C2A_B200_LIB=$PWD/variants/stats.so (the product build has them compiled out: they cost 6 %)."""
 import ctypes as C, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
