@@ -316,6 +316,55 @@ def test_edge_cases(models):
         api._check(api.lib().c2a_b200_solve_batch(m.h, None, None, None, None, C.c_int64(1), C.c_double(1e-4), C.c_double(1e-4), None))
 
 
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_random_small_meshes_every_entry_against_port(seed):
+    """Random triangle soups of 1 .. 40 triangles (hierarchies of depth 0 .. ~8, root-leaf pairs, slivers, one model much
+    larger than the other): the CCD query (both branches), the contact pass, both distance routines and both C2A_Collide
+    overloads against the oracle port, bit for bit."""
+    rng = np.random.default_rng(seed)
+    P = oracle.port()
+    for trial in range(6):
+        na, nb = int(rng.integers(1, 41)), int(rng.integers(1, 41))
+        scale_b = float(rng.choice([0.2, 1.0, 5.0]))
+        ta = rng.normal(size=(na, 3, 3)) + rng.normal(scale=2.0, size=(na, 1, 3))
+        tb = (rng.normal(size=(nb, 3, 3)) + rng.normal(scale=2.0, size=(nb, 1, 3))) * scale_b
+        if trial % 3 == 0:
+            ta[0, 2] = ta[0, 1] + 1e-9 * (ta[0, 1] - ta[0, 0])   # a sliver
+        ba, bb = api.build_bvh(ta.reshape(na, 9)), api.build_bvh(tb.reshape(nb, 9))
+        ma, mb = api.Model(ba, 0), api.Model(bb, 0)
+        rad = max(float(np.linalg.norm(ba["tris"].reshape(-1, 3), axis=1).max()), float(np.linalg.norm(bb["tris"].reshape(-1, 3), axis=1).max()))
+        poses = workloads.approach_batch(64, seed * 100 + trial, radius=rad)
+        tp = workloads.translation_batch(24, seed * 100 + trial, radius=rad, move_b=True)
+        sa = rng.integers(0, na, 64).astype(np.int32); sb = rng.integers(0, nb, 64).astype(np.int32)
+        ref = P.solve_batch(ba, bb, poses, sa, sb, threads=4)
+        got = api.solve_batch(ma, mb, poses, sa, sb)
+        for a, b in FIELDS:
+            assert np.array_equal(got[a], ref[b]), (seed, trial, a)
+        ref = P.solve_batch(ba, bb, tp, threads=1)
+        got = api.solve_batch(ma, mb, tp)
+        for a, b in FIELDS:
+            assert np.array_equal(got[a], ref[b]), (seed, trial, "translation", a)
+        sp = workloads.static_pose_batch(48, seed * 100 + trial, radius=rad)
+        for qs in (2, 4):
+            rd = P.distance(ba, bb, sp, sa[:48], sb[:48], qsize=qs); gd = api.distance_batch(ma, mb, sp, sa[:48], sb[:48], qsize=qs)
+            assert np.array_equal(gd["distance"], rd["distance"]) and np.array_equal(gd["num_bv_tests"], rd["num_bv_tests"]), (seed, trial, qs)
+            assert np.array_equal(gd["tri_pair"], np.stack([rd["tri_a"], rd["tri_b"]], 1)), (seed, trial, qs)
+        rn, rp, rbv, rtr = P.collide(ba, bb, sp, max_pairs=2048); gc = api.collide_batch(ma, mb, sp, max_pairs=2048)
+        assert np.array_equal(gc["num_pairs"], rn) and np.array_equal(gc["num_bv_tests"], rbv) and np.array_equal(gc["num_tri_tests"], rtr), (seed, trial)
+        for i in range(len(sp)):
+            assert np.array_equal(gc["pairs"][i, :rn[i]], rp[i]), (seed, trial, i)
+        rd = P.collide_distance(ba, bb, sp, sa[:48], sb[:48]); gd = api.collide_distance_batch(ma, mb, sp, sa[:48], sb[:48])
+        assert np.array_equal(gd["distance"], rd["distance"]) and np.array_equal(gd["num_tri_tests"], rd["num_tri_tests"]), (seed, trial)
+        thr = np.full(len(sp), 0.3 * rad)
+        num, recs = api.contacts_batch(ma, mb, sp, thr, max_contacts=32)
+        for i in range(0, len(sp), 6):
+            n_ref, r_ref = P.contacts(ba, bb, sp[i, :12], sp[i, 12:], thr[i], max_out=32)
+            assert num[i] == n_ref, (seed, trial, i)
+            k = min(n_ref, 32)
+            assert np.array_equal(recs[i][:k]["dist"], r_ref["dist"][:k]) and np.array_equal(recs[i][:k]["tri_a"], r_ref["tri_a"][:k]), (seed, trial, i)
+        ma.free(); mb.free()
+
+
 def test_large_batch_properties(models):
     """At a size the CPU oracle cannot check query by query: size-independent properties.
     (i) the dynamic scheduler is order independent: a permuted batch gives the permuted results;
